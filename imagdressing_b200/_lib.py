@@ -1,0 +1,115 @@
+"""ctypes binding of libimagd_b200.so (the C ABI declared in include/imagd_b200.h).
+
+The library is the product: there is no CPU or PyTorch fallback. Importing this module never needs a GPU (the
+build check and the symbol test run on a CPU box); calling a kernel without the library or without a B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libimagd_b200.so")
+
+IMAGD_OK = 0
+ACT_NONE, ACT_GEGLU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
+
+
+class Epilogue(Structure):
+    """struct imagd_epilogue (include/imagd_b200.h)."""
+
+    _fields_ = [
+        ("bias", c_void_p),
+        ("rowvec", c_void_p),
+        ("rowvec_ld", c_int64),
+        ("rows_per_group", c_int32),
+        ("act", c_int32),
+        ("residual", c_void_p),
+        ("ldr", c_int64),
+        ("alpha", c_float),
+        ("out_fp32", c_int32),
+    ]
+
+
+class KVStream(Structure):
+    """struct imagd_kv_stream (include/imagd_b200.h)."""
+
+    _fields_ = [
+        ("k", c_void_p),
+        ("v", c_void_p),
+        ("ld", c_int64),
+        ("len", c_int32),
+        ("broadcast", c_int32),
+        ("n_query_samples", c_int32),
+        ("out_scale", c_float),
+    ]
+
+
+# name -> (restype, argtypes); mirrors include/imagd_b200.h one to one (tests/test_abi.py checks the header).
+SIGNATURES = {
+    "imagd_version": (c_int, []),
+    "imagd_last_error": (c_char_p, []),
+    "imagd_device_check": (c_int, []),
+    "imagd_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
+                                POINTER(Epilogue), c_void_p]),
+    "imagd_conv3x3_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_int,
+                                   POINTER(Epilogue), c_void_p]),
+    "imagd_attention_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int,
+                                     POINTER(KVStream), POINTER(KVStream), c_float, c_void_p]),
+    "imagd_groupnorm_ws_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
+    "imagd_groupnorm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p,
+                                     c_void_p, c_float, c_int, c_void_p, c_void_p]),
+    "imagd_layernorm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_float,
+                                     c_void_p]),
+    "imagd_concat_add_bf16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p,
+                                      c_int64, c_void_p, c_int64, c_int64, c_void_p]),
+    "imagd_upsample2x_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "imagd_im2col3x3_s2_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "imagd_conv3x3_direct_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                          c_int, c_int, c_int, c_void_p, c_void_p]),
+    "imagd_nchw_f32_to_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "imagd_timestep_embedding": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "imagd_linear_small_m": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                     c_int, c_int, c_int, c_void_p]),
+    "imagd_cfg_ddim_step": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+
+
+class ImagdError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the in-tree library and attach signatures. Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImagdError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C imagdressing_b200/csrc`). There is no fallback path."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == ABI drift, fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != IMAGD_OK:
+        msg = load().imagd_last_error()
+        raise ImagdError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def require_b200() -> None:
+    rc = load().imagd_device_check()
+    if rc < 0:
+        msg = load().imagd_last_error()
+        raise ImagdError(f"imagd_b200 needs an sm_100 GPU: {msg.decode() if msg else rc}")

@@ -1,0 +1,383 @@
+// Two-stream ("hybrid") FlashAttention-style kernel on tcgen05 for sm_100a.
+//
+//   out = w0 * softmax(Q K0^T * s) V0  +  w1 * softmax(Q K1^T * s) V1
+//
+// The two softmaxes are independent (separate running max / sum and separate O accumulators) but share one
+// resident Q tile, exactly the arithmetic of RefSAttnProcessor2_0 (reference adapter/attention_processor.py:
+// 589-612: self SDPA, garment SDPA on the same query, scale-add) and of LoRAIPAttnProcessor2_0's text + IP
+// pair (:833-856). With w1 unused it is plain SDPA (cross-attention, the garment UNet's cached self-attention,
+// the Perceiver resampler).
+//
+// Data layout: Q/K/V stay in the projection GEMM's natural token-major output [rows, ld] (heads side by side in
+// the channel dim). TMA views them as (d, head, token, sample) and loads a 64-wide box per head; for
+// head_dim 40 / 80 / 160 the box over-runs the d extent and the hardware zero-fills, so no padded copies exist
+// in HBM and the MMA K extent is the head dim rounded to 16 (48 / 80 / 160).
+//
+// CTA = 128 queries of one (sample, head). 192 threads:
+//   warps 0-3  softmax: one query row per thread (TMEM lane = row); S read with tcgen05.ld, P written to smem
+//              in the UMMA K-major 128B-swizzle layout, O rescaled in TMEM only when the running max moves
+//   warp 4     TMA producer (K/V ring)
+//   warp 5     TMEM allocator + tcgen05.mma issuer:  S = Q K^T  (128x128xhd),  O_s += P V (128xhdx128)
+// TMEM columns: S [0,128), O_0 [128, +O_STRIDE), O_1 after it.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace imagd {
+
+struct AttnParams {
+    int B, Lq, heads, hd;
+    float scale_log2;  // sm_scale * log2(e)
+    int len[2];
+    int nq[2];       // stream s applies to samples [0, nq[s])
+    int bcast[2];
+    float oscale[2];
+    void* out;
+    int64_t out_ld;
+};
+
+constexpr int kAtomBytes = 128 * 128;  // one [128 rows x 64 bf16] swizzled tile
+
+template <int HD_MMA, int NATOM, int KV_STAGES>
+struct AttnCfg {
+    static constexpr int kOStride = (HD_MMA + 63) / 64 * 64;
+    static constexpr int kTmemNeed = 128 + 2 * kOStride;
+    static constexpr int kTmemCols = kTmemNeed <= 256 ? 256 : 512;
+    static constexpr int kQBytes = NATOM * kAtomBytes;
+    static constexpr int kKOff = kQBytes;
+    static constexpr int kVOff = kKOff + KV_STAGES * NATOM * kAtomBytes;
+    static constexpr int kPOff = kVOff + KV_STAGES * NATOM * kAtomBytes;
+    static constexpr int kBarOff = kPOff + 2 * kAtomBytes;
+    static constexpr int kNumBars = 1 + 3 * KV_STAGES + 3;
+    static constexpr int kTotal = kBarOff + kNumBars * 8 + 16;
+};
+
+template <int HD_MMA, int NATOM, int KV_STAGES>
+__global__ void __launch_bounds__(192, (AttnCfg<HD_MMA, NATOM, KV_STAGES>::kTmemCols <= 256 &&
+                                        AttnCfg<HD_MMA, NATOM, KV_STAGES>::kTotal <= 112 * 1024 + 512) ? 2 : 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
+                    const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
+                    const __grid_constant__ CUtensorMap tmV1, const AttnParams p) {
+    using C = AttnCfg<HD_MMA, NATOM, KV_STAGES>;
+    extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+        printf("imagd: dynamic shared memory base %u is not 1024-byte aligned\n", smem_u32(smem));
+        __trap();
+    }
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + C::kKOff;
+    uint8_t* sV = smem + C::kVOff;
+    uint8_t* sP = smem + C::kPOff;
+    uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
+    uint64_t* k_full = q_full + 1;
+    uint64_t* v_full = k_full + KV_STAGES;
+    uint64_t* kv_empty = v_full + KV_STAGES;
+    uint64_t* s_full = kv_empty + KV_STAGES;
+    uint64_t* p_full = s_full + 1;
+    uint64_t* o_full = p_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128;
+    const int h = blockIdx.y;
+    const int b = blockIdx.z;
+
+    const int nb0 = (p.len[0] + 127) / 128;
+    const int nb1 = (b < p.nq[1]) ? (p.len[1] + 127) / 128 : 0;
+    const int T = nb0 + nb1;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK0);
+        tma_prefetch_desc(&tmV0);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < KV_STAGES; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 128);
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 5) {
+        tmem_alloc(tmem_slot, C::kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base;
+    const uint32_t tmem_O = tmem_base + 128;
+
+    if (warp == 4) {
+        // ------------------------------------------------ TMA producer
+        if (elect_one()) {
+            mbar_arrive_expect_tx(q_full, C::kQBytes);
+#pragma unroll
+            for (int a = 0; a < NATOM; ++a) tma_load_4d(sQ + a * kAtomBytes, &tmQ, q_full, a * 64, h, q0, b);
+            for (int i = 0; i < T; ++i) {
+                const int s = i < nb0 ? 0 : 1;
+                const int j = s ? i - nb0 : i;
+                const int st = i % KV_STAGES;
+                const uint32_t ph = (i / KV_STAGES) & 1;
+                const CUtensorMap* mk = s ? &tmK1 : &tmK0;
+                const CUtensorMap* mv = s ? &tmV1 : &tmV0;
+                const int bk = p.bcast[s] ? 0 : b;
+                mbar_wait(&kv_empty[st], ph ^ 1);
+                mbar_arrive_expect_tx(&k_full[st], NATOM * kAtomBytes);
+#pragma unroll
+                for (int a = 0; a < NATOM; ++a)
+                    tma_load_4d(sK + (st * NATOM + a) * kAtomBytes, mk, &k_full[st], a * 64, h, j * 128, bk);
+                mbar_arrive_expect_tx(&v_full[st], NATOM * kAtomBytes);
+#pragma unroll
+                for (int a = 0; a < NATOM; ++a)
+                    tma_load_4d(sV + (st * NATOM + a) * kAtomBytes, mv, &v_full[st], a * 64, h, j * 128, bk);
+            }
+        }
+    } else if (warp == 5) {
+        // ------------------------------------------------ MMA issuer
+        if (elect_one()) {
+            constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);     // Q (K-major) x K (K-major)
+            constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD_MMA, 0, 1);  // P (K-major) x V (MN-major)
+            mbar_wait(q_full, 0);
+            for (int i = 0; i < T; ++i) {
+                const int s = i < nb0 ? 0 : 1;
+                const int j = s ? i - nb0 : i;
+                const int st = i % KV_STAGES;
+                const uint32_t ph = (i / KV_STAGES) & 1;
+                mbar_wait(&k_full[st], ph);
+                tc_fence_after();
+                const uint32_t q_addr = smem_u32(sQ);
+                const uint32_t k_addr = smem_u32(sK + st * NATOM * kAtomBytes);
+#pragma unroll
+                for (int ks = 0; ks < HD_MMA / 16; ++ks) {
+                    const uint32_t off = (ks / 4) * kAtomBytes + (ks % 4) * 32;
+                    umma_bf16(tmem_S, umma_smem_desc_sw128(q_addr + off, 16, 1024),
+                              umma_smem_desc_sw128(k_addr + off, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
+                }
+                umma_commit(s_full);
+                mbar_wait(p_full, i & 1);
+                mbar_wait(&v_full[st], ph);
+                tc_fence_after();
+                const uint32_t p_addr = smem_u32(sP);
+                const uint32_t v_addr = smem_u32(sV + st * NATOM * kAtomBytes);
+                const uint32_t o_addr = tmem_O + s * C::kOStride;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t poff = (ks / 4) * kAtomBytes + (ks % 4) * 32;
+                    umma_bf16(o_addr, umma_smem_desc_sw128(p_addr + poff, 16, 1024),
+                              umma_smem_desc_sw128(v_addr + ks * 2048, kAtomBytes, 1024), idesc_o,
+                              (j > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(&kv_empty[st]);
+            }
+            umma_commit(o_full);
+        }
+    } else {
+        // ------------------------------------------------ softmax / correction / epilogue (warps 0-3)
+        const int r = warp * 32 + lane;  // query row in tile == TMEM lane
+        const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+        float m_run = -INFINITY, l_run = 0.f, l_first = 1.f;
+        const uint32_t p_row = smem_u32(sP) + (r >> 3) * 1024 + (r & 7) * 128;
+        const uint32_t rx = r & 7;
+
+        for (int i = 0; i < T; ++i) {
+            const int s = i < nb0 ? 0 : 1;
+            const int j = s ? i - nb0 : i;
+            if (j == 0 && i > 0) {
+                l_first = l_run;
+                m_run = -INFINITY;
+                l_run = 0.f;
+            }
+            const int valid = min(128, p.len[s] - j * 128);
+            mbar_wait(s_full, i & 1);
+            tc_fence_after();
+
+            // pass 1: row max
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 128; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_S + lane_addr + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    if (c + k < valid) mx = fmaxf(mx, __uint_as_float(v[k]));
+            }
+            const float m_new = fmaxf(m_run, mx * p.scale_log2);
+            const float alpha = exp2f(m_run - m_new);  // 0 on the first block of a stream
+            if (j > 0 && __any_sync(0xffffffffu, m_new > m_run)) {
+                // rescale this stream's O accumulator in TMEM
+                const uint32_t o_addr = tmem_O + s * C::kOStride + lane_addr;
+#pragma unroll 1
+                for (int c = 0; c < HD_MMA; c += 16) {
+                    uint32_t o[16];
+                    tmem_ld16(o_addr + c, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+                    tmem_st16(o_addr + c, o);
+                }
+                tmem_st_wait();
+            }
+            m_run = m_new;
+
+            // pass 2: P = exp2(S*scale - m), row sum, write P (bf16) into the swizzled K-major smem tile
+            float sum = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 128; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_S + lane_addr + c, v);
+                tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int k = 0; k < 32; k += 2) {
+                    float e0 = (c + k < valid) ? exp2f(__uint_as_float(v[k]) * p.scale_log2 - m_new) : 0.f;
+                    float e1 = (c + k + 1 < valid) ? exp2f(__uint_as_float(v[k + 1]) * p.scale_log2 - m_new) : 0.f;
+                    sum += e0 + e1;
+                    pk[k / 2] = pack_bf16x2(e0, e1);
+                }
+                // 32 columns = 4 x 16-byte chunks; chunk index within the 64-wide atom: (c % 64) / 8 + q
+                const uint32_t atom_base = p_row + (c / 64) * kAtomBytes;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t chunk = ((c % 64) / 8 + q) ^ rx;
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(atom_base + chunk * 16),
+                                 "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                                 : "memory");
+                }
+            }
+            l_run = l_run * alpha + sum;
+
+            fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor core (async proxy)
+            tc_fence_before();
+            mbar_arrive(p_full);
+        }
+
+        // ---- epilogue: out = w0 * O0 / l0 + w1 * O1 / l1
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        float w0, w1 = 0.f;
+        if (nb1 > 0) {
+            w0 = p.oscale[0] / l_first;
+            w1 = p.oscale[1] / l_run;
+        } else {
+            w0 = p.oscale[0] / l_run;
+        }
+        const int q = q0 + r;
+        __nv_bfloat16* orow =
+            reinterpret_cast<__nv_bfloat16*>(p.out) + (static_cast<int64_t>(b) * p.Lq + q) * p.out_ld + h * p.hd;
+#pragma unroll 1
+        for (int c = 0; c < HD_MMA; c += 16) {
+            uint32_t o0[16], o1[16];
+            tmem_ld16(tmem_O + lane_addr + c, o0);
+            if (nb1 > 0) tmem_ld16(tmem_O + C::kOStride + lane_addr + c, o1);
+            tmem_ld_wait();
+            if (q < p.Lq && c < p.hd) {
+                float f[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    f[k] = w0 * __uint_as_float(o0[k]);
+                    if (nb1 > 0) f[k] += w1 * __uint_as_float(o1[k]);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(orow + c);
+                dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                    pack_bf16x2(f[6], f[7]));
+                if (c + 8 < p.hd)
+                    dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                                        pack_bf16x2(f[14], f[15]));
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+
+static int make_head_tmap(CUtensorMap* tm, const void* base, int64_t ld, int hd, int heads, int len, int nsamples) {
+    uint64_t dims[4] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(heads), static_cast<uint64_t>(len),
+                        static_cast<uint64_t>(nsamples)};
+    uint64_t strides[3] = {static_cast<uint64_t>(hd) * 2, static_cast<uint64_t>(ld) * 2,
+                           static_cast<uint64_t>(ld) * 2 * len};
+    uint32_t box[4] = {64, 1, 128, 1};
+    return make_tmap_bf16(tm, base, 4, dims, strides, box);
+}
+
+template <int HD_MMA, int NATOM, int KV_STAGES>
+static int launch_attn(const CUtensorMap* tms, const AttnParams& p, cudaStream_t stream) {
+    using C = AttnCfg<HD_MMA, NATOM, KV_STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        IMAGD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<HD_MMA, NATOM, KV_STAGES>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
+        attr_set = true;
+    }
+    dim3 grid((p.Lq + 127) / 128, p.heads, p.B);
+    attention_tc_kernel<HD_MMA, NATOM, KV_STAGES><<<grid, 192, C::kTotal, stream>>>(tms[0], tms[1], tms[2], tms[3],
+                                                                                   tms[4], p);
+    IMAGD_LAUNCH_CHECK("attention_tc_kernel");
+    return IMAGD_OK;
+}
+
+}  // namespace imagd
+
+extern "C" int imagd_attention_bf16(const void* q, int64_t q_ld, void* out, int64_t out_ld, int B, int Lq, int heads,
+                                    int head_dim, const imagd_kv_stream* s0, const imagd_kv_stream* s1, float sm_scale,
+                                    imagd_stream stream) {
+    using namespace imagd;
+    IMAGD_CHECK_ARG(q && out && s0 && s0->k && s0->v, "attention: null pointer");
+    IMAGD_CHECK_ARG(B > 0 && Lq > 0 && heads > 0, "attention: bad shape");
+    IMAGD_CHECK_ARG(head_dim == 40 || head_dim == 64 || head_dim == 80 || head_dim == 160,
+                    "attention: head_dim %d not in {40, 64, 80, 160}", head_dim);
+    IMAGD_CHECK_ARG(s0->len > 0 && s0->n_query_samples >= B, "attention: stream 0 must cover every query sample");
+    IMAGD_CHECK_ARG(out_ld % 8 == 0 && aligned16(out), "attention: output alignment");
+    const bool has1 = s1 != nullptr && s1->k != nullptr && s1->len > 0 && s1->n_query_samples > 0;
+
+    AttnParams p;
+    p.B = B;
+    p.Lq = Lq;
+    p.heads = heads;
+    p.hd = head_dim;
+    p.scale_log2 = sm_scale * 1.4426950408889634f;
+    p.len[0] = s0->len;
+    p.nq[0] = B;
+    p.bcast[0] = s0->broadcast;
+    p.oscale[0] = s0->out_scale;
+    p.len[1] = has1 ? s1->len : 0;
+    p.nq[1] = has1 ? (s1->n_query_samples < B ? s1->n_query_samples : B) : 0;
+    p.bcast[1] = has1 ? s1->broadcast : 0;
+    p.oscale[1] = has1 ? s1->out_scale : 0.f;
+    p.out = out;
+    p.out_ld = out_ld;
+
+    CUtensorMap tms[5];
+    int rc = make_head_tmap(&tms[0], q, q_ld, head_dim, heads, Lq, B);
+    if (rc != IMAGD_OK) return rc;
+    rc = make_head_tmap(&tms[1], s0->k, s0->ld, head_dim, heads, s0->len, s0->broadcast ? 1 : B);
+    if (rc != IMAGD_OK) return rc;
+    rc = make_head_tmap(&tms[2], s0->v, s0->ld, head_dim, heads, s0->len, s0->broadcast ? 1 : B);
+    if (rc != IMAGD_OK) return rc;
+    if (has1) {
+        const int ns = s1->broadcast ? 1 : p.nq[1];
+        rc = make_head_tmap(&tms[3], s1->k, s1->ld, head_dim, heads, s1->len, ns);
+        if (rc != IMAGD_OK) return rc;
+        rc = make_head_tmap(&tms[4], s1->v, s1->ld, head_dim, heads, s1->len, ns);
+        if (rc != IMAGD_OK) return rc;
+    } else {
+        tms[3] = tms[1];
+        tms[4] = tms[2];
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (head_dim) {
+        case 40: return launch_attn<48, 1, 2>(tms, p, st);
+        case 64: return launch_attn<64, 1, 2>(tms, p, st);
+        case 80: return launch_attn<80, 2, 2>(tms, p, st);
+        default: return launch_attn<160, 3, 1>(tms, p, st);
+    }
+}

@@ -1,0 +1,43 @@
+// Host-side helpers shared by the C-ABI translation units: error recording, TMA descriptor encoding.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/imagd_b200.h"
+
+namespace imagd {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define IMAGD_CHECK_ARG(cond, ...)     \
+    do {                               \
+        if (!(cond)) {                 \
+            ::imagd::set_error(__VA_ARGS__); \
+            return IMAGD_ERR_ARG;      \
+        }                              \
+    } while (0)
+
+#define IMAGD_CUDA(call)                                   \
+    do {                                                   \
+        cudaError_t e__ = (call);                          \
+        if (e__ != cudaSuccess) return ::imagd::cuda_fail(e__, #call); \
+    } while (0)
+
+#define IMAGD_LAUNCH_CHECK(name)                               \
+    do {                                                       \
+        cudaError_t e__ = cudaGetLastError();                  \
+        if (e__ != cudaSuccess) return ::imagd::cuda_fail(e__, name);  \
+    } while (0)
+
+// Encode a tiled bf16 TMA descriptor (SWIZZLE_128B, OOB zero fill). dims/strides innermost first;
+// strides_bytes has rank-1 entries (stride of dim 1..rank-1). Returns IMAGD_OK or an error code.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace imagd

@@ -1,0 +1,410 @@
+// HBM-/latency-bound glue kernels of the denoising step: skip concat (+ControlNet residual), nearest-2x upsample,
+// stride-2 im2col, thin direct 3x3 convs (conv_in / conv_out / ControlNet conditioning embedding), layout
+// conversion at the pipeline boundary, timestep embedding, small-M linears, and the fused CFG + DDIM step.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace imagd {
+
+__device__ __forceinline__ uint4 add_bf16x8(uint4 a, uint4 b) {
+    const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = pack_bf16x2(bf16lo(ua[k]) + bf16lo(ub[k]), bf16hi(ua[k]) + bf16hi(ub[k]));
+    return make_uint4(r[0], r[1], r[2], r[3]);
+}
+
+__global__ void concat_add_kernel(const __nv_bfloat16* __restrict__ a, int64_t lda, int Ca,
+                                  const __nv_bfloat16* __restrict__ ra, int64_t ldra,
+                                  const __nv_bfloat16* __restrict__ b, int64_t ldb, int Cb,
+                                  const __nv_bfloat16* __restrict__ rb, int64_t ldrb, __nv_bfloat16* __restrict__ out,
+                                  int64_t ldo, int64_t rows) {
+    const int CV = (Ca + Cb) / 8, CVa = Ca / 8;
+    const int64_t total = rows * CV;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t row = idx / CV;
+        const int cv = static_cast<int>(idx % CV);
+        uint4 v;
+        if (cv < CVa) {
+            v = __ldg(reinterpret_cast<const uint4*>(a + row * lda + cv * 8));
+            if (ra) v = add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(ra + row * ldra + cv * 8)));
+        } else {
+            const int c = (cv - CVa) * 8;
+            v = __ldg(reinterpret_cast<const uint4*>(b + row * ldb + c));
+            if (rb) v = add_bf16x8(v, __ldg(reinterpret_cast<const uint4*>(rb + row * ldrb + c)));
+        }
+        *reinterpret_cast<uint4*>(out + row * ldo + cv * 8) = v;
+    }
+}
+
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int NB, int H,
+                                  int W, int C) {
+    const int CV = C / 8;
+    const int64_t total = static_cast<int64_t>(NB) * 4 * H * W * CV;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int cv = static_cast<int>(idx % CV);
+        int64_t pix = idx / CV;
+        const int xo = static_cast<int>(pix % (2 * W));
+        pix /= 2 * W;
+        const int yo = static_cast<int>(pix % (2 * H));
+        const int n = static_cast<int>(pix / (2 * H));
+        const int64_t src = ((static_cast<int64_t>(n) * H + yo / 2) * W + xo / 2) * C + cv * 8;
+        *reinterpret_cast<uint4*>(y + (idx / CV) * C + cv * 8) = __ldg(reinterpret_cast<const uint4*>(x + src));
+    }
+}
+
+__global__ void im2col3x3_s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, int NB, int H,
+                                    int W, int C) {
+    const int Ho = H / 2, Wo = W / 2, CV = C / 8;
+    const int64_t total = static_cast<int64_t>(NB) * Ho * Wo * 9 * CV;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int cv = static_cast<int>(idx % CV);
+        int64_t t = idx / CV;
+        const int tap = static_cast<int>(t % 9);
+        t /= 9;
+        const int xo = static_cast<int>(t % Wo);
+        t /= Wo;
+        const int yo = static_cast<int>(t % Ho);
+        const int n = static_cast<int>(t / Ho);
+        const int yi = 2 * yo + tap / 3 - 1, xi = 2 * xo + tap % 3 - 1;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (yi >= 0 && yi < H && xi >= 0 && xi < W)
+            v = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<int64_t>(n) * H + yi) * W + xi) * C + cv * 8));
+        *reinterpret_cast<uint4*>(col + idx * 8) = v;
+    }
+}
+
+// thread per (output pixel, cout): thin convs where 9*Cin is small or the call happens once per image
+__global__ void conv3x3_direct_thread_kernel(const __nv_bfloat16* __restrict__ x, int NB, int H, int W, int Cin,
+                                             const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+                                             void* __restrict__ y, int Cout, int stride, int act, int out_nchw_f32,
+                                             const __nv_bfloat16* __restrict__ add) {
+    const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+    const int64_t total = static_cast<int64_t>(NB) * Ho * Wo * Cout;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int co = static_cast<int>(idx % Cout);
+        int64_t t = idx / Cout;
+        const int xo = static_cast<int>(t % Wo);
+        t /= Wo;
+        const int yo = static_cast<int>(t % Ho);
+        const int n = static_cast<int>(t / Ho);
+        float acc = bias ? bias[co] : 0.f;
+        const __nv_bfloat16* wr = w + static_cast<int64_t>(co) * 9 * Cin;
+        for (int tap = 0; tap < 9; ++tap) {
+            const int yi = yo * stride + tap / 3 - 1, xi = xo * stride + tap % 3 - 1;
+            if (yi < 0 || yi >= H || xi < 0 || xi >= W) continue;
+            const __nv_bfloat16* xr = x + ((static_cast<int64_t>(n) * H + yi) * W + xi) * Cin;
+            const __nv_bfloat16* wt = wr + tap * Cin;
+            for (int c = 0; c < Cin; ++c) acc += __bfloat162float(xr[c]) * __bfloat162float(wt[c]);
+        }
+        if (act == IMAGD_ACT_SILU) acc = silu(acc);
+        const int64_t opix = (static_cast<int64_t>(n) * Ho + yo) * Wo + xo;
+        if (add) acc += __bfloat162float(add[opix * Cout + co]);
+        if (out_nchw_f32)
+            reinterpret_cast<float*>(y)[((static_cast<int64_t>(n) * Cout + co) * Ho + yo) * Wo + xo] = acc;
+        else
+            reinterpret_cast<__nv_bfloat16*>(y)[opix * Cout + co] = __float2bfloat16(acc);
+    }
+}
+
+// warp per output pixel, Cout <= 8, Cin % 8 == 0: conv_out (320 -> 4). Lanes split the 9*Cin reduction.
+__global__ void __launch_bounds__(256) conv3x3_direct_warp_kernel(const __nv_bfloat16* __restrict__ x, int NB, int H,
+                                                                  int W, int Cin, const __nv_bfloat16* __restrict__ w,
+                                                                  const float* __restrict__ bias, void* __restrict__ y,
+                                                                  int Cout, int act, int out_nchw_f32) {
+    const int64_t pix = blockIdx.x * static_cast<int64_t>(blockDim.x / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pix >= static_cast<int64_t>(NB) * H * W) return;
+    const int xo = static_cast<int>(pix % W);
+    const int yo = static_cast<int>((pix / W) % H);
+    const int n = static_cast<int>(pix / (static_cast<int64_t>(W) * H));
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    const int CV = Cin / 8;
+    for (int tap = 0; tap < 9; ++tap) {
+        const int yi = yo + tap / 3 - 1, xi = xo + tap % 3 - 1;
+        if (yi < 0 || yi >= H || xi < 0 || xi >= W) continue;
+        const __nv_bfloat16* xr = x + ((static_cast<int64_t>(n) * H + yi) * W + xi) * Cin;
+        for (int cv = lane; cv < CV; cv += 32) {
+            const uint4 xv = __ldg(reinterpret_cast<const uint4*>(xr + cv * 8));
+            const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
+            for (int co = 0; co < Cout; ++co) {
+                const uint4 wv =
+                    __ldg(reinterpret_cast<const uint4*>(w + (static_cast<int64_t>(co) * 9 + tap) * Cin + cv * 8));
+                const uint32_t wu[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    acc[co] += bf16lo(xu[k]) * bf16lo(wu[k]) + bf16hi(xu[k]) * bf16hi(wu[k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    if (lane < Cout) {
+        float v = acc[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k)
+            if (lane == k) v = acc[k];
+        v += bias ? bias[lane] : 0.f;
+        if (act == IMAGD_ACT_SILU) v = silu(v);
+        if (out_nchw_f32)
+            reinterpret_cast<float*>(y)[((static_cast<int64_t>(n) * Cout + lane) * H + yo) * W + xo] = v;
+        else
+            reinterpret_cast<__nv_bfloat16*>(y)[pix * Cout + lane] = __float2bfloat16(v);
+    }
+}
+
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int NB, int C,
+                                             int H, int W, int Cpad) {
+    const int64_t total = static_cast<int64_t>(NB) * H * W * Cpad;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % Cpad);
+        const int64_t pix = idx / Cpad;
+        const int64_t hw = pix % (static_cast<int64_t>(H) * W);
+        const int64_t n = pix / (static_cast<int64_t>(H) * W);
+        const float v = c < C ? x[(n * C + c) * H * W + hw] : 0.f;
+        y[idx] = __float2bfloat16(v);
+    }
+}
+
+__global__ void timestep_embedding_kernel(const float* __restrict__ timesteps, const int32_t* __restrict__ step_ptr,
+                                          float* __restrict__ out, int NB, int dim) {
+    const int half = dim / 2;
+    const float t = timesteps[step_ptr ? *step_ptr : 0];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < NB * dim; idx += gridDim.x * blockDim.x) {
+        const int i = idx % dim;
+        const int k = i < half ? i : i - half;
+        const float freq = expf(-9.210340371976184f * static_cast<float>(k) / static_cast<float>(half));
+        const float a = t * freq;
+        out[idx] = i < half ? cosf(a) : sinf(a);
+    }
+}
+
+// warp per output feature; M tiled by 8
+__global__ void __launch_bounds__(256) linear_small_m_kernel(const float* __restrict__ x, int64_t ldx,
+                                                             const __nv_bfloat16* __restrict__ W, int64_t ldw,
+                                                             const float* __restrict__ bias, float* __restrict__ out,
+                                                             int64_t ldo, int M, int N, int K, int act_in, int act_out) {
+    const int n = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const __nv_bfloat16* wr = W + static_cast<int64_t>(n) * ldw;
+    for (int m0 = 0; m0 < M; m0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int k0 = lane * 8; k0 < K; k0 += 256) {
+            const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wr + k0));
+            const uint32_t wu[4] = {wv.x, wv.y, wv.z, wv.w};
+            float wf[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                wf[2 * k] = bf16lo(wu[k]);
+                wf[2 * k + 1] = bf16hi(wu[k]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (m0 + i < M) {
+                    const float* xr = x + static_cast<int64_t>(m0 + i) * ldx + k0;
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(xr));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(xr + 4));
+                    float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float xa = act_in == IMAGD_ACT_SILU ? silu(xv[k]) : xv[k];
+                        acc[i] += xa * wf[k];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (m0 + i < M) {
+                    float v = acc[i] + (bias ? bias[n] : 0.f);
+                    if (act_out == IMAGD_ACT_SILU) v = silu(v);
+                    out[static_cast<int64_t>(m0 + i) * ldo + n] = v;
+                }
+            }
+        }
+    }
+}
+
+__global__ void cfg_ddim_step_kernel(const float* __restrict__ eps_c, const float* __restrict__ eps_u, float g,
+                                     float* __restrict__ lat, const float* __restrict__ coef,
+                                     int32_t* __restrict__ step_ptr, const float* __restrict__ mask,
+                                     const float* __restrict__ img, const float* __restrict__ noise,
+                                     const float* __restrict__ blend_coef, int NB, int C, int HW) {
+    unsigned int* done_counter = reinterpret_cast<unsigned int*>(step_ptr + 1);
+    const int step = *step_ptr;
+    const float sa_t = coef[step * 4 + 0], sb_t = coef[step * 4 + 1], sa_p = coef[step * 4 + 2],
+                sb_p = coef[step * 4 + 3];
+    float bn_a = 1.f, bn_b = 0.f;
+    if (mask) {
+        bn_a = blend_coef[step * 2 + 0];
+        bn_b = blend_coef[step * 2 + 1];
+    }
+    const int64_t total = static_cast<int64_t>(NB) * C * HW;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float u = eps_u ? eps_u[idx] : 0.f;
+        const float c = eps_c[idx];
+        const float eps = eps_u ? u + g * (c - u) : c;
+        const float xt = lat[idx];
+        const float x0 = (xt - sb_t * eps) / sa_t;
+        float xn = sa_p * x0 + sb_p * eps;
+        if (mask) {
+            const int64_t n = idx / (static_cast<int64_t>(C) * HW);
+            const float m = mask[n * HW + idx % HW];
+            const float proper = bn_a * img[idx] + bn_b * noise[idx];
+            xn = (1.f - m) * proper + m * xn;
+        }
+        lat[idx] = xn;
+    }
+    // the last block to finish advances the device-side step counter (graph replays then see the next step)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(done_counter, 1u);
+        if (prev == gridDim.x - 1) {
+            *done_counter = 0u;
+            *step_ptr = step + 1;
+        }
+    }
+}
+
+static inline int grid_for(int64_t total, int threads) {
+    int64_t g = (total + threads - 1) / threads;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
+}  // namespace imagd
+
+extern "C" {
+
+int imagd_concat_add_bf16(const void* a, int64_t lda, int Ca, const void* res_a, int64_t ld_ra, const void* b,
+                          int64_t ldb, int Cb, const void* res_b, int64_t ld_rb, void* out, int64_t ldo, int64_t rows,
+                          imagd_stream stream) {
+    using namespace imagd;
+    IMAGD_CHECK_ARG(a && out && rows > 0, "concat_add: null pointer / rows");
+    if (!b) Cb = 0;
+    IMAGD_CHECK_ARG(Ca % 8 == 0 && Cb % 8 == 0 && lda % 8 == 0 && ldo % 8 == 0 && (Cb == 0 || ldb % 8 == 0),
+                    "concat_add: channel counts / strides must be multiples of 8");
+    IMAGD_CHECK_ARG((!res_a || ld_ra % 8 == 0) && (!res_b || ld_rb % 8 == 0), "concat_add: residual stride");
+    const int64_t total = rows * ((Ca + Cb) / 8);
+    concat_add_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a), lda, Ca, reinterpret_cast<const __nv_bfloat16*>(res_a), ld_ra,
+        reinterpret_cast<const __nv_bfloat16*>(b), ldb, Cb, reinterpret_cast<const __nv_bfloat16*>(res_b), ld_rb,
+        reinterpret_cast<__nv_bfloat16*>(out), ldo, rows);
+    IMAGD_LAUNCH_CHECK("concat_add_kernel");
+    return IMAGD_OK;
+}
+
+int imagd_upsample2x_bf16(const void* x, void* y, int NB, int H, int W, int C, imagd_stream stream) {
+    using namespace imagd;
+    IMAGD_CHECK_ARG(x && y && NB > 0 && H > 0 && W > 0 && C % 8 == 0, "upsample2x: bad args");
+    const int64_t total = static_cast<int64_t>(NB) * 4 * H * W * (C / 8);
+    upsample2x_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), NB, H, W, C);
+    IMAGD_LAUNCH_CHECK("upsample2x_kernel");
+    return IMAGD_OK;
+}
+
+int imagd_im2col3x3_s2_bf16(const void* x, void* col, int NB, int H, int W, int C, imagd_stream stream) {
+    using namespace imagd;
+    IMAGD_CHECK_ARG(x && col && NB > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "im2col_s2: bad args");
+    const int64_t total = static_cast<int64_t>(NB) * (H / 2) * (W / 2) * 9 * (C / 8);
+    im2col3x3_s2_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(col), NB, H, W, C);
+    IMAGD_LAUNCH_CHECK("im2col3x3_s2_kernel");
+    return IMAGD_OK;
+}
+
+int imagd_conv3x3_direct_bf16(const void* x, int NB, int H, int W, int Cin, const void* w, const float* bias, void* y,
+                              int Cout, int stride, int act, int out_nchw_f32, const void* add_nhwc,
+                              imagd_stream stream) {
+    using namespace imagd;
+    IMAGD_CHECK_ARG(x && w && y && NB > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3_direct: bad args");
+    IMAGD_CHECK_ARG(stride == 1 || stride == 2, "conv3x3_direct: stride %d", stride);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (Cout <= 8 && Cin % 8 == 0 && Cin >= 64 && stride == 1 && !add_nhwc) {
+        const int64_t pixels = static_cast<int64_t>(NB) * H * W;
+        conv3x3_direct_warp_kernel<<<static_cast<int>((pixels + 7) / 8), 256, 0, st>>>(
+            reinterpret_cast<const __nv_bfloat16*>(x), NB, H, W, Cin, reinterpret_cast<const __nv_bfloat16*>(w), bias, y,
+            Cout, act, out_nchw_f32);
+        IMAGD_LAUNCH_CHECK("conv3x3_direct_warp_kernel");
+        return IMAGD_OK;
+    }
+    const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+    const int64_t total = static_cast<int64_t>(NB) * Ho * Wo * Cout;
+    conv3x3_direct_thread_kernel<<<grid_for(total, 256) * 4 > 148 * 64 ? 148 * 64 : grid_for(total, 256) * 4, 256, 0,
+                                   st>>>(reinterpret_cast<const __nv_bfloat16*>(x), NB, H, W, Cin,
+                                         reinterpret_cast<const __nv_bfloat16*>(w), bias, y, Cout, stride, act,
+                                         out_nchw_f32, reinterpret_cast<const __nv_bfloat16*>(add_nhwc));
+    IMAGD_LAUNCH_CHECK("conv3x3_direct_thread_kernel");
+    return IMAGD_OK;
+}
+
+int imagd_nchw_f32_to_nhwc_bf16(const float* x, void* y, int NB, int C, int H, int W, int Cpad, imagd_stream stream) {
+    using namespace imagd;
+    IMAGD_CHECK_ARG(x && y && NB > 0 && C > 0 && Cpad >= C, "nchw_to_nhwc: bad args");
+    const int64_t total = static_cast<int64_t>(NB) * H * W * Cpad;
+    nchw_f32_to_nhwc_bf16_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, reinterpret_cast<__nv_bfloat16*>(y), NB, C, H, W, Cpad);
+    IMAGD_LAUNCH_CHECK("nchw_f32_to_nhwc_bf16_kernel");
+    return IMAGD_OK;
+}
+
+int imagd_timestep_embedding(const float* timesteps, const int32_t* step_ptr, float* out, int NB, int dim,
+                             imagd_stream stream) {
+    using namespace imagd;
+    IMAGD_CHECK_ARG(timesteps && out && NB > 0 && dim > 0 && dim % 2 == 0, "timestep_embedding: bad args");
+    timestep_embedding_kernel<<<grid_for(static_cast<int64_t>(NB) * dim, 256), 256, 0,
+                                static_cast<cudaStream_t>(stream)>>>(timesteps, step_ptr, out, NB, dim);
+    IMAGD_LAUNCH_CHECK("timestep_embedding_kernel");
+    return IMAGD_OK;
+}
+
+int imagd_linear_small_m(const float* x, int64_t ldx, const void* W, int64_t ldw, const float* bias, float* out,
+                         int64_t ldo, int M, int N, int K, int act_in, int act_out, imagd_stream stream) {
+    using namespace imagd;
+    IMAGD_CHECK_ARG(x && W && out && M > 0 && N > 0 && K > 0, "linear_small_m: bad args");
+    IMAGD_CHECK_ARG(K % 8 == 0 && ldx % 4 == 0 && ldw % 8 == 0 && aligned16(x) && aligned16(W),
+                    "linear_small_m: K / stride alignment");
+    linear_small_m_kernel<<<(N + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, ldx, reinterpret_cast<const __nv_bfloat16*>(W), ldw, bias, out, ldo, M, N, K, act_in, act_out);
+    IMAGD_LAUNCH_CHECK("linear_small_m_kernel");
+    return IMAGD_OK;
+}
+
+int imagd_cfg_ddim_step(const float* eps_cond, const float* eps_uncond, float guidance, float* latents,
+                        const float* coef, int32_t* step_ptr, const float* mask, const float* image_latents,
+                        const float* noise, const float* blend_coef, int NB, int C, int HW, imagd_stream stream) {
+    using namespace imagd;
+    IMAGD_CHECK_ARG(eps_cond && latents && coef && step_ptr && NB > 0 && C > 0 && HW > 0, "cfg_ddim_step: bad args");
+    IMAGD_CHECK_ARG(!mask || (image_latents && noise && blend_coef), "cfg_ddim_step: inpaint blend needs all operands");
+    const int64_t total = static_cast<int64_t>(NB) * C * HW;
+    int grid = grid_for(total, 256);
+    if (grid > 148) grid = 148;
+    cfg_ddim_step_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        eps_cond, eps_uncond, guidance, latents, coef, step_ptr, mask, image_latents, noise, blend_coef, NB, C, HW);
+    IMAGD_LAUNCH_CHECK("cfg_ddim_step_kernel");
+    return IMAGD_OK;
+}
+
+}  // extern "C"

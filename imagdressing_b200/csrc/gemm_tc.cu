@@ -1,0 +1,369 @@
+// tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   D[p, c] = epilogue( sum_{tap, k} A_tap[p, k] * W[c, tap*Cin + k] )
+//
+// A is a token-major bf16 activation [NB, H, W, ld]; for the 3x3 convolution the nine taps are nine shifted
+// views of the same tensor, fetched by TMA as 4-D boxes (channels, x, y, image) whose out-of-bounds part the
+// hardware zero-fills — that is the conv's zero padding, with no im2col buffer. A plain GEMM is the same
+// kernel with one tap and a [K, M, 1, 1] view.
+//
+// CTA = 128 output pixels x BLOCK_N output channels. Warp roles (192 threads):
+//   warp 0     TMA producer   (one elected lane; STAGES-deep smem ring, full/empty mbarriers)
+//   warp 1     TMEM allocator + tcgen05.mma issuer (one elected lane; fp32 accumulator in TMEM)
+//   warps 2-5  epilogue: tcgen05.ld -> bias / time-embedding row vector / activation / residual -> bf16 stores
+// Two CTAs fit per SM (96 KB smem, <=128 TMEM columns each) so one CTA's epilogue overlaps the other's mainloop.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace imagd {
+
+struct GemmParams {
+    // K loop
+    int taps;          // 1 or 9
+    int kb_per_tap;    // ceil(Cin / 64)
+    int cin;           // K per tap (weight column offset between taps)
+    // pixel-tile geometry: a tile is bw x bh x bn pixels (product 128)
+    int bw, bh, bn;
+    int tiles_x, tiles_y;
+    int W, H, NB;
+    // output
+    int N;             // logical output columns of the GEMM (before GEGLU halving)
+    void* out;
+    int64_t ldd;
+    imagd_epilogue ep;
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
+
+template <int BLOCK_N, int STAGES>
+struct GemmSmem {
+    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    using L = GemmSmem<BLOCK_N, STAGES>;
+    extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+        printf("imagd: dynamic shared memory base %u is not 1024-byte aligned\n", smem_u32(smem));
+        __trap();
+    }
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // tile coordinates
+    const int m_blk = blockIdx.x;
+    const int n_blk = blockIdx.y;
+    const int tx = m_blk % p.tiles_x;
+    const int ty = (m_blk / p.tiles_x) % p.tiles_y;
+    const int tn = m_blk / (p.tiles_x * p.tiles_y);
+    const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
+    const int total_kb = p.taps * p.kb_per_tap;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, BLOCK_N);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int kb = 0; kb < total_kb; ++kb) {
+                const int stage = kb % STAGES;
+                const uint32_t phase = (kb / STAGES) & 1;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+                const int tap = kb / p.kb_per_tap;
+                const int kc = kb - tap * p.kb_per_tap;
+                int dx = 0, dy = 0;
+                if (p.taps == 9) {
+                    dy = tap / 3 - 1;
+                    dx = tap % 3 - 1;
+                }
+                uint8_t* sa = smem + stage * L::kStageBytes;
+                uint8_t* sb = sa + kABytes;
+                tma_load_4d(sa, &tmA, &full_bar[stage], kc * kBlockK, x0 + dx, y0 + dy, n0);
+                tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.cin + kc * kBlockK, n_blk * BLOCK_N);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+            for (int kb = 0; kb < total_kb; ++kb) {
+                const int stage = kb % STAGES;
+                const uint32_t phase = (kb / STAGES) & 1;
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+                const uint32_t sb = sa + kABytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    const uint64_t adesc = umma_smem_desc_sw128(sa + k * 32, 16, 1024);
+                    const uint64_t bdesc = umma_smem_desc_sw128(sb + k * 32, 16, 1024);
+                    umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            }
+            umma_commit(tmem_full_bar);  // accumulator complete
+        }
+    } else {
+        // ---------------- epilogue ----------------
+        const int lane_group = warp & 3;               // TMEM lanes [32*lane_group, +32) belong to this warp
+        const int r = lane_group * 32 + lane;          // tile-local pixel
+        const int x = x0 + r % p.bw;
+        const int y = y0 + (r / p.bw) % p.bh;
+        const int n = n0 + r / (p.bw * p.bh);
+        const bool row_ok = (x < p.W) && (y < p.H) && (n < p.NB);
+        const int64_t pix = (static_cast<int64_t>(n) * p.H + y) * p.W + x;
+        const imagd_epilogue& ep = p.ep;
+        const float alpha = ep.alpha;
+        const float* rowvec = nullptr;
+        if (ep.rowvec != nullptr && row_ok) rowvec = ep.rowvec + (pix / ep.rows_per_group) * ep.rowvec_ld;
+        const __nv_bfloat16* res = nullptr;
+        if (ep.residual != nullptr && row_ok)
+            res = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + pix * ep.ldr;
+
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16);
+
+        if (ep.act == IMAGD_ACT_GEGLU) {
+            // tile = [64 value | 64 gate]; output columns n_blk*64 + [0, 64)
+            if constexpr (BLOCK_N == 128) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t va[32], vg[32];
+                    tmem_ld32(taddr + c0, va);
+                    tmem_ld32(taddr + 64 + c0, vg);
+                    tmem_ld_wait();
+                    const int pcol = n_blk * 128 + c0;  // packed column of value; gate at +64
+                    const int ocol = n_blk * 64 + c0;
+                    if (row_ok && pcol < p.N) {
+                        uint32_t packed[16];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            float a0 = alpha * __uint_as_float(va[j]), a1 = alpha * __uint_as_float(va[j + 1]);
+                            float g0 = alpha * __uint_as_float(vg[j]), g1 = alpha * __uint_as_float(vg[j + 1]);
+                            if (ep.bias) {
+                                a0 += __ldg(ep.bias + pcol + j);
+                                a1 += __ldg(ep.bias + pcol + j + 1);
+                                g0 += __ldg(ep.bias + pcol + 64 + j);
+                                g1 += __ldg(ep.bias + pcol + 64 + j + 1);
+                            }
+                            packed[j / 2] = pack_bf16x2(a0 * gelu_erf(g0), a1 * gelu_erf(g1));
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldd + ocol);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                    }
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                tmem_ld_wait();
+                const int col = n_blk * BLOCK_N + c0;
+                if (!row_ok || col >= p.N) continue;
+                // columns are handled in groups of 8 (N % 8 == 0 is enforced on the host)
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int cg = col + g * 8;
+                    if (cg >= p.N) break;
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = alpha * __uint_as_float(v[g * 8 + j]);
+                    if (ep.bias) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + cg));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + cg + 4));
+                        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                        f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                    }
+                    if (rowvec) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(rowvec + cg));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(rowvec + cg + 4));
+                        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                        f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                    }
+                    if (ep.act == IMAGD_ACT_SILU) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = silu(f[j]);
+                    } else if (ep.act == IMAGD_ACT_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
+                    }
+                    if (res) {
+                        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res + cg));
+                        f[0] += bf16lo(rv.x); f[1] += bf16hi(rv.x); f[2] += bf16lo(rv.y); f[3] += bf16hi(rv.y);
+                        f[4] += bf16lo(rv.z); f[5] += bf16hi(rv.z); f[6] += bf16lo(rv.w); f[7] += bf16hi(rv.w);
+                    }
+                    if (ep.out_fp32) {
+                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldd + cg);
+                        dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+                        dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+                    } else {
+                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldd + cg);
+                        *dst = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                          pack_bf16x2(f[6], f[7]));
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+
+// Split 128 pixels into a (bw, bh, bn) box of powers of two that wastes the fewest tile slots.
+static void choose_pixel_box(int W, int H, int NB, int* bw, int* bh, int* bn) {
+    double best = -1.0;
+    for (int w = 1; w <= 128; w *= 2) {
+        for (int h = 1; w * h <= 128; h *= 2) {
+            const int n = 128 / (w * h);
+            const int64_t tiles = static_cast<int64_t>((W + w - 1) / w) * ((H + h - 1) / h) * ((NB + n - 1) / n);
+            const double eff = static_cast<double>(static_cast<int64_t>(W) * H * NB) / (tiles * 128.0);
+            // prefer wider boxes on ties (longer contiguous TMA rows)
+            if (eff > best + 1e-9 || (eff > best - 1e-9 && w > *bw)) {
+                best = eff;
+                *bw = w;
+                *bh = h;
+                *bn = n;
+            }
+        }
+    }
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles,
+                       cudaStream_t stream) {
+    using L = GemmSmem<BLOCK_N, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        IMAGD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        L::kTotal));
+        attr_set = true;
+    }
+    const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+    dim3 grid(m_tiles, n_tiles, 1);
+    gemm_tc_kernel<BLOCK_N, STAGES><<<grid, 192, L::kTotal, stream>>>(tmA, tmB, p);
+    IMAGD_LAUNCH_CHECK("gemm_tc_kernel");
+    return IMAGD_OK;
+}
+
+static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int Cin, int taps, const void* Wt,
+                         int64_t ldw, void* D, int64_t ldd, int N, const imagd_epilogue* ep_in, cudaStream_t stream) {
+    imagd_epilogue ep;
+    if (ep_in) {
+        ep = *ep_in;
+    } else {
+        memset(&ep, 0, sizeof(ep));
+        ep.alpha = 1.0f;
+    }
+    IMAGD_CHECK_ARG(A && Wt && D, "gemm: null pointer");
+    IMAGD_CHECK_ARG(Cin % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K=%d lda=%lld ldw=%lld must be multiples of 8",
+                    Cin, (long long)lda, (long long)ldw);
+    IMAGD_CHECK_ARG(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
+    IMAGD_CHECK_ARG(taps == 1 || Cin % 64 == 0, "conv3x3: Cin=%d must be a multiple of 64", Cin);
+    const bool geglu = ep.act == IMAGD_ACT_GEGLU;
+    IMAGD_CHECK_ARG(!geglu || N % 128 == 0, "gemm: GEGLU needs packed N %% 128 == 0 (N=%d)", N);
+    IMAGD_CHECK_ARG(ldd % 8 == 0 && aligned16(D), "gemm: output ld=%lld / pointer must be 16-byte aligned", (long long)ldd);
+    IMAGD_CHECK_ARG(!ep.residual || (ep.ldr % 8 == 0 && aligned16(ep.residual)), "gemm: residual alignment");
+    IMAGD_CHECK_ARG(!ep.bias || aligned16(ep.bias), "gemm: bias alignment");
+    IMAGD_CHECK_ARG(!ep.rowvec || (aligned16(ep.rowvec) && ep.rowvec_ld % 4 == 0 && ep.rows_per_group > 0),
+                    "gemm: rowvec alignment / rows_per_group");
+
+    GemmParams p;
+    p.taps = taps;
+    p.kb_per_tap = (Cin + kBlockK - 1) / kBlockK;
+    p.cin = Cin;
+    p.bw = p.bh = p.bn = 1;
+    choose_pixel_box(W, H, NB, &p.bw, &p.bh, &p.bn);
+    p.tiles_x = (W + p.bw - 1) / p.bw;
+    p.tiles_y = (H + p.bh - 1) / p.bh;
+    const int tiles_n = (NB + p.bn - 1) / p.bn;
+    p.W = W;
+    p.H = H;
+    p.NB = NB;
+    p.N = N;
+    p.out = D;
+    p.ldd = ldd;
+    p.ep = ep;
+    const int64_t m_tiles64 = static_cast<int64_t>(p.tiles_x) * p.tiles_y * tiles_n;
+    IMAGD_CHECK_ARG(m_tiles64 > 0 && m_tiles64 < (1 << 30), "gemm: bad tile count");
+    const int m_tiles = static_cast<int>(m_tiles64);
+
+    // A: [NB, H, W, lda] viewed (c, x, y, n)
+    CUtensorMap tmA, tmB;
+    {
+        uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                            static_cast<uint64_t>(NB)};
+        uint64_t strides[3] = {static_cast<uint64_t>(lda) * 2, static_cast<uint64_t>(lda) * 2 * W,
+                               static_cast<uint64_t>(lda) * 2 * W * H};
+        uint32_t box[4] = {kBlockK, static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh), static_cast<uint32_t>(p.bn)};
+        int rc = make_tmap_bf16(&tmA, A, 4, dims, strides, box);
+        if (rc != IMAGD_OK) return rc;
+    }
+    // pick the N tile: 128 unless that wastes > 1/8 of the columns or leaves most SMs idle
+    const int n128 = (N + 127) / 128, n64 = (N + 63) / 64;
+    bool use128 = geglu || ((n128 * 128 - N) * 8 <= N && static_cast<int64_t>(m_tiles) * n128 >= 120);
+    if (N <= 64) use128 = geglu;
+    {
+        uint64_t dims[2] = {static_cast<uint64_t>(taps) * Cin, static_cast<uint64_t>(N)};
+        uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+        uint32_t box[2] = {kBlockK, static_cast<uint32_t>(use128 ? 128 : 64)};
+        int rc = make_tmap_bf16(&tmB, Wt, 2, dims, strides, box);
+        if (rc != IMAGD_OK) return rc;
+    }
+    (void)n64;
+    if (use128) return launch_gemm<128, 3>(tmA, tmB, p, m_tiles, stream);
+    return launch_gemm<64, 4>(tmA, tmB, p, m_tiles, stream);
+}
+
+}  // namespace imagd
+
+extern "C" {
+
+int imagd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd, int M, int N, int K,
+                    const imagd_epilogue* ep, imagd_stream stream) {
+    IMAGD_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+    return imagd::run_gemm_like(A, lda, 1, 1, M, K, 1, W, ldw, D, ldd, N, ep, static_cast<cudaStream_t>(stream));
+}
+
+int imagd_conv3x3_bf16(const void* X, int64_t ldx, int NB, int H, int W, int Cin, const void* Wt, void* Y, int64_t ldy,
+                       int Cout, const imagd_epilogue* ep, imagd_stream stream) {
+    IMAGD_CHECK_ARG(NB > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3: bad shape");
+    return imagd::run_gemm_like(X, ldx, NB, H, W, Cin, 9, Wt, static_cast<int64_t>(9) * Cin, Y, ldy, Cout, ep,
+                                static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

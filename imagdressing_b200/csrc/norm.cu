@@ -1,0 +1,235 @@
+// GroupNorm (+SiLU) and LayerNorm over token-major bf16 activations. HBM-bound: every element is read with
+// 128-bit loads, statistics are fp32, and the grid is sized to cover all 148 SMs even at batch 1.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace imagd {
+
+constexpr int kGnMaxC = 2560;
+constexpr int kGnThreads = 512;
+
+__host__ __device__ inline int gn_chunks(int HW) {
+    int c = (HW + 31) / 32;
+    return c < 1 ? 1 : (c > 64 ? 64 : c);
+}
+
+// Partial sums: ws[((n * chunks + chunk) * groups + g) * 2 + {0: sum, 1: sum of squares}]
+__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int HW,
+                                                              int C, int groups, int chunks, float* __restrict__ ws) {
+    __shared__ float s_sum[kGnMaxC];
+    __shared__ float s_sq[kGnMaxC];
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int CV = C / 8;
+    const int rows = kGnThreads / CV;  // pixel rows processed per iteration (>= 1 since C <= 2560 < 8*512)
+    const int ppc = (HW + chunks - 1) / chunks;
+    const int p_begin = chunk * ppc;
+    const int p_end = min(HW, p_begin + ppc);
+
+    for (int c = threadIdx.x; c < C; c += kGnThreads) {
+        s_sum[c] = 0.f;
+        s_sq[c] = 0.f;
+    }
+    __syncthreads();
+
+    const int cv = threadIdx.x % CV;
+    const int prow = threadIdx.x / CV;
+    if (prow < rows) {
+        float sum[8], sq[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum[k] = sq[k] = 0.f;
+        const __nv_bfloat16* base = x + (static_cast<int64_t>(n) * HW) * ldx + cv * 8;
+        for (int pix = p_begin + prow; pix < p_end; pix += rows) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<int64_t>(pix) * ldx));
+            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float a = bf16lo(u[k]), b = bf16hi(u[k]);
+                sum[2 * k] += a;
+                sq[2 * k] += a * a;
+                sum[2 * k + 1] += b;
+                sq[2 * k + 1] += b * b;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            atomicAdd(&s_sum[cv * 8 + k], sum[k]);
+            atomicAdd(&s_sq[cv * 8 + k], sq[k]);
+        }
+    }
+    __syncthreads();
+    const int cpg = C / groups;
+    for (int g = threadIdx.x; g < groups; g += kGnThreads) {
+        float a = 0.f, b = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            a += s_sum[c];
+            b += s_sq[c];
+        }
+        float* dst = ws + ((static_cast<int64_t>(n) * chunks + chunk) * groups + g) * 2;
+        dst[0] = a;
+        dst[1] = b;
+    }
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                                                       __nv_bfloat16* __restrict__ y, int64_t ldy, int HW, int C,
+                                                       int groups, int chunks, const float* __restrict__ ws,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float eps, int fuse_silu, int apply_chunks) {
+    __shared__ float s_scale[kGnMaxC];
+    __shared__ float s_shift[kGnMaxC];
+    __shared__ float s_mean[64];
+    __shared__ float s_rstd[64];
+    const int n = blockIdx.y;
+    const int cpg = C / groups;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int c = 0; c < chunks; ++c) {
+            const float* src = ws + ((static_cast<int64_t>(n) * chunks + c) * groups + g) * 2;
+            a += src[0];
+            b += src[1];
+        }
+        const float cnt = static_cast<float>(cpg) * static_cast<float>(HW);
+        const float mean = a / cnt;
+        const float var = fmaxf(b / cnt - mean * mean, 0.f);
+        s_mean[g] = mean;
+        s_rstd[g] = rsqrtf(var + eps);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float sc = (gamma ? gamma[c] : 1.f) * s_rstd[g];
+        s_scale[c] = sc;
+        s_shift[c] = (beta ? beta[c] : 0.f) - s_mean[g] * sc;
+    }
+    __syncthreads();
+
+    const int CV = C / 8;
+    const int ppc = (HW + apply_chunks - 1) / apply_chunks;
+    const int p_begin = blockIdx.x * ppc;
+    const int p_end = min(HW, p_begin + ppc);
+    const int64_t total = static_cast<int64_t>(p_end - p_begin) * CV;
+    for (int64_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int pix = p_begin + static_cast<int>(idx / CV);
+        const int c0 = static_cast<int>(idx % CV) * 8;
+        const int64_t row = static_cast<int64_t>(n) * HW + pix;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + c0));
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            f[2 * k] = bf16lo(u[k]) * s_scale[c0 + 2 * k] + s_shift[c0 + 2 * k];
+            f[2 * k + 1] = bf16hi(u[k]) * s_scale[c0 + 2 * k + 1] + s_shift[c0 + 2 * k + 1];
+        }
+        if (fuse_silu) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = silu(f[k]);
+        }
+        *reinterpret_cast<uint4*>(y + row * ldy + c0) =
+            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+}
+
+// One warp per row; C <= 2048, C % 8 == 0.
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                                                        __nv_bfloat16* __restrict__ y, int64_t ldy, int rows, int C,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps) {
+    const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int CV = C / 8;
+    float f[8][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int cv = lane + i * 32;
+        if (cv < CV) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx + cv * 8));
+            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                f[i][2 * k] = bf16lo(u[k]);
+                f[i][2 * k + 1] = bf16hi(u[k]);
+                sum += f[i][2 * k] + f[i][2 * k + 1];
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / static_cast<float>(C);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int cv = lane + i * 32;
+        if (cv < CV) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float d = f[i][k] - mean;
+                sq += d * d;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / static_cast<float>(C) + eps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int cv = lane + i * 32;
+        if (cv < CV) {
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int c = cv * 8 + k;
+                o[k] = (f[i][k] - mean) * rstd * (gamma ? __ldg(gamma + c) : 1.f) + (beta ? __ldg(beta + c) : 0.f);
+            }
+            *reinterpret_cast<uint4*>(y + static_cast<int64_t>(row) * ldy + cv * 8) =
+                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        }
+    }
+}
+
+}  // namespace imagd
+
+extern "C" {
+
+int64_t imagd_groupnorm_ws_bytes(int NB, int HW, int C, int groups) {
+    (void)C;
+    return static_cast<int64_t>(NB) * imagd::gn_chunks(HW) * groups * 2 * sizeof(float);
+}
+
+int imagd_groupnorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int NB, int HW, int C, int groups,
+                         const float* gamma, const float* beta, float eps, int fuse_silu, void* ws, imagd_stream stream) {
+    using namespace imagd;
+    IMAGD_CHECK_ARG(x && y && ws, "groupnorm: null pointer");
+    IMAGD_CHECK_ARG(NB > 0 && HW > 0 && C > 0 && C % 8 == 0 && C <= kGnMaxC, "groupnorm: C=%d unsupported", C);
+    IMAGD_CHECK_ARG(groups > 0 && groups <= 64 && C % groups == 0, "groupnorm: groups=%d", groups);
+    IMAGD_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y), "groupnorm: alignment");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int chunks = gn_chunks(HW);
+    gn_stats_kernel<<<dim3(chunks, NB), kGnThreads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C,
+                                                             groups, chunks, reinterpret_cast<float*>(ws));
+    IMAGD_LAUNCH_CHECK("gn_stats_kernel");
+    int apply_chunks = (HW + 15) / 16;
+    if (apply_chunks > 128) apply_chunks = 128;
+    gn_apply_kernel<<<dim3(apply_chunks, NB), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, HW, C, groups, chunks,
+        reinterpret_cast<const float*>(ws), gamma, beta, eps, fuse_silu, apply_chunks);
+    IMAGD_LAUNCH_CHECK("gn_apply_kernel");
+    return IMAGD_OK;
+}
+
+int imagd_layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int C, const float* gamma,
+                         const float* beta, float eps, imagd_stream stream) {
+    using namespace imagd;
+    IMAGD_CHECK_ARG(x && y, "layernorm: null pointer");
+    IMAGD_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && C <= 2048, "layernorm: C=%d unsupported", C);
+    IMAGD_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y), "layernorm: alignment");
+    const int wpb = 8;
+    layernorm_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, rows, C, gamma, beta,
+        eps);
+    IMAGD_LAUNCH_CHECK("layernorm_kernel");
+    return IMAGD_OK;
+}
+
+}  // extern "C"

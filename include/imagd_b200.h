@@ -1,0 +1,163 @@
+/*
+ * imagd_b200.h — C ABI of libimagd_b200.so: the sm_100a kernels behind the IMAGDressing-v1 denoising hot path.
+ *
+ * Boundary contract ("C-ABI extension"): plain pointers + sizes, no torch types; the caller
+ * owns every buffer (kernels never allocate), every launch goes to the caller's stream (so the whole step is
+ * CUDA-graph capturable), every entry point returns 0 or a negative imagd_status and records a message that
+ * imagd_last_error() returns.  All activations are bf16, token-major ("NHWC" / [rows, channels]) with an explicit
+ * row stride `ld*` in ELEMENTS; weights are bf16 [out_features, in_features] (torch nn.Linear layout; 3x3 conv
+ * weights repacked tap-major to [Cout, 3*3*Cin]); biases / norm affine / time-embedding vectors are fp32.
+ *
+ * Each entry point cites the reference code (relative to /root/reference) whose arithmetic it replaces.
+ * "diffusers-0.24" marks third-party code the reference calls.
+ */
+#ifndef IMAGD_B200_H
+#define IMAGD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* imagd_stream; /* cudaStream_t */
+
+enum imagd_status {
+    IMAGD_OK = 0,
+    IMAGD_ERR_ARG = -1,  /* bad shape / alignment / null pointer */
+    IMAGD_ERR_CUDA = -2, /* CUDA runtime / driver error */
+    IMAGD_ERR_ARCH = -3  /* device is not sm_100 */
+};
+
+enum imagd_act { IMAGD_ACT_NONE = 0, IMAGD_ACT_GEGLU = 1, IMAGD_ACT_SILU = 2, IMAGD_ACT_GELU = 3 };
+
+/* ---- library ---- */
+int imagd_version(void);
+const char* imagd_last_error(void);
+/* Returns 100 on a B200 (cc 10.0); IMAGD_ERR_ARCH on anything else; IMAGD_ERR_CUDA with no device. */
+int imagd_device_check(void);
+
+/* ---- fused GEMM / conv epilogue ----
+ * out[r, c] = act( alpha * acc[r, c] + bias[c] + rowvec[r / rows_per_group, c] ) + residual[r, c]
+ * IMAGD_ACT_GEGLU: the packed weight interleaves, per 128 output rows, 64 "value" rows then their 64 "gate"
+ * rows; out has N/2 columns: value * gelu_erf(gate)   (diffusers-0.24 GEGLU in BasicTransformerBlock.ff). */
+typedef struct imagd_epilogue {
+    const float* bias;     /* [N] or NULL */
+    const float* rowvec;   /* [groups, rowvec_ld] or NULL (ResnetBlock2D time-embedding add) */
+    int64_t rowvec_ld;
+    int32_t rows_per_group; /* rows (pixels) per sample */
+    int32_t act;            /* enum imagd_act */
+    const void* residual;   /* bf16 [M, ldr] or NULL */
+    int64_t ldr;
+    float alpha;            /* 1.0f for plain */
+    int32_t out_fp32;       /* 0: bf16 output, 1: fp32 output */
+} imagd_epilogue;
+
+/* D[M,N] = A[M,K] * W[N,K]^T (+ epilogue).  tcgen05 tensor cores, TMA-fed, fp32 accumulation in TMEM.
+ * Replaces every nn.Linear / 1x1 conv on the path: attn.to_q/to_k/to_v/to_out, to_k_ref/to_v_ref
+ * (adapter/attention_processor.py:568-615,598-601), to_k_ip/to_v_ip (:841-842), Transformer2DModel proj_in/out,
+ * FeedForward (diffusers-0.24), Resampler linears (adapter/resampler.py:13-20,45-47,186-188).
+ * K % 8 == 0, lda/ldw % 8 == 0, pointers 16-byte aligned. */
+int imagd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd, int M, int N,
+                    int K, const imagd_epilogue* ep, imagd_stream stream);
+
+/* Y[n,y,x,:] = sum_{ky,kx} X[n,y+ky-1,x+kx-1,:] * Wt[:, (ky*3+kx)*Cin : +Cin]^T  (stride 1, zero pad 1) as an
+ * implicit GEMM on tcgen05: the 9 shifted activation views are fetched by TMA with out-of-bounds zero fill.
+ * Replaces ResnetBlock2D.conv1/conv2 and Upsample2D.conv (diffusers-0.24).
+ * Cin % 64 == 0.  X: [NB,H,W,ldx], Y: [NB,H,W,ldy]. */
+int imagd_conv3x3_bf16(const void* X, int64_t ldx, int NB, int H, int W, int Cin, const void* Wt, void* Y,
+                       int64_t ldy, int Cout, const imagd_epilogue* ep, imagd_stream stream);
+
+/* ---- attention ----
+ * One KV stream of the two-stream ("hybrid") attention.  k and v are [n_kv_samples * len, ld] bf16 with head h at
+ * columns [h*head_dim, (h+1)*head_dim).  The stream applies to query samples [0, n_query_samples); later samples
+ * skip it (the unconditional half of a CFG batch has no garment stream:
+ * dressing_sd/pipelines/IMAGDressing_v1_pipeline.py:511-518, adapter/attention_processor.py:597). */
+typedef struct imagd_kv_stream {
+    const void* k;
+    const void* v;
+    int64_t ld;
+    int32_t len;             /* keys per sample */
+    int32_t broadcast;       /* 1: one KV sample shared by all query samples (garment dressed on a batch) */
+    int32_t n_query_samples; /* query samples [0, n) use this stream */
+    float out_scale;         /* weight of this stream's softmax output */
+} imagd_kv_stream;
+
+/* out = s0.out_scale * softmax(q k0^T * sm_scale) v0 + s1.out_scale * softmax(q k1^T * sm_scale) v1
+ * — two independent softmaxes sharing one Q tile (FlashAttention-style, S/O accumulators in TMEM).
+ * Replaces the two F.scaled_dot_product_attention calls + scale-add of RefSAttnProcessor2_0
+ * (adapter/attention_processor.py:589-612), the text+IP pair of LoRAIPAttnProcessor2_0 (:833-856), the single
+ * SDPA of CAttnProcessor2_0 / CacheAttnProcessor2_0 (:80, :270), and PerceiverAttention's fp32 softmax
+ * (adapter/resampler.py:71-74).  q: [B*Lq, q_ld], out: [B*Lq, out_ld].  head_dim in {40, 64, 80, 160}. s1 may be
+ * NULL. */
+int imagd_attention_bf16(const void* q, int64_t q_ld, void* out, int64_t out_ld, int B, int Lq, int heads,
+                         int head_dim, const imagd_kv_stream* s0, const imagd_kv_stream* s1, float sm_scale,
+                         imagd_stream stream);
+
+/* ---- normalisation ---- */
+/* GroupNorm over [NB, HW, C] (token-major) with optional fused SiLU; workspace ws holds the partial sums.
+ * Replaces ResnetBlock2D.norm1/norm2 + nonlinearity, Transformer2DModel.norm, conv_norm_out (diffusers-0.24). */
+int64_t imagd_groupnorm_ws_bytes(int NB, int HW, int C, int groups);
+int imagd_groupnorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int NB, int HW, int C, int groups,
+                         const float* gamma, const float* beta, float eps, int fuse_silu, void* ws,
+                         imagd_stream stream);
+/* LayerNorm over the last dim of [rows, C]; BasicTransformerBlock.norm1-3 (diffusers-0.24),
+ * adapter/resampler.py:16,43-44,187. gamma/beta may be NULL. */
+int imagd_layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int C, const float* gamma,
+                         const float* beta, float eps, imagd_stream stream);
+
+/* ---- data movement / small convs ---- */
+/* out[:, :Ca] = a ; out[:, Ca:Ca+Cb] = b (+ res_b) ; also a += res_a when given — the up-block skip concat
+ * (torch.cat([hidden, skip], 1), diffusers-0.24 unet_2d_blocks) with the ControlNet residual add folded in
+ * (UNet2DConditionModel.forward down_block_additional_residuals). b may be NULL (plain add/copy). */
+int imagd_concat_add_bf16(const void* a, int64_t lda, int Ca, const void* res_a, int64_t ld_ra, const void* b,
+                          int64_t ldb, int Cb, const void* res_b, int64_t ld_rb, void* out, int64_t ldo,
+                          int64_t rows, imagd_stream stream);
+/* Nearest-neighbour 2x upsample of [NB,H,W,C] -> [NB,2H,2W,C] (Upsample2D, diffusers-0.24). */
+int imagd_upsample2x_bf16(const void* x, void* y, int NB, int H, int W, int C, imagd_stream stream);
+/* im2col for the stride-2 pad-1 3x3 Downsample2D conv: [NB,H,W,C] -> [NB*(H/2)*(W/2), 9*C] tap-major. */
+int imagd_im2col3x3_s2_bf16(const void* x, void* col, int NB, int H, int W, int C, imagd_stream stream);
+/* Direct (SIMT) 3x3 conv, pad 1, stride 1 or 2, for the thin ends of the network where a tensor-core tile would
+ * be empty: conv_in (4->320), conv_out (320->4), ControlNet conditioning embedding (3->16->...->320).
+ * x: bf16 [NB,H,W,Cin]; w: bf16 [Cout, 9*Cin] tap-major; bias fp32; act in {NONE, SILU}.
+ * out_nchw_f32 != 0 writes fp32 NCHW (the latent layout of the pipeline API) instead of bf16 NHWC. */
+int imagd_conv3x3_direct_bf16(const void* x, int NB, int H, int W, int Cin, const void* w, const float* bias,
+                              void* y, int Cout, int stride, int act, int out_nchw_f32, const void* add_nhwc,
+                              imagd_stream stream);
+/* fp32 NCHW latents -> bf16 NHWC (channels zero-padded to Cpad). */
+int imagd_nchw_f32_to_nhwc_bf16(const float* x, void* y, int NB, int C, int H, int W, int Cpad,
+                                imagd_stream stream);
+
+/* ---- time conditioning ---- */
+/* Sinusoidal timestep embedding, flip_sin_to_cos=True, freq_shift=0: out[b] = [cos | sin] (dim/2 each), fp32.
+ * t = timesteps[step_ptr ? *step_ptr : 0] broadcast to all NB rows when per_sample == 0. diffusers-0.24
+ * get_timestep_embedding. */
+int imagd_timestep_embedding(const float* timesteps, const int32_t* step_ptr, float* out, int NB, int dim,
+                             imagd_stream stream);
+/* out[m, n] = act_out( sum_k act_in(x[m,k]) * W[n,k] + bias[n] ), fp32 activations, bf16 weights, for the
+ * M <= 64 "one row per sample" linears: TimestepEmbedding.linear_1/2 and every ResnetBlock2D.time_emb_proj
+ * (batched into one call by concatenating the weights). act: 0 none, 2 SiLU. */
+int imagd_linear_small_m(const float* x, int64_t ldx, const void* W, int64_t ldw, const float* bias, float* out,
+                         int64_t ldo, int M, int N, int K, int act_in, int act_out, imagd_stream stream);
+
+/* ---- sampler ---- */
+/* Classifier-free guidance + DDIM (eta = 0) step, optionally + the inpainting blend, in one pass over the
+ * latents (dressing_sd/pipelines/IMAGDressing_v1_pipeline.py:521-532; DDIMScheduler.step, diffusers-0.24;
+ * IMAGDressing_v1_pipeline_controlnet_inpainting.py:487-500).
+ *   eps  = eps_uncond + g * (eps_cond - eps_uncond)
+ *   x0   = (x - sqrt(1-a_t) eps) / sqrt(a_t) ;  x' = sqrt(a_p) x0 + sqrt(1-a_p) eps
+ *   if mask: x' = (1-mask) * (sqrt(a_n) img + sqrt(1-a_n) noise) + mask * x'       (a_n: alpha-bar at t_{i+1})
+ * coef: device array [n_steps, 4] = {sqrt(a_t), sqrt(1-a_t), sqrt(a_p), sqrt(1-a_p)}; blend_coef [n_steps, 2]
+ * = {sqrt(a_n), sqrt(1-a_n)} (last row {1, 0}).  step_ptr points at TWO device int32: [0] the step index, read
+ * on the device and incremented by the kernel (so one captured CUDA graph replays all steps), [1] a scratch
+ * counter the caller zero-initialises once.  All tensors fp32 NCHW [NB,4,h,w];
+ * mask is [NB,1,h,w]. */
+int imagd_cfg_ddim_step(const float* eps_cond, const float* eps_uncond, float guidance, float* latents,
+                        const float* coef, int32_t* step_ptr, const float* mask, const float* image_latents,
+                        const float* noise, const float* blend_coef, int NB, int C, int HW,
+                        imagd_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMAGD_B200_H */

@@ -1,0 +1,163 @@
+"""GPU parity: GroupNorm(+SiLU), LayerNorm, concat/add, upsample, im2col, direct convs, time embedding, small-M
+linear, CFG + DDIM step (through the C ABI) vs the fp32 oracle ops."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+from oracle import ops_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, dev, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev)
+
+
+@pytest.mark.parametrize(
+    "NB,H,W,C,silu,eps",
+    [(1, 64, 64, 320, True, 1e-5), (2, 32, 32, 640, True, 1e-5), (2, 16, 16, 1920, True, 1e-5),
+     (3, 8, 8, 2560, True, 1e-5), (1, 8, 8, 1280, False, 1e-6), (1, 64, 64, 960, True, 1e-5),
+     (1, 12, 9, 1280, True, 1e-5)],
+)
+def test_groupnorm(cuda_device, NB, H, W, C, silu, eps):
+    from imagdressing_b200 import ops
+
+    x = (_rand((NB, H, W, C), cuda_device, 1) * 1.5 + 0.3).bfloat16()
+    gamma = 1.0 + 0.1 * _rand((C,), cuda_device, 2)
+    beta = 0.1 * _rand((C,), cuda_device, 3)
+    out = ops.groupnorm(x, gamma, beta, 32, eps, silu=silu)
+    ref = ops_ref.groupnorm_ref(x, gamma, beta, 32, eps, silu)
+    assert rel_l2(out, ref) < 5e-3
+
+
+@pytest.mark.parametrize("rows,C", [(4096, 320), (1024, 640), (77, 768), (257, 1280), (16, 768), (3, 2048)])
+def test_layernorm(cuda_device, rows, C):
+    from imagdressing_b200 import ops
+
+    x = (_rand((rows, C), cuda_device, 4) * 2 - 0.5).bfloat16()
+    gamma = 1.0 + 0.1 * _rand((C,), cuda_device, 5)
+    beta = 0.1 * _rand((C,), cuda_device, 6)
+    out = ops.layernorm(x, gamma, beta, 1e-5)
+    assert rel_l2(out, ops_ref.layernorm_ref(x, gamma, beta)) < 5e-3
+
+
+def test_concat_add(cuda_device):
+    from imagdressing_b200 import ops
+
+    a = _rand((2, 16, 16, 1280), cuda_device, 7).bfloat16()
+    b = _rand((2, 16, 16, 640), cuda_device, 8).bfloat16()
+    rb = _rand((2, 16, 16, 640), cuda_device, 9).bfloat16()
+    out = ops.concat_add(a, b, res_b=rb)
+    ref = torch.cat([a.float(), b.float() + rb.float()], -1)
+    assert out.shape == (2, 16, 16, 1920)
+    assert rel_l2(out, ref) < 4e-3
+    assert torch.equal(out[..., :1280], a)  # pure copy half is bit-exact
+    ra = _rand((2, 16, 16, 1280), cuda_device, 10).bfloat16()
+    out2 = ops.concat_add(a, None, res_a=ra)
+    assert rel_l2(out2, a.float() + ra.float()) < 4e-3
+
+
+def test_upsample_and_im2col_bit_exact(cuda_device):
+    from imagdressing_b200 import ops
+
+    x = _rand((2, 8, 8, 64), cuda_device, 11).bfloat16()
+    up = ops.upsample2x(x)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up.float(), ref)
+    col = ops.im2col3x3_s2(x)  # [2, 4, 4, 9*64]
+    w = _rand((32, 64, 3, 3), cuda_device, 12, 0.05).bfloat16()
+    y = col.float().reshape(-1, 9 * 64) @ ops_ref.conv3x3_pack(w).float().t()
+    ref = ops_ref.conv3x3_ref(x, w, stride=2).reshape(-1, 32)
+    assert rel_l2(y, ref) < 1e-5
+
+
+def test_downsample_conv_via_im2col_gemm(cuda_device):
+    from imagdressing_b200 import ops
+
+    x = _rand((2, 32, 32, 320), cuda_device, 13).bfloat16()
+    w = _rand((320, 320, 3, 3), cuda_device, 14, 2880 ** -0.5).bfloat16()
+    bias = _rand((320,), cuda_device, 15)
+    col = ops.im2col3x3_s2(x)
+    out = ops.gemm(col.view(-1, 9 * 320), ops_ref.conv3x3_pack(w), bias=bias)
+    ref = ops_ref.conv3x3_ref(x, w, bias, stride=2).reshape(-1, 320)
+    assert rel_l2(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("Cin,Cout,stride,act,nchw", [(4, 320, 1, 0, False), (320, 4, 1, 0, True), (3, 16, 1, 2, False),
+                                                     (16, 32, 2, 2, False), (96, 256, 2, 2, False)])
+def test_conv3x3_direct(cuda_device, Cin, Cout, stride, act, nchw):
+    from imagdressing_b200 import ops
+
+    x = _rand((2, 16, 16, Cin), cuda_device, 16).bfloat16()
+    w = _rand((Cout, Cin, 3, 3), cuda_device, 17, (9 * Cin) ** -0.5).bfloat16()
+    bias = _rand((Cout,), cuda_device, 18)
+    out = ops.conv3x3_direct(x, ops_ref.conv3x3_pack(w), bias, stride=stride, act=act, out_nchw_f32=nchw)
+    ref = ops_ref.conv3x3_ref(x, w, bias, stride=stride)
+    if act == 2:
+        ref = F.silu(ref)
+    if nchw:
+        assert out.dtype == torch.float32
+        assert rel_l2(out, ref.permute(0, 3, 1, 2)) < 1e-4
+    else:
+        assert rel_l2(out, ref) < 5e-3
+
+
+def test_layout_and_time_embedding(cuda_device):
+    from imagdressing_b200 import ops
+
+    lat = _rand((2, 4, 64, 64), cuda_device, 19)
+    y = ops.nchw_f32_to_nhwc_bf16(lat, 8)
+    assert y.shape == (2, 64, 64, 8)
+    assert torch.equal(y[..., :4].float(), lat.permute(0, 2, 3, 1).bfloat16().float())
+    assert float(y[..., 4:].abs().max()) == 0.0
+    ts = torch.tensor([981.0, 961.0, 1.0], device=cuda_device)
+    step = torch.tensor([1, 0], device=cuda_device, dtype=torch.int32)
+    emb = ops.timestep_embedding(ts, step, 2, 320)
+    ref = ops_ref.timestep_embedding_ref(ts[1:2].expand(2), 320)
+    assert float((emb - ref).abs().max()) < 2e-4
+
+
+def test_linear_small_m(cuda_device):
+    from imagdressing_b200 import ops
+
+    x = _rand((5, 1280), cuda_device, 20)
+    w = _rand((2048, 1280), cuda_device, 21, 1280 ** -0.5).bfloat16()
+    b = _rand((2048,), cuda_device, 22)
+    out = ops.linear_small_m(x, w, b, act_in=ops.ACT_SILU, act_out=ops.ACT_SILU)
+    ref = F.silu(F.silu(x) @ w.float().t() + b)
+    assert rel_l2(out, ref) < 1e-4
+    x17 = _rand((17, 320), cuda_device, 23)
+    w2 = _rand((1280, 320), cuda_device, 24, 0.05).bfloat16()
+    assert rel_l2(ops.linear_small_m(x17, w2, None), x17 @ w2.float().t()) < 1e-4
+
+
+def test_cfg_ddim_step_and_counter(cuda_device):
+    from imagdressing_b200 import ops
+
+    dev = cuda_device
+    lat = _rand((2, 4, 64, 64), dev, 25)
+    ec, eu = _rand((2, 4, 64, 64), dev, 26), _rand((2, 4, 64, 64), dev, 27)
+    a = [(0.30, 0.35), (0.35, 0.42)]
+    coef = torch.tensor([[math.sqrt(t), math.sqrt(1 - t), math.sqrt(p), math.sqrt(1 - p)] for t, p in a], device=dev)
+    step = torch.zeros(2, device=dev, dtype=torch.int32)
+    x = lat.clone()
+    ref = lat.clone()
+    for i in range(2):
+        ops.cfg_ddim_step(ec, eu, 7.5, x, coef, step)
+        ref = ops_ref.ddim_step_ref(ec, eu, 7.5, ref, *a[i])
+    assert int(step[0]) == 2 and int(step[1]) == 0
+    assert rel_l2(x, ref) < 1e-5
+    # inpaint blend
+    mask = (torch.rand(2, 1, 64, 64, device=dev) > 0.5).float()
+    img, noise = _rand((2, 4, 64, 64), dev, 28), _rand((2, 4, 64, 64), dev, 29)
+    bc = torch.tensor([[0.8, 0.6], [1.0, 0.0]], device=dev)
+    step.zero_()
+    x = lat.clone()
+    ops.cfg_ddim_step(ec, eu, 5.0, x, coef, step, mask=mask, image_latents=img, noise=noise, blend_coef=bc)
+    r = ops_ref.ddim_step_ref(ec, eu, 5.0, lat, *a[0])
+    r = (1 - mask) * (0.8 * img + 0.6 * noise) + mask * r
+    assert rel_l2(x, r) < 1e-5
