@@ -40,6 +40,7 @@ class KVStream(Structure):
         ("v", c_void_p),
         ("ld", c_int64),
         ("len", c_int32),
+        ("sample_rows", c_int32),
         ("broadcast", c_int32),
         ("n_query_samples", c_int32),
         ("out_scale", c_float),

@@ -300,11 +300,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 // ------------------------------------------------------------------------------------------------ host side
 
-static int make_head_tmap(CUtensorMap* tm, const void* base, int64_t ld, int hd, int heads, int len, int nsamples) {
+static int make_head_tmap(CUtensorMap* tm, const void* base, int64_t ld, int hd, int heads, int len, int nsamples,
+                          int sample_rows = 0) {
     uint64_t dims[4] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(heads), static_cast<uint64_t>(len),
                         static_cast<uint64_t>(nsamples)};
     uint64_t strides[3] = {static_cast<uint64_t>(hd) * 2, static_cast<uint64_t>(ld) * 2,
-                           static_cast<uint64_t>(ld) * 2 * len};
+                           static_cast<uint64_t>(ld) * 2 * (sample_rows > 0 ? sample_rows : len)};
     uint32_t box[4] = {64, 1, 128, 1};
     return make_tmap_bf16(tm, base, 4, dims, strides, box);
 }
@@ -337,6 +338,7 @@ extern "C" int imagd_attention_bf16(const void* q, int64_t q_ld, void* out, int6
                     "attention: head_dim %d not in {40, 64, 80, 160}", head_dim);
     IMAGD_CHECK_ARG(s0->len > 0 && s0->n_query_samples >= B, "attention: stream 0 must cover every query sample");
     IMAGD_CHECK_ARG(out_ld % 8 == 0 && aligned16(out), "attention: output alignment");
+    IMAGD_CHECK_ARG(s0->sample_rows == 0 || s0->sample_rows >= s0->len, "attention: sample_rows < len");
     const bool has1 = s1 != nullptr && s1->k != nullptr && s1->len > 0 && s1->n_query_samples > 0;
 
     AttnParams p;
@@ -359,15 +361,15 @@ extern "C" int imagd_attention_bf16(const void* q, int64_t q_ld, void* out, int6
     CUtensorMap tms[5];
     int rc = make_head_tmap(&tms[0], q, q_ld, head_dim, heads, Lq, B);
     if (rc != IMAGD_OK) return rc;
-    rc = make_head_tmap(&tms[1], s0->k, s0->ld, head_dim, heads, s0->len, s0->broadcast ? 1 : B);
+    rc = make_head_tmap(&tms[1], s0->k, s0->ld, head_dim, heads, s0->len, s0->broadcast ? 1 : B, s0->sample_rows);
     if (rc != IMAGD_OK) return rc;
-    rc = make_head_tmap(&tms[2], s0->v, s0->ld, head_dim, heads, s0->len, s0->broadcast ? 1 : B);
+    rc = make_head_tmap(&tms[2], s0->v, s0->ld, head_dim, heads, s0->len, s0->broadcast ? 1 : B, s0->sample_rows);
     if (rc != IMAGD_OK) return rc;
     if (has1) {
         const int ns = s1->broadcast ? 1 : p.nq[1];
-        rc = make_head_tmap(&tms[3], s1->k, s1->ld, head_dim, heads, s1->len, ns);
+        rc = make_head_tmap(&tms[3], s1->k, s1->ld, head_dim, heads, s1->len, ns, s1->sample_rows);
         if (rc != IMAGD_OK) return rc;
-        rc = make_head_tmap(&tms[4], s1->v, s1->ld, head_dim, heads, s1->len, ns);
+        rc = make_head_tmap(&tms[4], s1->v, s1->ld, head_dim, heads, s1->len, ns, s1->sample_rows);
         if (rc != IMAGD_OK) return rc;
     } else {
         tms[3] = tms[1];

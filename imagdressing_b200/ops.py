@@ -86,9 +86,12 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, out: Optional[torch.Tensor] = N
     return out
 
 
-def kv_stream(k: torch.Tensor, v: torch.Tensor, length: int, *, broadcast: bool = False, n_query_samples: int = 1 << 30,
-              out_scale: float = 1.0) -> KVStream:
+def kv_stream(k: torch.Tensor, v: torch.Tensor, length: int, *, sample_rows: int = 0, broadcast: bool = False,
+              n_query_samples: int = 1 << 30, out_scale: float = 1.0) -> KVStream:
+    """k / v: 2-D views [rows, C] whose row 0 is the first visited key of sample 0; `sample_rows` = rows between
+    samples when that differs from `length` (a window of a longer context)."""
     s = KVStream()
+    s.sample_rows = int(sample_rows)
     assert k.stride(-1) == 1 and v.stride(-1) == 1 and k.dtype == BF16 and v.dtype == BF16
     ld = k.stride(-2)
     assert v.stride(-2) == ld

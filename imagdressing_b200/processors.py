@@ -1,0 +1,192 @@
+"""CUDA implementations behind the reference's attention-processor plugin API.
+
+`attention_forward` is the one routine all processors share: projection GEMMs (tcgen05), the two-stream attention
+kernel, and the output projection with bias (+ the transformer block's residual when the caller offered it).
+What differs per processor is only which weights are merged (LoRA) and what the second KV stream is:
+
+  RefSAttnProcessor2_0      self stream + garment stream (to_k_ref/to_v_ref of the cached garment features)
+  LoRAIPAttnProcessor2_0    text stream + IP-token stream (to_k_ip/to_v_ip of the last num_tokens context tokens)
+  CAttnProcessor2_0 / AttnProcessor2_0 / CacheAttnProcessor2_0   one stream
+
+Work that the reference repeats every denoising step but that does not depend on the step is done once and
+cached by tensor identity: text K/V projections, garment K/V projections, LoRA-merged weights
+(W' = W + lora_scale * up @ down).
+
+Reference: adapter/attention_processor.py (RefS :513-627, LoraRefS :391-511, C :202-295, LoRAIP :746-871,
+Cache :13-100, RefLoraS :1006-1128).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+BF16 = torch.bfloat16
+
+
+class TensorMemo:
+    """One-entry memo keyed by tensor identity + in-place version (holds a reference so the address cannot be
+    recycled under it)."""
+
+    __slots__ = ("src", "ver", "extra", "val")
+
+    def __init__(self):
+        self.src = None
+        self.ver = -1
+        self.extra = None
+        self.val = None
+
+    def get(self, t: torch.Tensor, extra=None):
+        if self.src is not None and self.src is t and self.ver == t._version and self.extra == extra:
+            return self.val
+        return None
+
+    def put(self, t: torch.Tensor, val, extra=None):
+        self.src, self.ver, self.extra, self.val = t, t._version, extra, val
+        return val
+
+    def clear(self):
+        self.src = self.val = None
+
+
+def as_bf16(t: torch.Tensor, memo: Optional[TensorMemo] = None) -> torch.Tensor:
+    if t.dtype == BF16 and t.is_contiguous():
+        return t
+    if memo is not None:
+        v = memo.get(t)
+        if v is not None:
+            return v
+        return memo.put(t, t.to(BF16).contiguous())
+    return t.to(BF16).contiguous()
+
+
+def _w(lin: nn.Linear) -> torch.Tensor:
+    return lin.weight.detach().float()
+
+
+def _merged(lin: nn.Linear, lora, lora_scale: float) -> torch.Tensor:
+    """W + lora_scale * up @ down (network_alpha is None everywhere in the reference)."""
+    w = _w(lin)
+    if lora is not None and lora_scale != 0.0:
+        w = w + float(lora_scale) * (lora.up.weight.detach().float() @ lora.down.weight.detach().float())
+    return w
+
+
+def _flat(t: torch.Tensor) -> torch.Tensor:
+    """[B, L, C] -> [B*L, C] view (keeps a column-slice's row stride)."""
+    B, L, C = t.shape
+    return t.as_strided((B * L, C), (t.stride(1), 1), t.storage_offset())
+
+
+class _ProcState:
+    """Mixin: caches owned by a processor instance."""
+
+    def _init_state(self):
+        self._ctx_memo = TensorMemo()   # context tensor -> bf16 copy
+        self._kv_memo = TensorMemo()    # context tensor -> projected K|V
+        self._kv2_memo = TensorMemo()   # second stream source -> projected K|V
+        self._g_memo = TensorMemo()     # garment feature tensor -> bf16 copy
+
+    def invalidate_packed(self):
+        for m in (self._ctx_memo, self._kv_memo, self._kv2_memo, self._g_memo):
+            m.clear()
+
+
+def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor], *,
+                      lora: Optional[dict] = None, lora_scale: float = 0.0,
+                      second: Optional[tuple] = None, text_len: Optional[int] = None) -> torch.Tensor:
+    """hidden_states [B, L, C]; returns [B, L, C] in hidden_states.dtype.
+
+    second = (source [Bs, Ls, Cs], to_k, to_v, out_scale, n_query_samples[, first, length]): the extra KV stream,
+    optionally a [first, first+length) token window of the source.
+    text_len: use only the first text_len context tokens for stream 0 (LoRAIP strips the IP tokens, :811-815).
+    """
+    in_dtype = hidden_states.dtype
+    B, L, C = hidden_states.shape
+    heads = attn.heads
+    hd = C // heads
+    x = as_bf16(hidden_states)
+    lkey = f"{id(proc)}:{lora_scale}" if lora else "base"
+
+    if encoder_hidden_states is None:
+        wqkv = attn.packed("qkv:" + lkey, lambda: torch.cat(
+            [_merged(attn.to_q, lora and lora["q"], lora_scale), _merged(attn.to_k, lora and lora["k"], lora_scale),
+             _merged(attn.to_v, lora and lora["v"], lora_scale)], 0).to(BF16).contiguous())
+        qkv = ops.gemm(x, wqkv)  # [B, L, 3C]
+        q2 = _flat(qkv[..., :C])
+        s0 = ops.kv_stream(_flat(qkv[..., C:2 * C]), _flat(qkv[..., 2 * C:]), L)
+    else:
+        wq = attn.packed("q:" + lkey, lambda: _merged(attn.to_q, lora and lora["q"], lora_scale).to(BF16).contiguous())
+        q2 = _flat(ops.gemm(x, wq))
+        ctx_src = encoder_hidden_states
+        Lc = ctx_src.shape[1] if text_len is None else text_len
+        kv = proc._kv_memo.get(ctx_src, (lkey, Lc))
+        if kv is None:
+            wkv = attn.packed("kv:" + lkey, lambda: torch.cat(
+                [_merged(attn.to_k, lora and lora["k"], lora_scale), _merged(attn.to_v, lora and lora["v"], lora_scale)],
+                0).to(BF16).contiguous())
+            ctx = as_bf16(ctx_src, proc._ctx_memo)
+            kv = proc._kv_memo.put(ctx_src, ops.gemm(ctx, wkv), (lkey, Lc))  # [B, Lctx, 2C]; rows >= Lc unused
+        # per-sample row stride stays the full context length; only the first Lc keys are visited
+        s0 = _stream_from_kv(kv, C, Lc)
+
+    s1 = None
+    if second is not None:
+        src, to_k, to_v, out_scale, n_q = second[:5]
+        first = second[5] if len(second) > 5 else 0
+        kv2 = proc._kv2_memo.get(src, id(to_k))
+        if kv2 is None:
+            w2 = attn.packed(f"kv2:{id(to_k)}", lambda: torch.cat([_w(to_k), _w(to_v)], 0).to(BF16).contiguous())
+            kv2 = proc._kv2_memo.put(src, ops.gemm(as_bf16(src, proc._g_memo), w2), id(to_k))
+        bcast = kv2.shape[0] == 1 and n_q > 1
+        if not bcast and kv2.shape[0] < n_q:
+            raise ValueError(f"second KV stream has batch {kv2.shape[0]} but {n_q} query samples use it")
+        length = second[6] if len(second) > 6 else kv2.shape[1] - first
+        s1 = _stream_from_kv(kv2, C, length, first, broadcast=bcast, n_query_samples=n_q, out_scale=out_scale)
+
+    o = ops.attention(q2, B, L, heads, hd, s0, s1)  # [B*L, C]
+
+    wo = attn.packed("o:" + lkey, lambda: _merged(attn.to_out[0], lora and lora["out"], lora_scale).to(BF16).contiguous())
+    bo = attn.packed("bo", lambda: attn.to_out[0].bias.detach().float().contiguous())
+    residual = attn._fused_residual
+    if residual is not None and residual.dtype == BF16 and residual.shape == hidden_states.shape:
+        attn._fused_residual = None  # consumed: fused into the out-projection epilogue
+        y = ops.gemm(o, wo, bias=bo, residual=residual.reshape(B * L, C))
+    else:
+        y = ops.gemm(o, wo, bias=bo)
+    y = y.view(B, L, C)
+    return y if in_dtype == BF16 else y.to(in_dtype)
+
+
+def _stream_from_kv(kv: torch.Tensor, C: int, length: int, first: int = 0, **kw):
+    """kv: [Bk, Lk, 2C] fused K|V projection; the stream visits keys [first, first+length) of each sample."""
+    Bk, Lk, _ = kv.shape
+    ld = kv.stride(1)
+    off = kv.storage_offset() + first * ld
+    k = kv.as_strided((Bk * Lk - first, C), (ld, 1), off)
+    v = kv.as_strided((Bk * Lk - first, C), (ld, 1), off + C)
+    return ops.kv_stream(k, v, length, sample_rows=Lk if length != Lk else 0, **kw)
+
+
+# ------------------------------------------------------------------------------------------------ processors
+class AttnProcessor2_0(_ProcState):
+    """Default processor: plain SDPA (diffusers-0.24 AttnProcessor2_0)."""
+
+    def __init__(self):
+        self._init_state()
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
+                 **kwargs):
+        return attention_forward(self, attn, hidden_states, encoder_hidden_states)
+
+
+def ref_stream(proc, hidden_states, sa_hidden_states, ref_samples):
+    """(source, to_k_ref, to_v_ref, scale, n_query_samples) or None — adapter/attention_processor.py:597-612."""
+    if sa_hidden_states is None:
+        return None
+    g = sa_hidden_states[proc.name]
+    n_q = hidden_states.shape[0] if ref_samples is None else int(ref_samples)
+    return (g, proc.to_k_ref, proc.to_v_ref, float(proc.scale), n_q)

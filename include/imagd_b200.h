@@ -78,6 +78,8 @@ typedef struct imagd_kv_stream {
     const void* v;
     int64_t ld;
     int32_t len;             /* keys per sample */
+    int32_t sample_rows;     /* rows between consecutive samples in k / v (0: = len); > len lets a stream visit a
+                                prefix or suffix window of a longer per-sample context (text vs IP tokens) */
     int32_t broadcast;       /* 1: one KV sample shared by all query samples (garment dressed on a batch) */
     int32_t n_query_samples; /* query samples [0, n) use this stream */
     float out_scale;         /* weight of this stream's softmax output */

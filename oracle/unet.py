@@ -406,18 +406,24 @@ class ControlNetModel(nn.Module, _AttnProcessorMixin):
         return down, mid
 
 
-def init_synthetic_(model: nn.Module, seed: int = 0, std: float = 0.02) -> nn.Module:
-    """Deterministic synthetic weights for parity/bench (no checkpoint offline): N(0, std) for conv/linear weights
-    scaled to keep activations O(1) through 60 layers, small random biases, GN/LN gamma=1+noise. Not the
-    reference's init — any fixed non-degenerate weights serve parity."""
-    g = torch.Generator().manual_seed(seed)
+def init_synthetic_(model: nn.Module, seed: int = 0) -> nn.Module:
+    """Deterministic synthetic weights (no checkpoints offline): each parameter is drawn from a
+    generator seeded by (seed, crc32(parameter name)), so any two module trees with the same state_dict keys get
+    identical values regardless of registration order. Fan-in scaled N(0, 1/fan_in) for matrices / convs, small
+    biases, norm gamma ~ 1 — keeps activations O(1) through the 60-odd layers."""
+    import math
+    import zlib
+
     with torch.no_grad():
         for name, p in model.named_parameters():
+            g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 63))
             if p.dim() >= 2:
-                fan_in = p[0].numel()
-                p.copy_(torch.randn(p.shape, generator=g) * (1.0 / math.sqrt(fan_in)))
+                v = torch.randn(p.shape, generator=g) * (1.0 / math.sqrt(p[0].numel()))
             elif "norm" in name and name.endswith("weight"):
-                p.copy_(1.0 + 0.05 * torch.randn(p.shape, generator=g))
+                v = 1.0 + 0.05 * torch.randn(p.shape, generator=g)
             else:
-                p.copy_(0.02 * torch.randn(p.shape, generator=g))
+                v = 0.02 * torch.randn(p.shape, generator=g)
+            p.copy_(v.to(p.dtype))
+    if hasattr(model, "invalidate_packed"):
+        model.invalidate_packed()
     return model
