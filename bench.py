@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of IMAGDressing-v1 garment-conditioned sampling (512x512, 50 DDIM steps, CFG) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic inputs: garment-UNet pass + 50 x (CFG-batched
+denoising UNet + fused CFG/DDIM). Workload at N=1 = BASELINE.json configs[1]: batch-1 512x512 50-step sampling,
+random-init SD1.5 + garment UNet (no checkpoints offline). `value` = images/s with inputs resident in HBM (device
+events, max over ranks); `e2e` = the same through the public pipeline call (dressing_sd.pipelines ... IMAGDressing_v1)
+with pinned HOST inputs, H2D and D2H copies inside the timed region. `roofline` = the dominant kernel timed in
+isolation with CUDA events against MEASURED_PEAKS.json; `cpu_baseline` = the fp32 oracle on the host cores on a
+bounded sample. `--impl reference` times the reference's CPU PyTorch path (oracle port) only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+HW = 64  # 512 / 8
+STEPS_DDIM = 50
+GUIDANCE = 7.5
+# analytic work model: TFLOP per 512x512 image = 50 x (0.951 + 0.803) + 0.803
+TFLOP_PER_IMAGE = 50 * (0.951 + 0.803) + 0.803
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1, help="images per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ model builders
+def build_product(dev):
+    from adapter.attention_processor import CacheAttnProcessor2_0, CAttnProcessor2_0, RefSAttnProcessor2_0
+    from dressing_sd.pipelines.IMAGDressing_v1_pipeline import IMAGDressing_v1
+    from imagdressing_b200 import modeling
+    from imagdressing_b200.scheduler import DDIMScheduler
+
+    unet = modeling.UNet2DConditionModel().to(dev, torch.bfloat16)
+    procs = {}
+    for name in unet.attn_processors.keys():  # inference_IMAGdressing.py:70-85
+        if name.startswith("mid_block"):
+            hidden = unet.config.block_out_channels[-1]
+        elif name.startswith("up_blocks"):
+            hidden = list(reversed(unet.config.block_out_channels))[int(name[len("up_blocks.")])]
+        else:
+            hidden = unet.config.block_out_channels[int(name[len("down_blocks.")])]
+        procs[name] = (RefSAttnProcessor2_0(name, hidden) if name.endswith("attn1.processor")
+                       else CAttnProcessor2_0(name, hidden, unet.config.cross_attention_dim))
+    unet.set_attn_processor(procs)
+    unet.to(dev, torch.bfloat16)
+    ref = modeling.UNet2DConditionModel().to(dev, torch.bfloat16)
+    ref.set_attn_processor({n: CacheAttnProcessor2_0() for n in ref.attn_processors.keys()})  # :90-94
+    modeling.init_synthetic_fast_(unet, 0)
+    modeling.init_synthetic_fast_(ref, 1)
+    sched = DDIMScheduler(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                          clip_sample=False, set_alpha_to_one=False, steps_offset=1)  # :119-127
+    pipe = IMAGDressing_v1(vae=None, reference_unet=ref, unet=unet, tokenizer=None, text_encoder=None,
+                           image_encoder=None, ImgProj=None, scheduler=sched, safety_checker=None, feature_extractor=None)
+    return pipe
+
+
+def synth_inputs(B, dev, rank=0, pinned=False):
+    """SURVEY.md §8d synthetic inputs; per-rank seeds derive from the global sample index."""
+    g = torch.Generator().manual_seed(42 + 1000 * rank)
+    t = dict(latents=torch.randn(B, 4, HW, HW, generator=g), garment=torch.randn(B, 4, HW, HW, generator=g) * 0.18215 * 5,
+             prompt=torch.randn(B, 77, 768, generator=g), negative=torch.randn(B, 77, 768, generator=g),
+             gtok=torch.randn(B, 16, 768, generator=g))
+    if pinned:
+        return {k: v.pin_memory() for k, v in t.items()}
+    return {k: v.to(dev) for k, v in t.items()}
+
+
+def run_pipe(pipe, x):
+    return pipe(prompt=None, null_prompt=None, negative_prompt=None, ref_image=None, width=HW * 8, height=HW * 8,
+                num_inference_steps=STEPS_DDIM, guidance_scale=GUIDANCE, image_scale=1.0, output_type="latent",
+                prompt_embeds=x["prompt"], negative_prompt_embeds=x["negative"], latents=x["latents"],
+                garment_tokens=x["gtok"], ref_image_latents=x["garment"]).images
+
+
+# ------------------------------------------------------------------------------------------------ roofline legs
+def kernel_roofline(dev, B):
+    """Time the two dominant kernels alone (CUDA events on the launching stream, L2 flushed between launches):
+    level-0 hybrid attention (the CFG batch: B cond samples with garment stream + B uncond) and the level-0 3x3
+    conv. Algorithmic FLOPs: attention 4*L*Lkv*C per stream per sample; conv 2*pixels*9*Cin*Cout."""
+    from imagdressing_b200 import ops
+
+    hbm, tf_burst, tf_sus, src = peaks()
+    flush = torch.empty(160 * 1024 * 1024, device=dev, dtype=torch.int32)  # 640 MB > 126 MB L2
+
+    def timeit(fn, iters=10):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sum(ts) / len(ts)
+
+    L, C, heads, hd, NB = HW * HW, 320, 8, 40, 2 * B
+    qkv = torch.randn(NB, L, 3 * C, device=dev).bfloat16()
+    kvr = torch.randn(B, L, 2 * C, device=dev).bfloat16()
+    flat = lambda t: t.as_strided((t.shape[0] * t.shape[1], t.shape[2]), (t.stride(1), 1), t.storage_offset())
+    s0 = ops.kv_stream(flat(qkv[..., C:2 * C]), flat(qkv[..., 2 * C:]), L)
+    s1 = ops.kv_stream(flat(kvr[..., :C]), flat(kvr[..., C:]), L, n_query_samples=B, out_scale=1.0)
+    out = torch.empty(NB * L, C, device=dev, dtype=torch.bfloat16)
+    ms_attn = timeit(lambda: ops.attention(flat(qkv[..., :C]), NB, L, heads, hd, s0, s1, out=out))
+    flops_attn = 4.0 * L * L * C * (NB + B)  # NB self streams + B garment streams
+    x = torch.randn(NB, HW, HW, C, device=dev).bfloat16()
+    w = (torch.randn(C, 9 * C, device=dev) * 0.02).bfloat16()
+    y = torch.empty(NB, HW, HW, C, device=dev, dtype=torch.bfloat16)
+    ms_conv = timeit(lambda: ops.conv3x3(x, w, out=y))
+    flops_conv = 2.0 * NB * L * 9 * C * C
+    res = {}
+    for name, ms, fl in (("hybrid_attention_l0", ms_attn, flops_attn), ("conv3x3_l0", ms_conv, flops_conv)):
+        ach = fl / (ms * 1e-3) / 1e12
+        res[name] = {"bound": "tensor", "achieved": round(ach, 2), "peak": tf_burst, "unit": "TFLOP/s",
+                     "frac": round(ach / tf_burst, 4), "traffic": None, "ms": round(ms, 4), "peak_source": src}
+    return res
+
+
+def cpu_baseline(sample_forwards=4, threads=None):
+    """The fp32 oracle (reference processors restated; oracle/unet.py) on the host cores: `sample_forwards` UNet
+    forwards of the B=1 512x512 workload (half conditional with the garment stream, half unconditional), scaled to
+    101 forwards per image (50 x 2 + 1 garment pass)."""
+    from oracle import processors as op
+    from oracle import unet as ou
+
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    with torch.no_grad():
+        o = ou.UNet2DConditionModel()
+        po = {}
+        for name in o.attn_processors:
+            hidden = {"mid": 1280, "up_blocks.1": 1280, "up_blocks.2": 640, "up_blocks.3": 320, "down_blocks.0": 320,
+                      "down_blocks.1": 640, "down_blocks.2": 1280}[next(k for k in (
+                          "mid", "up_blocks.1", "up_blocks.2", "up_blocks.3", "down_blocks.0", "down_blocks.1",
+                          "down_blocks.2") if name.startswith(k))]
+            po[name] = op.RefSAttnProcessor(name, hidden) if "attn1" in name else op.CAttnProcessor(name, hidden, 768)
+        o.set_attn_processor(po)
+        g = torch.Generator().manual_seed(0)
+        for p in o.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+        lat, txt = torch.randn(1, 4, HW, HW, generator=g), torch.randn(1, 77, 768, generator=g)
+        Ls = {320: HW * HW, 640: HW * HW // 4, 1280: HW * HW // 16}
+        sa = {}
+        for name, p in po.items():
+            if "attn1" in name:
+                C = p.to_k_ref.weight.shape[0]
+                Lr = HW * HW // 64 if name.startswith("mid") else Ls[C]
+                sa[name] = torch.randn(1, Lr, C, generator=g)
+        t = torch.tensor(981)
+        o(lat, t, txt)  # warm
+        t0 = time.perf_counter()
+        for i in range(sample_forwards):
+            if i % 2 == 0:
+                o(lat, t, txt, cross_attention_kwargs={"sa_hidden_states": sa})
+            else:
+                o(lat, t, txt)
+        dt = time.perf_counter() - t0
+    per_fwd = dt / sample_forwards
+    img_s = 1.0 / (per_fwd * (2 * STEPS_DDIM + 1))
+    return {"value": round(img_s, 6), "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": f"{sample_forwards} fp32 UNet forwards (B=1, 512x512; alternating hybrid/plain) = {dt:.1f} s, "
+                      f"scaled to {2 * STEPS_DDIM + 1} forwards/image", "s_per_forward": round(per_fwd, 3)}
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        ms = []
+        cb = None
+        for i in range(a.warmup + a.steps):
+            cb = cpu_baseline(sample_forwards=2)
+            if i >= a.warmup:
+                ms.append(1000.0 / cb["value"])
+        v = 1000.0 / (sum(ms) / len(ms))
+        cb["value"] = round(v, 6)
+        print(json.dumps({"impl": "reference", "metric": "images/sec, 512x512 50-step DDIM garment-conditioned (CFG)",
+                          "value": round(v, 6), "unit": "images/s", "n_gpus": 0, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": round(sum(ms) / len(ms), 1), "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "batch-1 512x512 50-step DDIM, CFG 7.5, random-init SD1.5 + garment UNet "
+                                     "(reference CPU PyTorch path: fp32 oracle port, each step = 2 UNet forwards scaled "
+                                     "to 101/image)", "global_batch": 1},
+                          "cpu_baseline": cb,
+                          "e2e": {"value": round(v, 6), "unit": "images/s", "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch.distributed as dist
+
+    from imagdressing_b200 import _lib
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.require_b200()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = a.batch
+    pipe = build_product(dev)
+    x_dev = synth_inputs(B, dev, rank)
+    x_host = synth_inputs(B, dev, rank, pinned=True)
+    gather_buf = torch.empty(world * B, 4, HW, HW, device=dev) if world > 1 else None
+
+    def one_step(x):
+        out = run_pipe(pipe, x)
+        if world > 1:  # the single collective of the path: all-gather of the output latents over NVLink
+            dist.all_gather_into_tensor(gather_buf, out.contiguous())
+            return gather_buf
+        return out
+
+    def one_step_e2e():
+        x = {k: v.to(dev, non_blocking=True) for k, v in x_host.items()}
+        return one_step(x).to("cpu", non_blocking=False)
+
+    def timed(fn, K):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(a.warmup, 3)):
+        one_step(x_dev)
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+    l0 = _lib.launch_count
+    ms_total = timed(lambda: one_step(x_dev), a.steps)
+    launches = _lib.launch_count - l0
+    clocks = clk.stop() if rank == 0 else None
+    one_step_e2e()
+    ms_e2e = timed(one_step_e2e, a.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    images = world * B * a.steps
+    value = images / (ms_total * 1e-3)
+    e2e_v = images / (ms_e2e * 1e-3)
+    hbm, tf_burst, tf_sus, src = peaks()
+    roofs = kernel_roofline(dev, B)
+    dominant = "conv3x3_l0"
+    roofline = dict(roofs[dominant])
+    roofline["kernel"] = dominant
+    h2d = sum(v.numel() * v.element_size() for v in x_host.values())
+    d2h = world * B * 4 * HW * HW * 4
+    line = {
+        "metric": "images/sec, 512x512 50-step DDIM garment-conditioned (CFG)",
+        "value": round(value, 4), "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": round(ms_total / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"batch-{B}/GPU 512x512 50-step DDIM garment-conditioned sampling, CFG {GUIDANCE} "
+                               "(BASELINE.json configs[1]); random-init SD1.5 denoising UNet + garment UNet; timed "
+                               "region = garment pass + 50 steps (VAE/CLIP excluded)",
+                   "global_batch": world * B, "latent": [HW, HW], "ddim_steps": STEPS_DDIM, "parallelism": f"dp{world}",
+                   "l2": "activations+weights (3.4 GB bf16) exceed the 126 MB L2; no explicit flush between steps"},
+        "e2e": {"value": round(e2e_v, 4), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "clocks": clocks,
+        "model_tflops": round(value / world * TFLOP_PER_IMAGE, 1),
+        "model_frac_of_sustained_bf16": round(value / world * TFLOP_PER_IMAGE / tf_sus, 4),
+        "roofline": roofline, "kernels": roofs,
+    }
+    if not a.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -69,7 +69,7 @@ SIGNATURES = {
     "imagd_im2col3x3_s2_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "imagd_conv3x3_direct_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                           c_int, c_int, c_int, c_void_p, c_void_p]),
-    "imagd_nchw_f32_to_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "imagd_nchw_f32_to_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "imagd_timestep_embedding": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "imagd_linear_small_m": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int,
                                      c_int, c_int, c_int, c_void_p]),
@@ -103,7 +103,17 @@ def load() -> ctypes.CDLL:
     return lib
 
 
+# kernels launched through the C ABI (bench.py reports it as gpu_launches); graph replays add their node count
+LAUNCHES = {"imagd_gemm_bf16": 1, "imagd_conv3x3_bf16": 1, "imagd_attention_bf16": 1, "imagd_groupnorm_bf16": 2,
+            "imagd_layernorm_bf16": 1, "imagd_concat_add_bf16": 1, "imagd_upsample2x_bf16": 1,
+            "imagd_im2col3x3_s2_bf16": 1, "imagd_conv3x3_direct_bf16": 1, "imagd_nchw_f32_to_nhwc_bf16": 1,
+            "imagd_timestep_embedding": 1, "imagd_linear_small_m": 1, "imagd_cfg_ddim_step": 1}
+launch_count = 0
+
+
 def check(rc: int, what: str) -> None:
+    global launch_count
+    launch_count += LAUNCHES.get(what, 0)
     if rc != IMAGD_OK:
         msg = load().imagd_last_error()
         raise ImagdError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")

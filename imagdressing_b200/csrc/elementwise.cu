@@ -162,14 +162,14 @@ __global__ void __launch_bounds__(256) conv3x3_direct_warp_kernel(const __nv_bfl
 }
 
 __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int NB, int C,
-                                             int H, int W, int Cpad) {
-    const int64_t total = static_cast<int64_t>(NB) * H * W * Cpad;
+                                             int H, int W, int Cpad, int repeat) {
+    const int64_t total = static_cast<int64_t>(NB) * repeat * H * W * Cpad;
     for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int c = static_cast<int>(idx % Cpad);
         const int64_t pix = idx / Cpad;
         const int64_t hw = pix % (static_cast<int64_t>(H) * W);
-        const int64_t n = pix / (static_cast<int64_t>(H) * W);
+        const int64_t n = (pix / (static_cast<int64_t>(H) * W)) % NB;
         const float v = c < C ? x[(n * C + c) * H * W + hw] : 0.f;
         y[idx] = __float2bfloat16(v);
     }
@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(256) linear_small_m_kernel(const float* __rest
                 if (m0 + i < M) {
                     float v = acc[i] + (bias ? bias[n] : 0.f);
                     if (act_out == IMAGD_ACT_SILU) v = silu(v);
+                    else if (act_out == IMAGD_ACT_GELU) v = gelu_erf(v);
                     out[static_cast<int64_t>(m0 + i) * ldo + n] = v;
                 }
             }
@@ -360,12 +361,13 @@ int imagd_conv3x3_direct_bf16(const void* x, int NB, int H, int W, int Cin, cons
     return IMAGD_OK;
 }
 
-int imagd_nchw_f32_to_nhwc_bf16(const float* x, void* y, int NB, int C, int H, int W, int Cpad, imagd_stream stream) {
+int imagd_nchw_f32_to_nhwc_bf16(const float* x, void* y, int NB, int C, int H, int W, int Cpad, int repeat,
+                                imagd_stream stream) {
     using namespace imagd;
-    IMAGD_CHECK_ARG(x && y && NB > 0 && C > 0 && Cpad >= C, "nchw_to_nhwc: bad args");
-    const int64_t total = static_cast<int64_t>(NB) * H * W * Cpad;
+    IMAGD_CHECK_ARG(x && y && NB > 0 && C > 0 && Cpad >= C && repeat >= 1, "nchw_to_nhwc: bad args");
+    const int64_t total = static_cast<int64_t>(NB) * repeat * H * W * Cpad;
     nchw_f32_to_nhwc_bf16_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, reinterpret_cast<__nv_bfloat16*>(y), NB, C, H, W, Cpad);
+        x, reinterpret_cast<__nv_bfloat16*>(y), NB, C, H, W, Cpad, repeat);
     IMAGD_LAUNCH_CHECK("nchw_f32_to_nhwc_bf16_kernel");
     return IMAGD_OK;
 }

@@ -16,20 +16,15 @@ __host__ __device__ inline int gn_chunks(int HW) {
 // Partial sums: ws[((n * chunks + chunk) * groups + g) * 2 + {0: sum, 1: sum of squares}]
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int HW,
                                                               int C, int groups, int chunks, float* __restrict__ ws) {
-    __shared__ float s_sum[kGnMaxC];
-    __shared__ float s_sq[kGnMaxC];
+    // per (pixel-row slot, channel) partials, reduced in a fixed order below -> bit-reproducible statistics
+    __shared__ float s_sum[kGnThreads * 8];
+    __shared__ float s_sq[kGnThreads * 8];
     const int n = blockIdx.y, chunk = blockIdx.x;
     const int CV = C / 8;
     const int rows = kGnThreads / CV;  // pixel rows processed per iteration (>= 1 since C <= 2560 < 8*512)
     const int ppc = (HW + chunks - 1) / chunks;
     const int p_begin = chunk * ppc;
     const int p_end = min(HW, p_begin + ppc);
-
-    for (int c = threadIdx.x; c < C; c += kGnThreads) {
-        s_sum[c] = 0.f;
-        s_sq[c] = 0.f;
-    }
-    __syncthreads();
 
     const int cv = threadIdx.x % CV;
     const int prow = threadIdx.x / CV;
@@ -52,9 +47,20 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat1
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            atomicAdd(&s_sum[cv * 8 + k], sum[k]);
-            atomicAdd(&s_sq[cv * 8 + k], sq[k]);
+            s_sum[prow * C + cv * 8 + k] = sum[k];
+            s_sq[prow * C + cv * 8 + k] = sq[k];
         }
+    }
+    __syncthreads();
+    // fold the row slots into slot 0 (fixed order)
+    for (int c = threadIdx.x; c < C; c += kGnThreads) {
+        float a = s_sum[c], b = s_sq[c];
+        for (int r = 1; r < rows; ++r) {
+            a += s_sum[r * C + c];
+            b += s_sq[r * C + c];
+        }
+        s_sum[c] = a;
+        s_sq[c] = b;
     }
     __syncthreads();
     const int cpg = C / groups;

@@ -216,14 +216,14 @@ def conv3x3_direct(x: torch.Tensor, w: torch.Tensor, bias, *, stride: int = 1, a
     return out
 
 
-def nchw_f32_to_nhwc_bf16(x: torch.Tensor, cpad: Optional[int] = None, *, out=None) -> torch.Tensor:
+def nchw_f32_to_nhwc_bf16(x: torch.Tensor, cpad: Optional[int] = None, *, repeat: int = 1, out=None) -> torch.Tensor:
     lib = _lib.load()
     NB, C, H, W = x.shape
     assert x.is_contiguous() and x.dtype == torch.float32
     cpad = cpad or C
     if out is None:
-        out = torch.empty(NB, H, W, cpad, device=x.device, dtype=BF16)
-    _lib.check(lib.imagd_nchw_f32_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), NB, C, H, W, cpad, _stream()),
+        out = torch.empty(NB * repeat, H, W, cpad, device=x.device, dtype=BF16)
+    _lib.check(lib.imagd_nchw_f32_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), NB, C, H, W, cpad, repeat, _stream()),
                "imagd_nchw_f32_to_nhwc_bf16")
     return out
 

@@ -49,7 +49,15 @@ class TensorMemo:
         return val
 
     def clear(self):
-        self.src = self.val = None
+        self.src = None  # keep `val`: its storage is reused so captured CUDA graphs keep valid addresses
+
+    def reusable(self, shape, dtype=BF16):
+        """Previous value's storage when the shape matches — recomputing in place keeps device addresses stable
+        across images, which is what lets one captured step graph be replayed for every image."""
+        v = self.val
+        if v is not None and tuple(v.shape) == tuple(shape) and v.dtype == dtype:
+            return v
+        return None
 
 
 def as_bf16(t: torch.Tensor, memo: Optional[TensorMemo] = None) -> torch.Tensor:
@@ -59,6 +67,10 @@ def as_bf16(t: torch.Tensor, memo: Optional[TensorMemo] = None) -> torch.Tensor:
         v = memo.get(t)
         if v is not None:
             return v
+        buf = memo.reusable(t.shape)
+        if buf is not None:
+            buf.copy_(t)
+            return memo.put(t, buf)
         return memo.put(t, t.to(BF16).contiguous())
     return t.to(BF16).contiguous()
 
@@ -129,7 +141,8 @@ def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_st
                 [_merged(attn.to_k, lora and lora["k"], lora_scale), _merged(attn.to_v, lora and lora["v"], lora_scale)],
                 0).to(BF16).contiguous())
             ctx = as_bf16(ctx_src, proc._ctx_memo)
-            kv = proc._kv_memo.put(ctx_src, ops.gemm(ctx, wkv), (lkey, Lc))  # [B, Lctx, 2C]; rows >= Lc unused
+            buf = proc._kv_memo.reusable((*ctx.shape[:-1], 2 * C))
+            kv = proc._kv_memo.put(ctx_src, ops.gemm(ctx, wkv, out=buf), (lkey, Lc))  # [B, Lctx, 2C]
         # per-sample row stride stays the full context length; only the first Lc keys are visited
         s0 = _stream_from_kv(kv, C, Lc)
 
@@ -140,7 +153,9 @@ def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_st
         kv2 = proc._kv2_memo.get(src, id(to_k))
         if kv2 is None:
             w2 = attn.packed(f"kv2:{id(to_k)}", lambda: torch.cat([_w(to_k), _w(to_v)], 0).to(BF16).contiguous())
-            kv2 = proc._kv2_memo.put(src, ops.gemm(as_bf16(src, proc._g_memo), w2), id(to_k))
+            src_bf = as_bf16(src, proc._g_memo)
+            buf = proc._kv2_memo.reusable((*src_bf.shape[:-1], 2 * C))
+            kv2 = proc._kv2_memo.put(src, ops.gemm(src_bf, w2, out=buf), id(to_k))
         bcast = kv2.shape[0] == 1 and n_q > 1
         if not bcast and kv2.shape[0] < n_q:
             raise ValueError(f"second KV stream has batch {kv2.shape[0]} but {n_q} query samples use it")

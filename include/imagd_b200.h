@@ -126,8 +126,10 @@ int imagd_im2col3x3_s2_bf16(const void* x, void* col, int NB, int H, int W, int 
 int imagd_conv3x3_direct_bf16(const void* x, int NB, int H, int W, int Cin, const void* w, const float* bias,
                               void* y, int Cout, int stride, int act, int out_nchw_f32, const void* add_nhwc,
                               imagd_stream stream);
-/* fp32 NCHW latents -> bf16 NHWC (channels zero-padded to Cpad). */
-int imagd_nchw_f32_to_nhwc_bf16(const float* x, void* y, int NB, int C, int H, int W, int Cpad,
+/* fp32 NCHW latents -> bf16 NHWC (channels zero-padded to Cpad). The output batch is NB * repeat (sample i reads
+ * source i % NB): repeat = 2 builds the CFG-duplicated model input (torch.cat([latents] * 2),
+ * dressing_sd/pipelines/IMAGDressing_v1_pipeline.py:483-485) in the same pass. */
+int imagd_nchw_f32_to_nhwc_bf16(const float* x, void* y, int NB, int C, int H, int W, int Cpad, int repeat,
                                 imagd_stream stream);
 
 /* ---- time conditioning ---- */
