@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 HW = 64  # 512 / 8
-STEPS_DDIM = 50
+STEPS_DDIM = int(os.environ.get("IMAGD_DDIM_STEPS", "50"))  # 50 is the metric; the env knob only shortens ncu runs
 GUIDANCE = 7.5
 # analytic work model: TFLOP per 512x512 image = 50 x (0.951 + 0.803) + 0.803
 TFLOP_PER_IMAGE = 50 * (0.951 + 0.803) + 0.803
@@ -122,6 +122,8 @@ def build_product(dev):
                           clip_sample=False, set_alpha_to_one=False, steps_offset=1)  # :119-127
     pipe = IMAGDressing_v1(vae=None, reference_unet=ref, unet=unet, tokenizer=None, text_encoder=None,
                            image_encoder=None, ImgProj=None, scheduler=sched, safety_checker=None, feature_extractor=None)
+    if os.environ.get("IMAGD_NO_GRAPH"):  # profiling aid: every kernel launched eagerly so ncu lists them
+        pipe._engine.use_cuda_graph = False
     return pipe
 
 
@@ -189,14 +191,33 @@ def kernel_roofline(dev, B):
     return res
 
 
-def cpu_baseline(sample_forwards=4, threads=None):
+def pick_cpu_threads():
+    """torch with one thread per logical CPU thrashes on big hosts: probe a few counts on a conv and keep the best."""
+    import torch.nn.functional as F
+
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    x, w = torch.randn(1, 320, 64, 64), torch.randn(320, 320, 3, 3)
+    best, best_t = 1, 1e9
+    for n in sorted({min(avail, c) for c in (8, 16, 32, 64, 128)}):
+        torch.set_num_threads(n)
+        F.conv2d(x, w, padding=1)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            F.conv2d(x, w, padding=1)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = n, dt
+    return best
+
+
+def cpu_baseline(sample_forwards=2, threads=None):
     """The fp32 oracle (reference processors restated; oracle/unet.py) on the host cores: `sample_forwards` UNet
     forwards of the B=1 512x512 workload (half conditional with the garment stream, half unconditional), scaled to
     101 forwards per image (50 x 2 + 1 garment pass)."""
     from oracle import processors as op
     from oracle import unet as ou
 
-    threads = threads or os.cpu_count() or 1
+    threads = threads or pick_cpu_threads()
     torch.set_num_threads(threads)
     with torch.no_grad():
         o = ou.UNet2DConditionModel()
