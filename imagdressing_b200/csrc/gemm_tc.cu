@@ -12,6 +12,9 @@
 //   warp 1     TMEM allocator + tcgen05.mma issuer (one elected lane; fp32 accumulator in TMEM)
 //   warps 2-5  epilogue: tcgen05.ld -> bias / time-embedding row vector / activation / residual -> bf16 stores
 // Two CTAs fit per SM (96 KB smem, <=128 TMEM columns each) so one CTA's epilogue overlaps the other's mainloop.
+#include <algorithm>
+#include <cstring>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -31,6 +34,12 @@ struct GemmParams {
     void* out;
     int64_t ldd;
     imagd_epilogue ep;
+    // split-K: gridDim.z CTAs share one output tile; fp32 partials meet in `ws`, the last arriver reduces them in
+    // a fixed order (deterministic) and runs the epilogue
+    int splits;
+    int kb_per_split;
+    float* ws;
+    unsigned int* counters;
 };
 
 constexpr int kBlockM = 128;
@@ -45,8 +54,10 @@ struct GemmSmem {
     static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16;
 };
 
+__host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 64 ? 64 : (n <= 128 ? 128 : 256); }
+
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(192, (GemmSmem<BLOCK_N, STAGES>::kTotal <= 112 * 1024) ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     using L = GemmSmem<BLOCK_N, STAGES>;
     extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -70,6 +81,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int tn = m_blk / (p.tiles_x * p.tiles_y);
     const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
     const int total_kb = p.taps * p.kb_per_tap;
+    const int kb_begin = blockIdx.z * p.kb_per_split;
+    const int nk = min(total_kb, kb_begin + p.kb_per_split) - kb_begin;  // >= 1 (host guarantees)
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
@@ -82,7 +95,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, BLOCK_N);
+        tmem_alloc(tmem_slot, tmem_cols_for(BLOCK_N));
         tmem_relinquish();
     }
     tc_fence_before();
@@ -92,9 +105,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         if (elect_one()) {
-            for (int kb = 0; kb < total_kb; ++kb) {
-                const int stage = kb % STAGES;
-                const uint32_t phase = (kb / STAGES) & 1;
+            for (int i = 0; i < nk; ++i) {
+                const int kb = kb_begin + i;
+                const int stage = i % STAGES;
+                const uint32_t phase = (i / STAGES) & 1;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
                 const int tap = kb / p.kb_per_tap;
@@ -113,9 +127,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
-            for (int kb = 0; kb < total_kb; ++kb) {
-                const int stage = kb % STAGES;
-                const uint32_t phase = (kb / STAGES) & 1;
+            for (int i = 0; i < nk; ++i) {
+                const int stage = i % STAGES;
+                const uint32_t phase = (i / STAGES) & 1;
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
@@ -124,7 +138,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int k = 0; k < kBlockK / 16; ++k) {
                     const uint64_t adesc = umma_smem_desc_sw128(sa + k * 32, 16, 1024);
                     const uint64_t bdesc = umma_smem_desc_sw128(sb + k * 32, 16, 1024);
-                    umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
             }
@@ -151,15 +165,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16);
 
+        // ---- split-K rendezvous
+        const bool split = p.splits > 1;
+        const int64_t tile_elems = static_cast<int64_t>(kBlockM) * BLOCK_N;
+        const int64_t tile_id = static_cast<int64_t>(blockIdx.y) * gridDim.x + blockIdx.x;
+        const int64_t n_tiles_total = static_cast<int64_t>(gridDim.x) * gridDim.y;
+        if (split) {
+            float* mine = p.ws + (static_cast<int64_t>(blockIdx.z) * n_tiles_total + tile_id) * tile_elems +
+                          static_cast<int64_t>(r) * BLOCK_N;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    __stcg(reinterpret_cast<float4*>(mine + c0 + j),
+                           make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                       __uint_as_float(v[j + 3])));
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) {  // first epilogue thread
+                const unsigned int old = atomicAdd(&p.counters[tile_id], 1u);
+                *tmem_slot = (old == static_cast<unsigned int>(p.splits - 1)) ? 1u : 0u;  // slot is free to reuse now
+                if (old == static_cast<unsigned int>(p.splits - 1)) p.counters[tile_id] = 0u;  // re-arm for next launch
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const bool last = *reinterpret_cast<volatile uint32_t*>(tmem_slot) != 0u;
+            if (!last) goto epilogue_done;
+            __threadfence();
+        }
+        // accumulator chunk loader: TMEM (single CTA per tile) or the fixed-order sum of the split partials
+        auto load_acc = [&](int c0, uint32_t(&v)[32]) {
+            if (!split) {
+                tmem_ld32(taddr + c0, v);
+                tmem_ld_wait();
+            } else {
+                float acc[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+                for (int sidx = 0; sidx < p.splits; ++sidx) {
+                    const float* src = p.ws + (static_cast<int64_t>(sidx) * n_tiles_total + tile_id) * tile_elems +
+                                       static_cast<int64_t>(r) * BLOCK_N + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 t = __ldcg(reinterpret_cast<const float4*>(src + j));
+                        acc[j] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(acc[j]);
+            }
+        };
+
         if (ep.act == IMAGD_ACT_GEGLU) {
             // tile = [64 value | 64 gate]; output columns n_blk*64 + [0, 64)
             if constexpr (BLOCK_N == 128) {
 #pragma unroll 1
                 for (int c0 = 0; c0 < 64; c0 += 32) {
                     uint32_t va[32], vg[32];
-                    tmem_ld32(taddr + c0, va);
-                    tmem_ld32(taddr + 64 + c0, vg);
-                    tmem_ld_wait();
+                    load_acc(c0, va);
+                    load_acc(64 + c0, vg);
                     const int pcol = n_blk * 128 + c0;  // packed column of value; gate at +64
                     const int ocol = n_blk * 64 + c0;
                     if (row_ok && pcol < p.N) {
@@ -187,8 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
             for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
                 uint32_t v[32];
-                tmem_ld32(taddr + c0, v);
-                tmem_ld_wait();
+                load_acc(c0, v);
                 const int col = n_blk * BLOCK_N + c0;
                 if (!row_ok || col >= p.N) continue;
                 // columns are handled in groups of 8 (N % 8 == 0 is enforced on the host)
@@ -237,9 +303,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     }
 
+epilogue_done:
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols_for(BLOCK_N));
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -263,6 +330,73 @@ static void choose_pixel_box(int W, int H, int NB, int* bw, int* bh, int* bn) {
     }
 }
 
+// ---- split-K scratch: fp32 partial tiles + per-tile arrival counters, one set per device, allocated on first use
+// (outside any stream capture: the engine's eager warm-up step comes first). Kernels on one stream serialise, so
+// one scratch area per device suffices; concurrent streams must not share a device.
+constexpr size_t kWsBytes = size_t(96) << 20;
+constexpr int kMaxTilesSplit = 1 << 16;
+static float* g_ws[16] = {nullptr};
+static unsigned int* g_counters[16] = {nullptr};
+
+static int ensure_scratch(float** ws, unsigned int** counters) {
+    int dev = 0;
+    IMAGD_CUDA(cudaGetDevice(&dev));
+    IMAGD_CHECK_ARG(dev >= 0 && dev < 16, "gemm: device index %d out of range", dev);
+    if (!g_ws[dev]) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(cudaStreamLegacy, &st);
+        IMAGD_CUDA(cudaMalloc(&g_ws[dev], kWsBytes));
+        IMAGD_CUDA(cudaMalloc(&g_counters[dev], kMaxTilesSplit * sizeof(unsigned int)));
+        IMAGD_CUDA(cudaMemset(g_counters[dev], 0, kMaxTilesSplit * sizeof(unsigned int)));
+        IMAGD_CUDA(cudaDeviceSynchronize());
+    }
+    *ws = g_ws[dev];
+    *counters = g_counters[dev];
+    return IMAGD_OK;
+}
+
+// Cost model (SM cycles) behind the tile / split choice. The mainloop is bound by whichever is slower per k-block:
+// the tensor pipe (2*BN cycles for a 128 x BN x 64 block; doubled when two CTAs share an SM) or the smem fill
+// ((128+BN)*128 bytes at the per-CTA share of the L2->SM fabric: ~36 B/clk latency-bound alone, ~6000 B/clk chip).
+struct GemmCfg {
+    int bn, splits;
+};
+static GemmCfg choose_cfg(int m_tiles, int N, int kb_total, bool geglu) {
+    static const int kBN[4] = {64, 128, 160, 256};
+    static const int kS[9] = {1, 2, 3, 4, 6, 8, 12, 16, 24};
+    GemmCfg best{geglu ? 128 : 64, 1};
+    double best_cost = 1e30;
+    for (int bi = 0; bi < 4; ++bi) {
+        const int bn = kBN[bi];
+        if (geglu && bn != 128) continue;
+        if (bn > 64 && bn >= 2 * N) continue;  // tile mostly empty
+        const int n_tiles = (N + bn - 1) / bn;
+        const int64_t ctas = static_cast<int64_t>(m_tiles) * n_tiles;
+        const int occ = bn <= 160 ? 2 : 1;
+        for (int si = 0; si < 9; ++si) {
+            const int S = kS[si];
+            if (S > 1 && (geglu || kb_total / S < 6)) break;
+            const int64_t total = ctas * S;
+            if (S > 1 && (ctas > kMaxTilesSplit || static_cast<size_t>(total) * 128 * bn * 4 > kWsBytes)) break;
+            const int kb = (kb_total + S - 1) / S;
+            const int64_t slots = 148 * occ;
+            const int64_t waves = (total + slots - 1) / slots;
+            const double conc = static_cast<double>(total < slots ? total : slots);
+            const double bw = std::min(36.0, 6000.0 / conc);
+            const double t_load = (128.0 + bn) * 128.0 / bw;
+            const double t_mma = 2.0 * bn * (conc > 148 ? 2.0 : 1.0);
+            double t_tile = kb * std::max(t_load, t_mma) + 3000.0;
+            if (S > 1) t_tile += 1500.0 + S * 128.0 * bn * 4.0 / 128.0;  // partial write + ordered re-read
+            const double cost = waves * t_tile;
+            if (cost < best_cost) {
+                best_cost = cost;
+                best = {bn, S};
+            }
+        }
+    }
+    return best;
+}
+
 template <int BLOCK_N, int STAGES>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles,
                        cudaStream_t stream) {
@@ -274,11 +408,13 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
         attr_set = true;
     }
     const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
-    dim3 grid(m_tiles, n_tiles, 1);
+    dim3 grid(m_tiles, n_tiles, p.splits);
     gemm_tc_kernel<BLOCK_N, STAGES><<<grid, 192, L::kTotal, stream>>>(tmA, tmB, p);
     IMAGD_LAUNCH_CHECK("gemm_tc_kernel");
     return IMAGD_OK;
 }
+
+static int g_force_bn = 0, g_force_splits = 0;  // test hooks (imagd_gemm_debug_force)
 
 static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int Cin, int taps, const void* Wt,
                          int64_t ldw, void* D, int64_t ldd, int N, const imagd_epilogue* ep_in, cudaStream_t stream) {
@@ -321,6 +457,24 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
     const int64_t m_tiles64 = static_cast<int64_t>(p.tiles_x) * p.tiles_y * tiles_n;
     IMAGD_CHECK_ARG(m_tiles64 > 0 && m_tiles64 < (1 << 30), "gemm: bad tile count");
     const int m_tiles = static_cast<int>(m_tiles64);
+    const int kb_total = taps * p.kb_per_tap;
+
+    GemmCfg cfg = choose_cfg(m_tiles, N, kb_total, geglu);
+    if (g_force_bn) cfg.bn = geglu ? 128 : g_force_bn;
+    if (g_force_splits && !geglu) cfg.splits = std::min(g_force_splits, kb_total);
+    p.splits = cfg.splits;
+    p.kb_per_split = (kb_total + cfg.splits - 1) / cfg.splits;
+    p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+    p.ws = nullptr;
+    p.counters = nullptr;
+    if (p.splits > 1) {
+        int rc = ensure_scratch(&p.ws, &p.counters);
+        if (rc != IMAGD_OK) return rc;
+        const int64_t n_tiles = (N + cfg.bn - 1) / cfg.bn;
+        IMAGD_CHECK_ARG(m_tiles64 * n_tiles <= kMaxTilesSplit &&
+                            static_cast<size_t>(m_tiles64 * n_tiles * p.splits) * 128 * cfg.bn * 4 <= kWsBytes,
+                        "gemm: split-K scratch too small");
+    }
 
     // A: [NB, H, W, lda] viewed (c, x, y, n)
     CUtensorMap tmA, tmB;
@@ -333,20 +487,19 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
         int rc = make_tmap_bf16(&tmA, A, 4, dims, strides, box);
         if (rc != IMAGD_OK) return rc;
     }
-    // pick the N tile: 128 unless that wastes > 1/8 of the columns or leaves most SMs idle
-    const int n128 = (N + 127) / 128, n64 = (N + 63) / 64;
-    bool use128 = geglu || ((n128 * 128 - N) * 8 <= N && static_cast<int64_t>(m_tiles) * n128 >= 120);
-    if (N <= 64) use128 = geglu;
     {
         uint64_t dims[2] = {static_cast<uint64_t>(taps) * Cin, static_cast<uint64_t>(N)};
         uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
-        uint32_t box[2] = {kBlockK, static_cast<uint32_t>(use128 ? 128 : 64)};
+        uint32_t box[2] = {kBlockK, static_cast<uint32_t>(cfg.bn)};
         int rc = make_tmap_bf16(&tmB, Wt, 2, dims, strides, box);
         if (rc != IMAGD_OK) return rc;
     }
-    (void)n64;
-    if (use128) return launch_gemm<128, 3>(tmA, tmB, p, m_tiles, stream);
-    return launch_gemm<64, 4>(tmA, tmB, p, m_tiles, stream);
+    switch (cfg.bn) {
+        case 64: return launch_gemm<64, 4>(tmA, tmB, p, m_tiles, stream);
+        case 128: return launch_gemm<128, 3>(tmA, tmB, p, m_tiles, stream);
+        case 160: return launch_gemm<160, 3>(tmA, tmB, p, m_tiles, stream);
+        default: return launch_gemm<256, 4>(tmA, tmB, p, m_tiles, stream);
+    }
 }
 
 }  // namespace imagd
@@ -357,6 +510,14 @@ int imagd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
                     const imagd_epilogue* ep, imagd_stream stream) {
     IMAGD_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
     return imagd::run_gemm_like(A, lda, 1, 1, M, K, 1, W, ldw, D, ldd, N, ep, static_cast<cudaStream_t>(stream));
+}
+
+int imagd_gemm_debug_force(int block_n, int splits) {
+    IMAGD_CHECK_ARG(block_n == 0 || block_n == 64 || block_n == 128 || block_n == 160 || block_n == 256,
+                    "debug_force: block_n %d", block_n);
+    imagd::g_force_bn = block_n;
+    imagd::g_force_splits = splits;
+    return IMAGD_OK;
 }
 
 int imagd_conv3x3_bf16(const void* X, int64_t ldx, int NB, int H, int W, int Cin, const void* Wt, void* Y, int64_t ldy,

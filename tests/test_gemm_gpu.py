@@ -131,3 +131,40 @@ def test_conv3x3_linearity_full_size(cuda_device):
     lhs = ops.conv3x3(xs, w).float()
     rhs = ops.conv3x3(x1, w).float() + ops.conv3x3(x2, w).float()
     assert rel_l2(lhs, rhs) < 2e-2
+
+
+@pytest.mark.parametrize("bn,splits", [(64, 1), (128, 1), (160, 1), (256, 1), (64, 4), (128, 3), (160, 2), (256, 8), (64, 24)])
+def test_gemm_tile_and_splitk_variants(cuda_device, bn, splits):
+    """Every N-tile / split-K kernel variant (forced through the test hook) on a ragged GEMM and a conv."""
+    from imagdressing_b200 import _lib, ops
+
+    lib = _lib.load()
+    try:
+        assert lib.imagd_gemm_debug_force(bn, splits) == 0
+        M, N, K = 300, 648, 1024
+        a = _rand((M, K), cuda_device, 31).bfloat16()
+        w = _rand((N, K), cuda_device, 32, K ** -0.5).bfloat16()
+        bias = _rand((N,), cuda_device, 33)
+        res = _rand((M, N), cuda_device, 34).bfloat16()
+        out = ops.gemm(a, w, bias=bias, residual=res)
+        assert rel_l2(out, ops_ref.gemm_ref(a, w, bias, residual=res)) < TOL
+        out2 = ops.gemm(a, w, bias=bias, residual=res)
+        assert torch.equal(out, out2)  # split-K reduction order is fixed -> bit-reproducible
+        x = _rand((2, 8, 8, 256), cuda_device, 35).bfloat16()
+        wc = _rand((328, 256, 3, 3), cuda_device, 36, (9 * 256) ** -0.5).bfloat16()
+        temb = _rand((2, 328), cuda_device, 37)
+        y = ops.conv3x3(x, ops_ref.conv3x3_pack(wc), rowvec=temb)
+        assert rel_l2(y, ops_ref.conv3x3_ref(x, wc, None, temb)) < TOL
+    finally:
+        lib.imagd_gemm_debug_force(0, 0)
+
+
+def test_gemm_auto_config_deep_level_shapes(cuda_device):
+    """The shapes where the automatic choice picks split-K (few output tiles, long K)."""
+    from imagdressing_b200 import ops
+
+    for (NB, H, W, Cin, Cout) in [(2, 8, 8, 2560, 1280), (2, 16, 16, 1280, 1280), (2, 8, 8, 1280, 1280)]:
+        x = _rand((NB, H, W, Cin), cuda_device, 41).bfloat16()
+        w = _rand((Cout, Cin, 3, 3), cuda_device, 42, (9 * Cin) ** -0.5).bfloat16()
+        b = _rand((Cout,), cuda_device, 43)
+        assert rel_l2(ops.conv3x3(x, ops_ref.conv3x3_pack(w), bias=b), ops_ref.conv3x3_ref(x, w, b)) < TOL
