@@ -14,6 +14,8 @@
 // Two CTAs fit per SM (96 KB smem, <=128 TMEM columns each) so one CTA's epilogue overlaps the other's mainloop.
 #include <algorithm>
 #include <cstring>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -355,46 +357,46 @@ static int ensure_scratch(float** ws, unsigned int** counters) {
     return IMAGD_OK;
 }
 
-// Cost model (SM cycles) behind the tile / split choice. The mainloop is bound by whichever is slower per k-block:
-// the tensor pipe (2*BN cycles for a 128 x BN x 64 block; doubled when two CTAs share an SM) or the smem fill
-// ((128+BN)*128 bytes at the per-CTA share of the L2->SM fabric: ~36 B/clk latency-bound alone, ~6000 B/clk chip).
+// ---- tile / pipeline-depth / split-K choice --------------------------------------------------------------------
+// Variants: N tile 64 / 128 / 160 / 256; "shallow" pipelines (<= 112 KB smem, two CTAs per SM so one CTA's epilogue
+// overlaps the other's mainloop — best when the grid covers the chip more than once) or "deep" ones (~190 KB, one
+// CTA per SM with twice the bytes in flight — best when there are fewer CTAs than SMs and each CTA is bound by the
+// latency of its own TMA ring); split-K for the deep UNet levels whose output has only a handful of tiles.
+// The choice is table-driven: csrc/gemm_tuning.inc holds the measured-best variant for every problem the UNet /
+// ControlNet issue at the benchmarked batch sizes (tools/gemm_sweep.py); unseen problems use the rule below,
+// which was read off the same measurements.
 struct GemmCfg {
-    int bn, splits;
+    int bn, stages, splits;
 };
+struct TuneEntry {
+    int m_tiles, N, kb_total, geglu, bn, stages, splits;
+};
+static const TuneEntry kTuneTable[] = {
+#include "gemm_tuning.inc"
+    {0, 0, 0, 0, 0, 0, 0}};
+
+static int shallow_stages(int bn) { return bn == 64 ? 4 : (bn == 256 ? 2 : 3); }
+static int deep_stages(int bn) { return bn == 64 ? 8 : (bn == 128 ? 6 : (bn == 160 ? 5 : 4)); }
+
 static GemmCfg choose_cfg(int m_tiles, int N, int kb_total, bool geglu) {
-    static const int kBN[4] = {64, 128, 160, 256};
-    static const int kS[9] = {1, 2, 3, 4, 6, 8, 12, 16, 24};
-    GemmCfg best{geglu ? 128 : 64, 1};
-    double best_cost = 1e30;
-    for (int bi = 0; bi < 4; ++bi) {
-        const int bn = kBN[bi];
-        if (geglu && bn != 128) continue;
-        if (bn > 64 && bn >= 2 * N) continue;  // tile mostly empty
-        const int n_tiles = (N + bn - 1) / bn;
-        const int64_t ctas = static_cast<int64_t>(m_tiles) * n_tiles;
-        const int occ = bn <= 160 ? 2 : 1;
-        for (int si = 0; si < 9; ++si) {
-            const int S = kS[si];
-            if (S > 1 && (geglu || kb_total / S < 6)) break;
-            const int64_t total = ctas * S;
-            if (S > 1 && (ctas > kMaxTilesSplit || static_cast<size_t>(total) * 128 * bn * 4 > kWsBytes)) break;
-            const int kb = (kb_total + S - 1) / S;
-            const int64_t slots = 148 * occ;
-            const int64_t waves = (total + slots - 1) / slots;
-            const double conc = static_cast<double>(total < slots ? total : slots);
-            const double bw = std::min(36.0, 6000.0 / conc);
-            const double t_load = (128.0 + bn) * 128.0 / bw;
-            const double t_mma = 2.0 * bn * (conc > 148 ? 2.0 : 1.0);
-            double t_tile = kb * std::max(t_load, t_mma) + 3000.0;
-            if (S > 1) t_tile += 1500.0 + S * 128.0 * bn * 4.0 / 128.0;  // partial write + ordered re-read
-            const double cost = waves * t_tile;
-            if (cost < best_cost) {
-                best_cost = cost;
-                best = {bn, S};
-            }
-        }
+    for (const TuneEntry* e = kTuneTable; e->bn != 0; ++e)
+        if (e->m_tiles == m_tiles && e->N == N && e->kb_total == kb_total && e->geglu == (geglu ? 1 : 0))
+            return {e->bn, e->stages, e->splits};
+    // fallback rule
+    auto ctas = [&](int bn) { return static_cast<int64_t>(m_tiles) * ((N + bn - 1) / bn); };
+    if (geglu) return {128, ctas(128) > 160 ? 3 : 6, 1};
+    if (ctas(160) >= 400) return {160, 3, 1};                      // many waves: widest 2-CTA/SM tile
+    int bn = 64;
+    if (ctas(160) >= 150 && ctas(160) <= 296 && (N % 160 == 0 || N > 640)) bn = 160;
+    else if (ctas(128) >= 150) bn = 128;
+    int splits = 1;
+    if (ctas(bn) < 100 && kb_total >= 60) {
+        splits = static_cast<int>((160 + ctas(bn) - 1) / ctas(bn));
+        splits = std::min(splits, std::min(6, kb_total / 30));
+        splits = std::max(splits, 1);
     }
-    return best;
+    const bool deep = ctas(bn) * splits <= 180;
+    return {bn, deep ? deep_stages(bn) : shallow_stages(bn), splits};
 }
 
 template <int BLOCK_N, int STAGES>
@@ -414,7 +416,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     return IMAGD_OK;
 }
 
-static int g_force_bn = 0, g_force_splits = 0;  // test hooks (imagd_gemm_debug_force)
+static int g_force_bn = 0, g_force_stages = 0, g_force_splits = 0;  // test hooks (imagd_gemm_debug_force)
+static int g_log_on = 0;
+static std::vector<std::string> g_log;  // unique problem keys seen while logging (tools/gemm_sweep.py)
 
 static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int Cin, int taps, const void* Wt,
                          int64_t ldw, void* D, int64_t ldd, int N, const imagd_epilogue* ep_in, cudaStream_t stream) {
@@ -460,8 +464,18 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
     const int kb_total = taps * p.kb_per_tap;
 
     GemmCfg cfg = choose_cfg(m_tiles, N, kb_total, geglu);
-    if (g_force_bn) cfg.bn = geglu ? 128 : g_force_bn;
+    if (g_force_bn) {
+        cfg.bn = geglu ? 128 : g_force_bn;
+        cfg.stages = g_force_stages ? g_force_stages : shallow_stages(cfg.bn);
+        if (cfg.stages != shallow_stages(cfg.bn) && cfg.stages != deep_stages(cfg.bn)) cfg.stages = shallow_stages(cfg.bn);
+    }
     if (g_force_splits && !geglu) cfg.splits = std::min(g_force_splits, kb_total);
+    if (g_log_on) {
+        char key[160];
+        snprintf(key, sizeof(key), "%d %d %d %d %d %d %d %d %d %d", taps, NB, H, W, Cin, N, geglu ? 1 : 0, m_tiles,
+                 kb_total, ep.out_fp32);
+        if (std::find(g_log.begin(), g_log.end(), key) == g_log.end()) g_log.push_back(key);
+    }
     p.splits = cfg.splits;
     p.kb_per_split = (kb_total + cfg.splits - 1) / cfg.splits;
     p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
@@ -494,11 +508,18 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
         int rc = make_tmap_bf16(&tmB, Wt, 2, dims, strides, box);
         if (rc != IMAGD_OK) return rc;
     }
-    switch (cfg.bn) {
-        case 64: return launch_gemm<64, 4>(tmA, tmB, p, m_tiles, stream);
-        case 128: return launch_gemm<128, 3>(tmA, tmB, p, m_tiles, stream);
-        case 160: return launch_gemm<160, 3>(tmA, tmB, p, m_tiles, stream);
-        default: return launch_gemm<256, 4>(tmA, tmB, p, m_tiles, stream);
+    switch (cfg.bn * 100 + cfg.stages) {
+        case 6404: return launch_gemm<64, 4>(tmA, tmB, p, m_tiles, stream);
+        case 6408: return launch_gemm<64, 8>(tmA, tmB, p, m_tiles, stream);
+        case 12803: return launch_gemm<128, 3>(tmA, tmB, p, m_tiles, stream);
+        case 12806: return launch_gemm<128, 6>(tmA, tmB, p, m_tiles, stream);
+        case 16003: return launch_gemm<160, 3>(tmA, tmB, p, m_tiles, stream);
+        case 16005: return launch_gemm<160, 5>(tmA, tmB, p, m_tiles, stream);
+        case 25602: return launch_gemm<256, 2>(tmA, tmB, p, m_tiles, stream);
+        case 25604: return launch_gemm<256, 4>(tmA, tmB, p, m_tiles, stream);
+        default:
+            set_error("gemm: no kernel variant for N tile %d with %d stages", cfg.bn, cfg.stages);
+            return IMAGD_ERR_ARG;
     }
 }
 
@@ -512,12 +533,28 @@ int imagd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
     return imagd::run_gemm_like(A, lda, 1, 1, M, K, 1, W, ldw, D, ldd, N, ep, static_cast<cudaStream_t>(stream));
 }
 
-int imagd_gemm_debug_force(int block_n, int splits) {
+int imagd_gemm_debug_force(int block_n, int stages, int splits) {
     IMAGD_CHECK_ARG(block_n == 0 || block_n == 64 || block_n == 128 || block_n == 160 || block_n == 256,
                     "debug_force: block_n %d", block_n);
     imagd::g_force_bn = block_n;
+    imagd::g_force_stages = stages;
     imagd::g_force_splits = splits;
     return IMAGD_OK;
+}
+
+int imagd_gemm_debug_log(int enable, char* out, int out_bytes) {
+    if (enable >= 0) {
+        imagd::g_log_on = enable;
+        if (enable) imagd::g_log.clear();
+    }
+    if (out && out_bytes > 0) {
+        std::string all;
+        for (const auto& k : imagd::g_log) all += k + "\n";
+        IMAGD_CHECK_ARG(static_cast<int>(all.size()) < out_bytes, "debug_log: buffer too small (%d needed)",
+                        static_cast<int>(all.size()) + 1);
+        memcpy(out, all.c_str(), all.size() + 1);
+    }
+    return static_cast<int>(imagd::g_log.size());
 }
 
 int imagd_conv3x3_bf16(const void* X, int64_t ldx, int NB, int H, int W, int Cin, const void* Wt, void* Y, int64_t ldy,

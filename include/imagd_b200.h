@@ -61,9 +61,13 @@ typedef struct imagd_epilogue {
 int imagd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd, int M, int N,
                     int K, const imagd_epilogue* ep, imagd_stream stream);
 
-/* Test hook: force the N tile (0 = automatic; 64 / 128 / 160 / 256) and the split-K factor (0 = automatic) of the
- * next imagd_gemm_bf16 / imagd_conv3x3_bf16 calls, so the parity tests cover every kernel variant. */
-int imagd_gemm_debug_force(int block_n, int splits);
+/* Test / tuning hooks. debug_force: force the N tile (0 = automatic; 64 / 128 / 160 / 256), the TMA ring depth
+ * (0 = the shallow two-CTAs-per-SM variant) and the split-K factor (0 = automatic) of the next imagd_gemm_bf16 /
+ * imagd_conv3x3_bf16 calls, so the parity tests cover every kernel variant. debug_log: enable = 1 starts recording
+ * the distinct problems issued ("taps NB H W Cin N geglu m_tiles kb_total out_fp32" per line), 0 stops, -1 leaves
+ * the state; when `out` is given the recorded lines are copied there. Returns the number of lines. */
+int imagd_gemm_debug_force(int block_n, int stages, int splits);
+int imagd_gemm_debug_log(int enable, char* out, int out_bytes);
 
 /* Y[n,y,x,:] = sum_{ky,kx} X[n,y+ky-1,x+kx-1,:] * Wt[:, (ky*3+kx)*Cin : +Cin]^T  (stride 1, zero pad 1) as an
  * implicit GEMM on tcgen05: the 9 shifted activation views are fetched by TMA with out-of-bounds zero fill.

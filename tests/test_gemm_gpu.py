@@ -133,14 +133,16 @@ def test_conv3x3_linearity_full_size(cuda_device):
     assert rel_l2(lhs, rhs) < 2e-2
 
 
-@pytest.mark.parametrize("bn,splits", [(64, 1), (128, 1), (160, 1), (256, 1), (64, 4), (128, 3), (160, 2), (256, 8), (64, 24)])
-def test_gemm_tile_and_splitk_variants(cuda_device, bn, splits):
+@pytest.mark.parametrize("bn,stages,splits", [(64, 4, 1), (128, 3, 1), (160, 3, 1), (256, 2, 1), (64, 8, 1), (128, 6, 1),
+                                              (160, 5, 1), (256, 4, 1), (64, 8, 4), (128, 6, 3), (160, 3, 2),
+                                              (256, 4, 8), (64, 4, 24)])
+def test_gemm_tile_and_splitk_variants(cuda_device, bn, stages, splits):
     """Every N-tile / split-K kernel variant (forced through the test hook) on a ragged GEMM and a conv."""
     from imagdressing_b200 import _lib, ops
 
     lib = _lib.load()
     try:
-        assert lib.imagd_gemm_debug_force(bn, splits) == 0
+        assert lib.imagd_gemm_debug_force(bn, stages, splits) == 0
         M, N, K = 300, 648, 1024
         a = _rand((M, K), cuda_device, 31).bfloat16()
         w = _rand((N, K), cuda_device, 32, K ** -0.5).bfloat16()
@@ -156,7 +158,7 @@ def test_gemm_tile_and_splitk_variants(cuda_device, bn, splits):
         y = ops.conv3x3(x, ops_ref.conv3x3_pack(wc), rowvec=temb)
         assert rel_l2(y, ops_ref.conv3x3_ref(x, wc, None, temb)) < TOL
     finally:
-        lib.imagd_gemm_debug_force(0, 0)
+        lib.imagd_gemm_debug_force(0, 0, 0)
 
 
 def test_gemm_auto_config_deep_level_shapes(cuda_device):
