@@ -13,12 +13,15 @@
 // head_dim 40 / 80 / 160 the box over-runs the d extent and the hardware zero-fills, so no padded copies exist
 // in HBM and the MMA K extent is the head dim rounded to 16 (48 / 80 / 160).
 //
-// CTA = 128 queries of one (sample, head). 192 threads:
-//   warps 0-3  softmax: one query row per thread (TMEM lane = row); S read with tcgen05.ld, P written to smem
-//              in the UMMA K-major 128B-swizzle layout, O rescaled in TMEM only when the running max moves
-//   warp 4     TMA producer (K/V ring)
-//   warp 5     TMEM allocator + tcgen05.mma issuer:  S = Q K^T  (128x128xhd),  O_s += P V (128xhdx128)
-// TMEM columns: S [0,128), O_0 [128, +O_STRIDE), O_1 after it.
+// CTA = 128 queries of one (sample, head). 320 threads:
+//   warps 0-7  softmax: TMEM lane = query row; warps w and w+4 own the same 32 rows and split the 128 score
+//              columns in halves (twice the warps to hide the exp / convert latency — at head_dim 40 the softmax,
+//              not the tensor pipe, bounds the kernel). S is read once with tcgen05.ld and held in registers, the two
+//              half-row maxima meet through 512 bytes of smem, P is written to smem in the UMMA K-major
+//              128B-swizzle layout, O is rescaled in TMEM only when the running max moves
+//   warp 8     TMA producer (K/V ring)
+//   warp 9     TMEM allocator + tcgen05.mma issuer:  S = Q K^T  (128x128xhd),  O_s += P V (128xhdx128)
+// TMEM columns: S [0,128), O_0 [128, +O_STRIDE), O_1 after it. Two CTAs per SM at head_dim 40 / 64.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -48,12 +51,13 @@ struct AttnCfg {
     static constexpr int kPOff = kVOff + KV_STAGES * NATOM * kAtomBytes;
     static constexpr int kBarOff = kPOff + 2 * kAtomBytes;
     static constexpr int kNumBars = 1 + 3 * KV_STAGES + 3;
-    static constexpr int kTotal = kBarOff + kNumBars * 8 + 16;
+    static constexpr int kMxOff = kBarOff + kNumBars * 8 + 16;  // [2 halves][128 rows] bf16 partial row maxima
+    static constexpr int kTotal = kMxOff + 512;
 };
 
 template <int HD_MMA, int NATOM, int KV_STAGES>
-__global__ void __launch_bounds__(192, (AttnCfg<HD_MMA, NATOM, KV_STAGES>::kTmemCols <= 256 &&
-                                        AttnCfg<HD_MMA, NATOM, KV_STAGES>::kTotal <= 112 * 1024 + 512) ? 2 : 1)
+__global__ void __launch_bounds__(320, (AttnCfg<HD_MMA, NATOM, KV_STAGES>::kTmemCols <= 256 &&
+                                        AttnCfg<HD_MMA, NATOM, KV_STAGES>::kTotal <= 113 * 1024) ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                     const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
                     const __grid_constant__ CUtensorMap tmV1, const AttnParams p) {
@@ -97,11 +101,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             mbar_init(&kv_empty[i], 1);
         }
         mbar_init(s_full, 1);
-        mbar_init(p_full, 128);
+        mbar_init(p_full, 256);
         mbar_init(o_full, 1);
         fence_barrier_init();
     }
-    if (warp == 5) {
+    if (warp == 9) {
         tmem_alloc(tmem_slot, C::kTmemCols);
         tmem_relinquish();
     }
@@ -112,7 +116,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t tmem_S = tmem_base;
     const uint32_t tmem_O = tmem_base + 128;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ------------------------------------------------ TMA producer
         if (elect_one()) {
             mbar_arrive_expect_tx(q_full, C::kQBytes);
@@ -137,7 +141,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     tma_load_4d(sV + (st * NATOM + a) * kAtomBytes, mv, &v_full[st], a * 64, h, j * 128, bk);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ------------------------------------------------ MMA issuer
         if (elect_one()) {
             constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);     // Q (K-major) x K (K-major)
@@ -177,12 +181,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             umma_commit(o_full);
         }
     } else {
-        // ------------------------------------------------ softmax / correction / epilogue (warps 0-3)
-        const int r = warp * 32 + lane;  // query row in tile == TMEM lane
-        const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-        float m_run = -INFINITY, l_run = 0.f, l_first = 1.f;
-        const uint32_t p_row = smem_u32(sP) + (r >> 3) * 1024 + (r & 7) * 128;
+        // ------------------------------------------------ softmax / correction / epilogue (warps 0-7)
+        const int lg = warp & 3;          // TMEM lane quadrant
+        const int half = warp >> 2;       // which 64 score columns of the row this thread owns
+        const int r = lg * 32 + lane;     // query row in tile == TMEM lane
+        const uint32_t lane_addr = static_cast<uint32_t>(lg * 32) << 16;
+        __nv_bfloat16* mxbuf = reinterpret_cast<__nv_bfloat16*>(smem + C::kMxOff);
+        float m_run = -INFINITY, l_run = 0.f, l_first = 0.f;
+        const uint32_t p_row = smem_u32(sP) + half * kAtomBytes + (r >> 3) * 1024 + (r & 7) * 128;
         const uint32_t rx = r & 7;
+        // this thread's share of the O columns (16-column chunks) for the in-TMEM rescale and the epilogue
+        constexpr int kChunks = HD_MMA / 16;
+        const int ch_begin = half == 0 ? 0 : (kChunks + 1) / 2;
+        const int ch_end = half == 0 ? (kChunks + 1) / 2 : kChunks;
 
         for (int i = 0; i < T; ++i) {
             const int s = i < nb0 ? 0 : 1;
@@ -192,86 +203,111 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 m_run = -INFINITY;
                 l_run = 0.f;
             }
-            const int valid = min(128, p.len[s] - j * 128);
+            const int valid = min(128, p.len[s] - j * 128) - half * 64;  // valid columns in my half (may be <= 0)
             mbar_wait(s_full, i & 1);
             tc_fence_after();
 
-            // pass 1: row max
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 128; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_S + lane_addr + c, v);
+            // scores of my half row -> registers (read TMEM once)
+            uint32_t v[64];
+            {
+                uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+                uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+                tmem_ld32(tmem_S + lane_addr + half * 64, lo);
+                tmem_ld32(tmem_S + lane_addr + half * 64 + 32, hi);
                 tmem_ld_wait();
-#pragma unroll
-                for (int k = 0; k < 32; ++k)
-                    if (c + k < valid) mx = fmaxf(mx, __uint_as_float(v[k]));
             }
-            const float m_new = fmaxf(m_run, mx * p.scale_log2);
-            const float alpha = exp2f(m_run - m_new);  // 0 on the first block of a stream
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+            if (valid >= 64) {
+#pragma unroll
+                for (int k = 0; k < 64; k += 4) {
+                    mx0 = fmaxf(mx0, __uint_as_float(v[k]));
+                    mx1 = fmaxf(mx1, __uint_as_float(v[k + 1]));
+                    mx2 = fmaxf(mx2, __uint_as_float(v[k + 2]));
+                    mx3 = fmaxf(mx3, __uint_as_float(v[k + 3]));
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 64; ++k)
+                    if (k < valid) mx0 = fmaxf(mx0, __uint_as_float(v[k]));
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+            // Any m >= the true row max keeps exp2(s - m) <= 1, so the two half-row threads only have to agree on
+            // one: each publishes its maximum rounded UP to bf16 and both take the larger.
+            const __nv_bfloat16 mine = __float2bfloat16_ru(mx);
+            mxbuf[half * 128 + r] = mine;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float m_blk = fmaxf(__bfloat162float(mine), __bfloat162float(mxbuf[(half ^ 1) * 128 + r]));
+            const float m_new = fmaxf(m_run, m_blk);
+            const float alpha = ex2_approx(m_run - m_new);  // 0 on the first block of a stream
             if (j > 0 && __any_sync(0xffffffffu, m_new > m_run)) {
-                // rescale this stream's O accumulator in TMEM
+                // rescale my chunks of this stream's O accumulator in TMEM
                 const uint32_t o_addr = tmem_O + s * C::kOStride + lane_addr;
 #pragma unroll 1
-                for (int c = 0; c < HD_MMA; c += 16) {
+                for (int c = ch_begin; c < ch_end; ++c) {
                     uint32_t o[16];
-                    tmem_ld16(o_addr + c, o);
+                    tmem_ld16(o_addr + c * 16, o);
                     tmem_ld_wait();
 #pragma unroll
                     for (int k = 0; k < 16; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
-                    tmem_st16(o_addr + c, o);
+                    tmem_st16(o_addr + c * 16, o);
                 }
                 tmem_st_wait();
             }
             m_run = m_new;
 
-            // pass 2: P = exp2(S*scale - m), row sum, write P (bf16) into the swizzled K-major smem tile
-            float sum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 128; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_S + lane_addr + c, v);
-                tmem_ld_wait();
-                uint32_t pk[16];
+            // P = exp2(S*scale - m) for my 64 columns -> one 64-wide swizzled atom of the P tile
+            float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+            const float sc = p.scale_log2;
 #pragma unroll
-                for (int k = 0; k < 32; k += 2) {
-                    float e0 = (c + k < valid) ? exp2f(__uint_as_float(v[k]) * p.scale_log2 - m_new) : 0.f;
-                    float e1 = (c + k + 1 < valid) ? exp2f(__uint_as_float(v[k + 1]) * p.scale_log2 - m_new) : 0.f;
-                    sum += e0 + e1;
-                    pk[k / 2] = pack_bf16x2(e0, e1);
-                }
-                // 32 columns = 4 x 16-byte chunks; chunk index within the 64-wide atom: (c % 64) / 8 + q
-                const uint32_t atom_base = p_row + (c / 64) * kAtomBytes;
+            for (int q = 0; q < 8; ++q) {
+                float e[8];
+                if (valid >= 64) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t chunk = ((c % 64) / 8 + q) ^ rx;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(atom_base + chunk * 16),
-                                 "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
-                                 : "memory");
+                    for (int k = 0; k < 8; ++k) e[k] = ex2_approx(__uint_as_float(v[q * 8 + k]) * sc - m_new);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        e[k] = (q * 8 + k < valid) ? ex2_approx(__uint_as_float(v[q * 8 + k]) * sc - m_new) : 0.f;
                 }
+                sum0 += e[0] + e[4];
+                sum1 += e[1] + e[5];
+                sum2 += e[2] + e[6];
+                sum3 += e[3] + e[7];
+                const uint32_t chunk = static_cast<uint32_t>(q) ^ rx;
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16),
+                             "r"(pack_bf16x2(e[0], e[1])), "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])),
+                             "r"(pack_bf16x2(e[6], e[7]))
+                             : "memory");
             }
-            l_run = l_run * alpha + sum;
+            l_run = l_run * alpha + ((sum0 + sum1) + (sum2 + sum3));
 
             fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor core (async proxy)
             tc_fence_before();
             mbar_arrive(p_full);
         }
 
-        // ---- epilogue: out = w0 * O0 / l0 + w1 * O1 / l1
+        // ---- epilogue: out = w0 * O0 / l0 + w1 * O1 / l1 (row sums of the two half-row threads meet in the idle P tile)
         mbar_wait(o_full, 0);
         tc_fence_after();
+        float* lbuf = reinterpret_cast<float*>(sP);  // [2 halves][2 values][128 rows]
+        lbuf[(half * 2 + 0) * 128 + r] = l_first;
+        lbuf[(half * 2 + 1) * 128 + r] = l_run;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float lf = l_first + lbuf[((half ^ 1) * 2 + 0) * 128 + r];
+        const float lr = l_run + lbuf[((half ^ 1) * 2 + 1) * 128 + r];
         float w0, w1 = 0.f;
         if (nb1 > 0) {
-            w0 = p.oscale[0] / l_first;
-            w1 = p.oscale[1] / l_run;
+            w0 = p.oscale[0] / lf;
+            w1 = p.oscale[1] / lr;
         } else {
-            w0 = p.oscale[0] / l_run;
+            w0 = p.oscale[0] / lr;
         }
         const int q = q0 + r;
         __nv_bfloat16* orow =
             reinterpret_cast<__nv_bfloat16*>(p.out) + (static_cast<int64_t>(b) * p.Lq + q) * p.out_ld + h * p.hd;
 #pragma unroll 1
-        for (int c = 0; c < HD_MMA; c += 16) {
+        for (int cc = ch_begin; cc < ch_end; ++cc) {
+            const int c = cc * 16;
             uint32_t o0[16], o1[16];
             tmem_ld16(tmem_O + lane_addr + c, o0);
             if (nb1 > 0) tmem_ld16(tmem_O + C::kOStride + lane_addr + c, o1);
@@ -295,7 +331,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, C::kTmemCols);
+    if (warp == 9) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -320,7 +356,7 @@ static int launch_attn(const CUtensorMap* tms, const AttnParams& p, cudaStream_t
         attr_set = true;
     }
     dim3 grid((p.Lq + 127) / 128, p.heads, p.B);
-    attention_tc_kernel<HD_MMA, NATOM, KV_STAGES><<<grid, 192, C::kTotal, stream>>>(tms[0], tms[1], tms[2], tms[3],
+    attention_tc_kernel<HD_MMA, NATOM, KV_STAGES><<<grid, 320, C::kTotal, stream>>>(tms[0], tms[1], tms[2], tms[3],
                                                                                    tms[4], p);
     IMAGD_LAUNCH_CHECK("attention_tc_kernel");
     return IMAGD_OK;

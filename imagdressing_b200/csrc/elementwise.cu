@@ -111,20 +111,73 @@ __global__ void conv3x3_direct_thread_kernel(const __nv_bfloat16* __restrict__ x
     }
 }
 
-// warp per output pixel, Cout <= 8, Cin % 8 == 0: conv_out (320 -> 4). Lanes split the 9*Cin reduction.
+// conv_in (Cin = 4): 8 threads per output pixel, each keeps the 3x3x4 patch in registers and produces Cout/8 channels
+// from weights staged in shared memory; stores are 16-byte vectors.
+__global__ void __launch_bounds__(256) conv3x3_cin4_kernel(const __nv_bfloat16* __restrict__ x, int NB, int H, int W,
+                                                           const __nv_bfloat16* __restrict__ w,
+                                                           const float* __restrict__ bias,
+                                                           __nv_bfloat16* __restrict__ y, int Cout,
+                                                           const __nv_bfloat16* __restrict__ add) {
+    extern __shared__ float s_w[];  // [Cout][37] (row padded: fewer bank conflicts) + [Cout] bias
+    for (int i = threadIdx.x; i < Cout * 36; i += blockDim.x) s_w[(i / 36) * 37 + i % 36] = __bfloat162float(w[i]);
+    float* s_b = s_w + Cout * 37;
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const int64_t pix = blockIdx.x * static_cast<int64_t>(blockDim.x / 8) + (threadIdx.x >> 3);
+    const int part = threadIdx.x & 7;
+    if (pix >= static_cast<int64_t>(NB) * H * W) return;
+    const int xo = static_cast<int>(pix % W);
+    const int yo = static_cast<int>((pix / W) % H);
+    const int n = static_cast<int>(pix / (static_cast<int64_t>(W) * H));
+    float patch[36];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int yi = yo + tap / 3 - 1, xi = xo + tap % 3 - 1;
+        uint2 v = make_uint2(0u, 0u);
+        if (yi >= 0 && yi < H && xi >= 0 && xi < W)
+            v = __ldg(reinterpret_cast<const uint2*>(x + ((static_cast<int64_t>(n) * H + yi) * W + xi) * 4));
+        patch[tap * 4 + 0] = bf16lo(v.x);
+        patch[tap * 4 + 1] = bf16hi(v.x);
+        patch[tap * 4 + 2] = bf16lo(v.y);
+        patch[tap * 4 + 3] = bf16hi(v.y);
+    }
+    const int per = Cout / 8;  // channels per thread (multiple of 8)
+    for (int c0 = part * per; c0 < (part + 1) * per; c0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float* wr = s_w + (c0 + k) * 37;
+            float a = s_b[c0 + k];
+#pragma unroll
+            for (int t = 0; t < 36; ++t) a += patch[t] * wr[t];
+            acc[k] = a;
+        }
+        if (add) {
+            const uint4 av = __ldg(reinterpret_cast<const uint4*>(add + pix * Cout + c0));
+            acc[0] += bf16lo(av.x); acc[1] += bf16hi(av.x); acc[2] += bf16lo(av.y); acc[3] += bf16hi(av.y);
+            acc[4] += bf16lo(av.z); acc[5] += bf16hi(av.z); acc[6] += bf16lo(av.w); acc[7] += bf16hi(av.w);
+        }
+        *reinterpret_cast<uint4*>(y + pix * Cout + c0) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                                   pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+    }
+}
+
+// warp per output pixel, COUT <= 8, Cin % 8 == 0: conv_out (320 -> 4). Lanes split the 9*Cin reduction.
+template <int COUT>
 __global__ void __launch_bounds__(256) conv3x3_direct_warp_kernel(const __nv_bfloat16* __restrict__ x, int NB, int H,
                                                                   int W, int Cin, const __nv_bfloat16* __restrict__ w,
                                                                   const float* __restrict__ bias, void* __restrict__ y,
-                                                                  int Cout, int act, int out_nchw_f32) {
+                                                                  int act, int out_nchw_f32) {
+    constexpr int Cout = COUT;
     const int64_t pix = blockIdx.x * static_cast<int64_t>(blockDim.x / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (pix >= static_cast<int64_t>(NB) * H * W) return;
     const int xo = static_cast<int>(pix % W);
     const int yo = static_cast<int>((pix / W) % H);
     const int n = static_cast<int>(pix / (static_cast<int64_t>(W) * H));
-    float acc[8];
+    float acc[COUT];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int k = 0; k < COUT; ++k) acc[k] = 0.f;
     const int CV = Cin / 8;
     for (int tap = 0; tap < 9; ++tap) {
         const int yi = yo + tap / 3 - 1, xi = xo + tap % 3 - 1;
@@ -133,7 +186,8 @@ __global__ void __launch_bounds__(256) conv3x3_direct_warp_kernel(const __nv_bfl
         for (int cv = lane; cv < CV; cv += 32) {
             const uint4 xv = __ldg(reinterpret_cast<const uint4*>(xr + cv * 8));
             const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
-            for (int co = 0; co < Cout; ++co) {
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
                 const uint4 wv =
                     __ldg(reinterpret_cast<const uint4*>(w + (static_cast<int64_t>(co) * 9 + tap) * Cin + cv * 8));
                 const uint32_t wu[4] = {wv.x, wv.y, wv.z, wv.w};
@@ -144,13 +198,13 @@ __global__ void __launch_bounds__(256) conv3x3_direct_warp_kernel(const __nv_bfl
         }
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
+    for (int k = 0; k < COUT; ++k)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
     if (lane < Cout) {
         float v = acc[0];
 #pragma unroll
-        for (int k = 1; k < 8; ++k)
+        for (int k = 1; k < COUT; ++k)
             if (lane == k) v = acc[k];
         v += bias ? bias[lane] : 0.f;
         if (act == IMAGD_ACT_SILU) v = silu(v);
@@ -343,12 +397,26 @@ int imagd_conv3x3_direct_bf16(const void* x, int NB, int H, int W, int Cin, cons
     IMAGD_CHECK_ARG(x && w && y && NB > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "conv3x3_direct: bad args");
     IMAGD_CHECK_ARG(stride == 1 || stride == 2, "conv3x3_direct: stride %d", stride);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (Cout <= 8 && Cin % 8 == 0 && Cin >= 64 && stride == 1 && !add_nhwc) {
+    if (Cout == 4 && Cin % 8 == 0 && Cin >= 64 && stride == 1 && !add_nhwc) {
         const int64_t pixels = static_cast<int64_t>(NB) * H * W;
-        conv3x3_direct_warp_kernel<<<static_cast<int>((pixels + 7) / 8), 256, 0, st>>>(
+        conv3x3_direct_warp_kernel<4><<<static_cast<int>((pixels + 7) / 8), 256, 0, st>>>(
             reinterpret_cast<const __nv_bfloat16*>(x), NB, H, W, Cin, reinterpret_cast<const __nv_bfloat16*>(w), bias, y,
-            Cout, act, out_nchw_f32);
+            act, out_nchw_f32);
         IMAGD_LAUNCH_CHECK("conv3x3_direct_warp_kernel");
+        return IMAGD_OK;
+    }
+    if (Cin == 4 && Cout % 64 == 0 && Cout <= 640 && stride == 1 && act == IMAGD_ACT_NONE && !out_nchw_f32) {
+        const int64_t pixels = static_cast<int64_t>(NB) * H * W;
+        const size_t smem = static_cast<size_t>(Cout) * 38 * sizeof(float);
+        static bool attr_set = false;
+        if (!attr_set) {
+            IMAGD_CUDA(cudaFuncSetAttribute(conv3x3_cin4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 640 * 38 * 4));
+            attr_set = true;
+        }
+        conv3x3_cin4_kernel<<<static_cast<int>((pixels + 31) / 32), 256, smem, st>>>(
+            reinterpret_cast<const __nv_bfloat16*>(x), NB, H, W, reinterpret_cast<const __nv_bfloat16*>(w), bias,
+            reinterpret_cast<__nv_bfloat16*>(y), Cout, reinterpret_cast<const __nv_bfloat16*>(add_nhwc));
+        IMAGD_LAUNCH_CHECK("conv3x3_cin4_kernel");
         return IMAGD_OK;
     }
     const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;

@@ -7,15 +7,20 @@ namespace imagd {
 
 constexpr int kGnMaxC = 2560;
 constexpr int kGnThreads = 512;
+constexpr int kGnCounters = 1024;  // max samples per call
 
 __host__ __device__ inline int gn_chunks(int HW) {
     int c = (HW + 31) / 32;
     return c < 1 ? 1 : (c > 64 ? 64 : c);
 }
 
-// Partial sums: ws[((n * chunks + chunk) * groups + g) * 2 + {0: sum, 1: sum of squares}]
+// Workspace layout: [kGnCounters uint arrival counters (zero-initialised once by the caller; re-armed by the kernel)]
+// | [NB*chunks*groups*2] partial {sum, sum of squares} | [NB*groups*2] final {mean, rstd}.
+// The last block of a sample to finish folds the partials in a fixed order
+// (bit-reproducible) so the apply kernel reads 2 numbers per group instead of re-reducing `chunks` partials per CTA.
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int HW,
-                                                              int C, int groups, int chunks, float* __restrict__ ws) {
+                                                              int C, int groups, int chunks, float* __restrict__ ws,
+                                                              int NB, float eps) {
     // per (pixel-row slot, channel) partials, reduced in a fixed order below -> bit-reproducible statistics
     __shared__ float s_sum[kGnThreads * 8];
     __shared__ float s_sq[kGnThreads * 8];
@@ -71,8 +76,35 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat1
             b += s_sq[c];
         }
         float* dst = ws + ((static_cast<int64_t>(n) * chunks + chunk) * groups + g) * 2;
-        dst[0] = a;
-        dst[1] = b;
+        __stcg(dst, a);
+        __stcg(dst + 1, b);
+    }
+    // ---- last block of this sample finalizes
+    float* fin = ws + static_cast<int64_t>(NB) * chunks * groups * 2;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws) - kGnCounters;
+    __shared__ unsigned int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int old = atomicAdd(&counters[n], 1u);
+        s_last = (old == static_cast<unsigned int>(chunks - 1)) ? 1u : 0u;
+        if (s_last) counters[n] = 0u;  // re-arm
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int g = threadIdx.x; g < groups; g += kGnThreads) {
+        float a = 0.f, b = 0.f;
+        for (int c = 0; c < chunks; ++c) {
+            const float* src = ws + ((static_cast<int64_t>(n) * chunks + c) * groups + g) * 2;
+            a += __ldcg(src);
+            b += __ldcg(src + 1);
+        }
+        const float cnt = static_cast<float>(cpg) * static_cast<float>(HW);
+        const float mean = a / cnt;
+        const float var = fmaxf(b / cnt - mean * mean, 0.f);
+        fin[(static_cast<int64_t>(n) * groups + g) * 2] = mean;
+        fin[(static_cast<int64_t>(n) * groups + g) * 2 + 1] = rsqrtf(var + eps);
     }
 }
 
@@ -80,32 +112,17 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
                                                        __nv_bfloat16* __restrict__ y, int64_t ldy, int HW, int C,
                                                        int groups, int chunks, const float* __restrict__ ws,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       float eps, int fuse_silu, int apply_chunks) {
+                                                       int fuse_silu, int apply_chunks, int NB) {
     __shared__ float s_scale[kGnMaxC];
     __shared__ float s_shift[kGnMaxC];
-    __shared__ float s_mean[64];
-    __shared__ float s_rstd[64];
     const int n = blockIdx.y;
     const int cpg = C / groups;
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-        float a = 0.f, b = 0.f;
-        for (int c = 0; c < chunks; ++c) {
-            const float* src = ws + ((static_cast<int64_t>(n) * chunks + c) * groups + g) * 2;
-            a += src[0];
-            b += src[1];
-        }
-        const float cnt = static_cast<float>(cpg) * static_cast<float>(HW);
-        const float mean = a / cnt;
-        const float var = fmaxf(b / cnt - mean * mean, 0.f);
-        s_mean[g] = mean;
-        s_rstd[g] = rsqrtf(var + eps);
-    }
-    __syncthreads();
+    const float* fin = ws + static_cast<int64_t>(NB) * chunks * groups * 2 + static_cast<int64_t>(n) * groups * 2;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / cpg;
-        const float sc = (gamma ? gamma[c] : 1.f) * s_rstd[g];
+        const float sc = (gamma ? gamma[c] : 1.f) * fin[2 * g + 1];
         s_scale[c] = sc;
-        s_shift[c] = (beta ? beta[c] : 0.f) - s_mean[g] * sc;
+        s_shift[c] = (beta ? beta[c] : 0.f) - fin[2 * g] * sc;
     }
     __syncthreads();
 
@@ -113,10 +130,10 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
     const int ppc = (HW + apply_chunks - 1) / apply_chunks;
     const int p_begin = blockIdx.x * ppc;
     const int p_end = min(HW, p_begin + ppc);
-    const int64_t total = static_cast<int64_t>(p_end - p_begin) * CV;
-    for (int64_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int pix = p_begin + static_cast<int>(idx / CV);
-        const int c0 = static_cast<int>(idx % CV) * 8;
+    const int total = (p_end - p_begin) * CV;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int pix = p_begin + idx / CV;
+        const int c0 = (idx % CV) * 8;
         const int64_t row = static_cast<int64_t>(n) * HW + pix;
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + c0));
         const uint32_t u[4] = {v.x, v.y, v.z, v.w};
@@ -200,26 +217,28 @@ extern "C" {
 
 int64_t imagd_groupnorm_ws_bytes(int NB, int HW, int C, int groups) {
     (void)C;
-    return static_cast<int64_t>(NB) * imagd::gn_chunks(HW) * groups * 2 * sizeof(float);
+    return (imagd::kGnCounters + static_cast<int64_t>(NB) * imagd::gn_chunks(HW) * groups * 2 +
+            static_cast<int64_t>(NB) * groups * 2) * sizeof(float);
 }
 
 int imagd_groupnorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int NB, int HW, int C, int groups,
                          const float* gamma, const float* beta, float eps, int fuse_silu, void* ws, imagd_stream stream) {
     using namespace imagd;
     IMAGD_CHECK_ARG(x && y && ws, "groupnorm: null pointer");
-    IMAGD_CHECK_ARG(NB > 0 && HW > 0 && C > 0 && C % 8 == 0 && C <= kGnMaxC, "groupnorm: C=%d unsupported", C);
+    IMAGD_CHECK_ARG(NB > 0 && NB <= kGnCounters && HW > 0 && C > 0 && C % 8 == 0 && C <= kGnMaxC,
+                    "groupnorm: NB=%d C=%d unsupported", NB, C);
     IMAGD_CHECK_ARG(groups > 0 && groups <= 64 && C % groups == 0, "groupnorm: groups=%d", groups);
     IMAGD_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y), "groupnorm: alignment");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int chunks = gn_chunks(HW);
     gn_stats_kernel<<<dim3(chunks, NB), kGnThreads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C,
-                                                             groups, chunks, reinterpret_cast<float*>(ws));
+                                                             groups, chunks, reinterpret_cast<float*>(ws) + kGnCounters, NB, eps);
     IMAGD_LAUNCH_CHECK("gn_stats_kernel");
     int apply_chunks = (HW + 15) / 16;
     if (apply_chunks > 128) apply_chunks = 128;
     gn_apply_kernel<<<dim3(apply_chunks, NB), 256, 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, HW, C, groups, chunks,
-        reinterpret_cast<const float*>(ws), gamma, beta, eps, fuse_silu, apply_chunks);
+        reinterpret_cast<const float*>(ws) + kGnCounters, gamma, beta, fuse_silu, apply_chunks, NB);
     IMAGD_LAUNCH_CHECK("gn_apply_kernel");
     return IMAGD_OK;
 }

@@ -126,7 +126,7 @@ _gn_ws = {}
 def _gn_workspace(device, nbytes: int) -> torch.Tensor:
     ws = _gn_ws.get(device)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 16), device=device, dtype=torch.uint8)
+        ws = torch.zeros(max(nbytes, 1 << 20), device=device, dtype=torch.uint8)  # counters must start at 0
         _gn_ws[device] = ws
     return ws
 
