@@ -30,10 +30,10 @@ namespace imagd {
 struct AttnParams {
     int B, Lq, heads, hd;
     float scale_log2;  // sm_scale * log2(e)
-    int len[2];
-    int nq[2];       // stream s applies to samples [0, nq[s])
-    int bcast[2];
-    float oscale[2];
+    int len0, len1;        // keys per sample of stream 0 / 1
+    int nq1;               // stream 1 applies to samples [0, nq1)
+    int bcast0, bcast1;
+    float oscale0, oscale1;
     void* out;
     int64_t out_ld;
 };
@@ -86,8 +86,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int h = blockIdx.y;
     const int b = blockIdx.z;
 
-    const int nb0 = (p.len[0] + 127) / 128;
-    const int nb1 = (b < p.nq[1]) ? (p.len[1] + 127) / 128 : 0;
+    const int nb0 = (p.len0 + 127) / 128;
+    const int nb1 = (b < p.nq1) ? (p.len1 + 127) / 128 : 0;
     const int T = nb0 + nb1;
 
     if (threadIdx.x == 0) {
@@ -129,7 +129,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const uint32_t ph = (i / KV_STAGES) & 1;
                 const CUtensorMap* mk = s ? &tmK1 : &tmK0;
                 const CUtensorMap* mv = s ? &tmV1 : &tmV0;
-                const int bk = p.bcast[s] ? 0 : b;
+                const int bk = (s ? p.bcast1 : p.bcast0) ? 0 : b;
                 mbar_wait(&kv_empty[st], ph ^ 1);
                 mbar_arrive_expect_tx(&k_full[st], NATOM * kAtomBytes);
 #pragma unroll
@@ -203,32 +203,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 m_run = -INFINITY;
                 l_run = 0.f;
             }
-            const int valid = min(128, p.len[s] - j * 128) - half * 64;  // valid columns in my half (may be <= 0)
+            const int valid = min(128, (s ? p.len1 : p.len0) - j * 128) - half * 64;  // valid columns in my half (may be <= 0)
             mbar_wait(s_full, i & 1);
             tc_fence_after();
 
-            // scores of my half row -> registers (read TMEM once)
-            uint32_t v[64];
-            {
-                uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-                uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-                tmem_ld32(tmem_S + lane_addr + half * 64, lo);
-                tmem_ld32(tmem_S + lane_addr + half * 64 + 32, hi);
-                tmem_ld_wait();
-            }
+            // pass 1: maximum of my 64 columns, 32 at a time (registers are the scarce resource: 2 CTAs x 320
+            // threads per SM leaves 102 each, and there is no L1 left to absorb spills next to 226 KB of smem)
             float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-            if (valid >= 64) {
 #pragma unroll
-                for (int k = 0; k < 64; k += 4) {
-                    mx0 = fmaxf(mx0, __uint_as_float(v[k]));
-                    mx1 = fmaxf(mx1, __uint_as_float(v[k + 1]));
-                    mx2 = fmaxf(mx2, __uint_as_float(v[k + 2]));
-                    mx3 = fmaxf(mx3, __uint_as_float(v[k + 3]));
+            for (int cc = 0; cc < 2; ++cc) {
+                uint32_t v[32];
+                tmem_ld32(tmem_S + lane_addr + half * 64 + cc * 32, v);
+                tmem_ld_wait();
+                if (valid >= 64) {
+#pragma unroll
+                    for (int k = 0; k < 32; k += 4) {
+                        mx0 = fmaxf(mx0, __uint_as_float(v[k]));
+                        mx1 = fmaxf(mx1, __uint_as_float(v[k + 1]));
+                        mx2 = fmaxf(mx2, __uint_as_float(v[k + 2]));
+                        mx3 = fmaxf(mx3, __uint_as_float(v[k + 3]));
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        if (cc * 32 + k < valid) mx0 = fmaxf(mx0, __uint_as_float(v[k]));
                 }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 64; ++k)
-                    if (k < valid) mx0 = fmaxf(mx0, __uint_as_float(v[k]));
             }
             const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
             // Any m >= the true row max keeps exp2(s - m) <= 1, so the two half-row threads only have to agree on
@@ -255,29 +254,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             m_run = m_new;
 
-            // P = exp2(S*scale - m) for my 64 columns -> one 64-wide swizzled atom of the P tile
+            // pass 2: P = exp2(S*scale - m) for my 64 columns -> one 64-wide swizzled atom of the P tile
             float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
             const float sc = p.scale_log2;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float e[8];
-                if (valid >= 64) {
+            for (int cc = 0; cc < 2; ++cc) {
+                uint32_t v[32];
+                tmem_ld32(tmem_S + lane_addr + half * 64 + cc * 32, v);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) e[k] = ex2_approx(__uint_as_float(v[q * 8 + k]) * sc - m_new);
-                } else {
+                for (int q = 0; q < 4; ++q) {
+                    float e[8];
+                    if (valid >= 64) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        e[k] = (q * 8 + k < valid) ? ex2_approx(__uint_as_float(v[q * 8 + k]) * sc - m_new) : 0.f;
+                        for (int k = 0; k < 8; ++k) e[k] = ex2_approx(__uint_as_float(v[q * 8 + k]) * sc - m_new);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            e[k] = (cc * 32 + q * 8 + k < valid) ? ex2_approx(__uint_as_float(v[q * 8 + k]) * sc - m_new)
+                                                                : 0.f;
+                    }
+                    sum0 += e[0] + e[4];
+                    sum1 += e[1] + e[5];
+                    sum2 += e[2] + e[6];
+                    sum3 += e[3] + e[7];
+                    const uint32_t chunk = static_cast<uint32_t>(cc * 4 + q) ^ rx;
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16),
+                                 "r"(pack_bf16x2(e[0], e[1])), "r"(pack_bf16x2(e[2], e[3])),
+                                 "r"(pack_bf16x2(e[4], e[5])), "r"(pack_bf16x2(e[6], e[7]))
+                                 : "memory");
                 }
-                sum0 += e[0] + e[4];
-                sum1 += e[1] + e[5];
-                sum2 += e[2] + e[6];
-                sum3 += e[3] + e[7];
-                const uint32_t chunk = static_cast<uint32_t>(q) ^ rx;
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16),
-                             "r"(pack_bf16x2(e[0], e[1])), "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])),
-                             "r"(pack_bf16x2(e[6], e[7]))
-                             : "memory");
             }
             l_run = l_run * alpha + ((sum0 + sum1) + (sum2 + sum3));
 
@@ -297,10 +303,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const float lr = l_run + lbuf[((half ^ 1) * 2 + 1) * 128 + r];
         float w0, w1 = 0.f;
         if (nb1 > 0) {
-            w0 = p.oscale[0] / lf;
-            w1 = p.oscale[1] / lr;
+            w0 = p.oscale0 / lf;
+            w1 = p.oscale1 / lr;
         } else {
-            w0 = p.oscale[0] / lr;
+            w0 = p.oscale0 / lr;
         }
         const int q = q0 + r;
         __nv_bfloat16* orow =
@@ -383,14 +389,13 @@ extern "C" int imagd_attention_bf16(const void* q, int64_t q_ld, void* out, int6
     p.heads = heads;
     p.hd = head_dim;
     p.scale_log2 = sm_scale * 1.4426950408889634f;
-    p.len[0] = s0->len;
-    p.nq[0] = B;
-    p.bcast[0] = s0->broadcast;
-    p.oscale[0] = s0->out_scale;
-    p.len[1] = has1 ? s1->len : 0;
-    p.nq[1] = has1 ? (s1->n_query_samples < B ? s1->n_query_samples : B) : 0;
-    p.bcast[1] = has1 ? s1->broadcast : 0;
-    p.oscale[1] = has1 ? s1->out_scale : 0.f;
+    p.len0 = s0->len;
+    p.bcast0 = s0->broadcast;
+    p.oscale0 = s0->out_scale;
+    p.len1 = has1 ? s1->len : 0;
+    p.nq1 = has1 ? (s1->n_query_samples < B ? s1->n_query_samples : B) : 0;
+    p.bcast1 = has1 ? s1->broadcast : 0;
+    p.oscale1 = has1 ? s1->out_scale : 0.f;
     p.out = out;
     p.out_ld = out_ld;
 
@@ -402,7 +407,7 @@ extern "C" int imagd_attention_bf16(const void* q, int64_t q_ld, void* out, int6
     rc = make_head_tmap(&tms[2], s0->v, s0->ld, head_dim, heads, s0->len, s0->broadcast ? 1 : B, s0->sample_rows);
     if (rc != IMAGD_OK) return rc;
     if (has1) {
-        const int ns = s1->broadcast ? 1 : p.nq[1];
+        const int ns = s1->broadcast ? 1 : p.nq1;
         rc = make_head_tmap(&tms[3], s1->k, s1->ld, head_dim, heads, s1->len, ns, s1->sample_rows);
         if (rc != IMAGD_OK) return rc;
         rc = make_head_tmap(&tms[4], s1->v, s1->ld, head_dim, heads, s1->len, ns, s1->sample_rows);
