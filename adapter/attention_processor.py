@@ -63,6 +63,8 @@ class CacheAttnProcessor2_0(_ProcState):
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
                  **kwargs):
+        if kwargs.get("_prepare_only", False):
+            return attention_forward(self, attn, hidden_states, encoder_hidden_states, prepare_only=True)
         self.cache["hidden_states"] = hidden_states
         return attention_forward(self, attn, hidden_states, encoder_hidden_states)
 
@@ -82,7 +84,8 @@ class RefSAttnProcessor2_0(_ModuleProc):
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
                  num_images_per_prompt=1, cond_hidden_states=None, sa_hidden_states=None, ref_samples=None, **kwargs):
         return attention_forward(self, attn, hidden_states, encoder_hidden_states,
-                                 second=ref_stream(self, hidden_states, sa_hidden_states, ref_samples))
+                                 second=ref_stream(self, hidden_states, sa_hidden_states, ref_samples),
+                                 prepare_only=kwargs.get("_prepare_only", False))
 
 
 class CAttnProcessor2_0(_ModuleProc):
@@ -97,7 +100,8 @@ class CAttnProcessor2_0(_ModuleProc):
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
                  num_images_per_prompt=1, cond_hidden_states=None, sa_hidden_states=None, **kwargs):
-        return attention_forward(self, attn, hidden_states, encoder_hidden_states)
+        return attention_forward(self, attn, hidden_states, encoder_hidden_states,
+                                 prepare_only=kwargs.get("_prepare_only", False))
 
 
 class _LoraRefBase(_ModuleProc):
@@ -122,7 +126,8 @@ class _LoraRefBase(_ModuleProc):
                  num_images_per_prompt=1, cond_hidden_states=None, sa_hidden_states=None, ref_samples=None, **kwargs):
         return attention_forward(self, attn, hidden_states, encoder_hidden_states, lora=self._lora(),
                                  lora_scale=float(self.lora_scale),
-                                 second=ref_stream(self, hidden_states, sa_hidden_states, ref_samples))
+                                 second=ref_stream(self, hidden_states, sa_hidden_states, ref_samples),
+                                 prepare_only=kwargs.get("_prepare_only", False))
 
 
 class LoraRefSAttnProcessor2_0(_LoraRefBase):
@@ -165,7 +170,8 @@ class LoRAIPAttnProcessor2_0(_ModuleProc):
         second = (encoder_hidden_states, self.to_k_ip, self.to_v_ip, float(self.scale), hidden_states.shape[0],
                   end_pos, self.num_tokens)
         return attention_forward(self, attn, hidden_states, encoder_hidden_states, lora=self._lora(),
-                                 lora_scale=float(self.lora_scale), second=second, text_len=end_pos)
+                                 lora_scale=float(self.lora_scale), second=second, text_len=end_pos,
+                                 prepare_only=kwargs.get("_prepare_only", False))
 
 
 class IPAttnProcessor2_0(_ModuleProc):
@@ -188,7 +194,8 @@ class IPAttnProcessor2_0(_ModuleProc):
         end_pos = encoder_hidden_states.shape[1] - self.num_tokens
         second = (encoder_hidden_states, self.to_k_ip, self.to_v_ip, float(self.scale), hidden_states.shape[0],
                   end_pos, self.num_tokens)
-        return attention_forward(self, attn, hidden_states, encoder_hidden_states, second=second, text_len=end_pos)
+        return attention_forward(self, attn, hidden_states, encoder_hidden_states, second=second, text_len=end_pos,
+                                 prepare_only=kwargs.get("_prepare_only", False))
 
 
 class BaseSAttnProcessor2_0(_ModuleProc):

@@ -1,4 +1,5 @@
 // Library-level entry points of the C ABI: version, error string, device check, TMA descriptor encoding.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -13,6 +14,15 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("IMAGD_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 int cuda_fail(cudaError_t e, const char* what) {

@@ -80,6 +80,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* o_full = p_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128;
@@ -115,6 +116,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_S = tmem_base;
     const uint32_t tmem_O = tmem_base + 128;
+    pdl_wait();
 
     if (warp == 8) {
         // ------------------------------------------------ TMA producer
@@ -362,9 +364,8 @@ static int launch_attn(const CUtensorMap* tms, const AttnParams& p, cudaStream_t
         attr_set = true;
     }
     dim3 grid((p.Lq + 127) / 128, p.heads, p.B);
-    attention_tc_kernel<HD_MMA, NATOM, KV_STAGES><<<grid, 320, C::kTotal, stream>>>(tms[0], tms[1], tms[2], tms[3],
-                                                                                   tms[4], p);
-    IMAGD_LAUNCH_CHECK("attention_tc_kernel");
+    IMAGD_CUDA(launch_pdl(attention_tc_kernel<HD_MMA, NATOM, KV_STAGES>, grid, dim3(320), C::kTotal, stream, tms[0],
+                          tms[1], tms[2], tms[3], tms[4], p));
     return IMAGD_OK;
 }
 

@@ -1,6 +1,8 @@
 // HBM-/latency-bound glue kernels of the denoising step: skip concat (+ControlNet residual), nearest-2x upsample,
 // stride-2 im2col, thin direct 3x3 convs (conv_in / conv_out / ControlNet conditioning embedding), layout
 // conversion at the pipeline boundary, timestep embedding, small-M linears, and the fused CFG + DDIM step.
+#include <algorithm>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -19,6 +21,8 @@ __global__ void concat_add_kernel(const __nv_bfloat16* __restrict__ a, int64_t l
                                   const __nv_bfloat16* __restrict__ b, int64_t ldb, int Cb,
                                   const __nv_bfloat16* __restrict__ rb, int64_t ldrb, __nv_bfloat16* __restrict__ out,
                                   int64_t ldo, int64_t rows) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int CV = (Ca + Cb) / 8, CVa = Ca / 8;
     const int64_t total = rows * CV;
     for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -40,6 +44,8 @@ __global__ void concat_add_kernel(const __nv_bfloat16* __restrict__ a, int64_t l
 
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int NB, int H,
                                   int W, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int CV = C / 8;
     const int64_t total = static_cast<int64_t>(NB) * 4 * H * W * CV;
     for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -57,6 +63,8 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bflo
 
 __global__ void im2col3x3_s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, int NB, int H,
                                     int W, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int Ho = H / 2, Wo = W / 2, CV = C / 8;
     const int64_t total = static_cast<int64_t>(NB) * Ho * Wo * 9 * CV;
     for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -82,6 +90,8 @@ __global__ void conv3x3_direct_thread_kernel(const __nv_bfloat16* __restrict__ x
                                              const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
                                              void* __restrict__ y, int Cout, int stride, int act, int out_nchw_f32,
                                              const __nv_bfloat16* __restrict__ add) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
     const int64_t total = static_cast<int64_t>(NB) * Ho * Wo * Cout;
     for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -118,6 +128,8 @@ __global__ void __launch_bounds__(256) conv3x3_cin4_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ bias,
                                                            __nv_bfloat16* __restrict__ y, int Cout,
                                                            const __nv_bfloat16* __restrict__ add) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float s_w[];  // [Cout][37] (row padded: fewer bank conflicts) + [Cout] bias
     for (int i = threadIdx.x; i < Cout * 36; i += blockDim.x) s_w[(i / 36) * 37 + i % 36] = __bfloat162float(w[i]);
     float* s_b = s_w + Cout * 37;
@@ -168,6 +180,8 @@ __global__ void __launch_bounds__(256) conv3x3_direct_warp_kernel(const __nv_bfl
                                                                   int W, int Cin, const __nv_bfloat16* __restrict__ w,
                                                                   const float* __restrict__ bias, void* __restrict__ y,
                                                                   int act, int out_nchw_f32) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int Cout = COUT;
     const int64_t pix = blockIdx.x * static_cast<int64_t>(blockDim.x / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -217,6 +231,8 @@ __global__ void __launch_bounds__(256) conv3x3_direct_warp_kernel(const __nv_bfl
 
 __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int NB, int C,
                                              int H, int W, int Cpad, int repeat) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t total = static_cast<int64_t>(NB) * repeat * H * W * Cpad;
     for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -231,6 +247,8 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_b
 
 __global__ void timestep_embedding_kernel(const float* __restrict__ timesteps, const int32_t* __restrict__ step_ptr,
                                           float* __restrict__ out, int NB, int dim) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int half = dim / 2;
     const float t = timesteps[step_ptr ? *step_ptr : 0];
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < NB * dim; idx += gridDim.x * blockDim.x) {
@@ -247,6 +265,8 @@ __global__ void __launch_bounds__(256) linear_small_m_kernel(const float* __rest
                                                              const __nv_bfloat16* __restrict__ W, int64_t ldw,
                                                              const float* __restrict__ bias, float* __restrict__ out,
                                                              int64_t ldo, int M, int N, int K, int act_in, int act_out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int n = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
@@ -303,6 +323,8 @@ __global__ void cfg_ddim_step_kernel(const float* __restrict__ eps_c, const floa
                                      int32_t* __restrict__ step_ptr, const float* __restrict__ mask,
                                      const float* __restrict__ img, const float* __restrict__ noise,
                                      const float* __restrict__ blend_coef, int NB, int C, int HW) {
+    pdl_launch_dependents();
+    pdl_wait();
     unsigned int* done_counter = reinterpret_cast<unsigned int*>(step_ptr + 1);
     const int step = *step_ptr;
     const float sa_t = coef[step * 4 + 0], sb_t = coef[step * 4 + 1], sa_p = coef[step * 4 + 2],
@@ -362,11 +384,10 @@ int imagd_concat_add_bf16(const void* a, int64_t lda, int Ca, const void* res_a,
                     "concat_add: channel counts / strides must be multiples of 8");
     IMAGD_CHECK_ARG((!res_a || ld_ra % 8 == 0) && (!res_b || ld_rb % 8 == 0), "concat_add: residual stride");
     const int64_t total = rows * ((Ca + Cb) / 8);
-    concat_add_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    IMAGD_CUDA(launch_pdl(concat_add_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
         reinterpret_cast<const __nv_bfloat16*>(a), lda, Ca, reinterpret_cast<const __nv_bfloat16*>(res_a), ld_ra,
         reinterpret_cast<const __nv_bfloat16*>(b), ldb, Cb, reinterpret_cast<const __nv_bfloat16*>(res_b), ld_rb,
-        reinterpret_cast<__nv_bfloat16*>(out), ldo, rows);
-    IMAGD_LAUNCH_CHECK("concat_add_kernel");
+        reinterpret_cast<__nv_bfloat16*>(out), ldo, rows));
     return IMAGD_OK;
 }
 
@@ -374,9 +395,8 @@ int imagd_upsample2x_bf16(const void* x, void* y, int NB, int H, int W, int C, i
     using namespace imagd;
     IMAGD_CHECK_ARG(x && y && NB > 0 && H > 0 && W > 0 && C % 8 == 0, "upsample2x: bad args");
     const int64_t total = static_cast<int64_t>(NB) * 4 * H * W * (C / 8);
-    upsample2x_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), NB, H, W, C);
-    IMAGD_LAUNCH_CHECK("upsample2x_kernel");
+    IMAGD_CUDA(launch_pdl(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), NB, H, W, C));
     return IMAGD_OK;
 }
 
@@ -384,9 +404,8 @@ int imagd_im2col3x3_s2_bf16(const void* x, void* col, int NB, int H, int W, int 
     using namespace imagd;
     IMAGD_CHECK_ARG(x && col && NB > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "im2col_s2: bad args");
     const int64_t total = static_cast<int64_t>(NB) * (H / 2) * (W / 2) * 9 * (C / 8);
-    im2col3x3_s2_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(col), NB, H, W, C);
-    IMAGD_LAUNCH_CHECK("im2col3x3_s2_kernel");
+    IMAGD_CUDA(launch_pdl(im2col3x3_s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(col), NB, H, W, C));
     return IMAGD_OK;
 }
 
@@ -399,10 +418,9 @@ int imagd_conv3x3_direct_bf16(const void* x, int NB, int H, int W, int Cin, cons
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (Cout == 4 && Cin % 8 == 0 && Cin >= 64 && stride == 1 && !add_nhwc) {
         const int64_t pixels = static_cast<int64_t>(NB) * H * W;
-        conv3x3_direct_warp_kernel<4><<<static_cast<int>((pixels + 7) / 8), 256, 0, st>>>(
+        IMAGD_CUDA(launch_pdl(conv3x3_direct_warp_kernel<4>, dim3(static_cast<int>((pixels + 7) / 8)), dim3(256), 0, st, 
             reinterpret_cast<const __nv_bfloat16*>(x), NB, H, W, Cin, reinterpret_cast<const __nv_bfloat16*>(w), bias, y,
-            act, out_nchw_f32);
-        IMAGD_LAUNCH_CHECK("conv3x3_direct_warp_kernel");
+            act, out_nchw_f32));
         return IMAGD_OK;
     }
     if (Cin == 4 && Cout % 64 == 0 && Cout <= 640 && stride == 1 && act == IMAGD_ACT_NONE && !out_nchw_f32) {
@@ -413,19 +431,17 @@ int imagd_conv3x3_direct_bf16(const void* x, int NB, int H, int W, int Cin, cons
             IMAGD_CUDA(cudaFuncSetAttribute(conv3x3_cin4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 640 * 38 * 4));
             attr_set = true;
         }
-        conv3x3_cin4_kernel<<<static_cast<int>((pixels + 31) / 32), 256, smem, st>>>(
+        IMAGD_CUDA(launch_pdl(conv3x3_cin4_kernel, dim3(static_cast<int>((pixels + 31) / 32)), dim3(256), smem, st, 
             reinterpret_cast<const __nv_bfloat16*>(x), NB, H, W, reinterpret_cast<const __nv_bfloat16*>(w), bias,
-            reinterpret_cast<__nv_bfloat16*>(y), Cout, reinterpret_cast<const __nv_bfloat16*>(add_nhwc));
-        IMAGD_LAUNCH_CHECK("conv3x3_cin4_kernel");
+            reinterpret_cast<__nv_bfloat16*>(y), Cout, reinterpret_cast<const __nv_bfloat16*>(add_nhwc)));
         return IMAGD_OK;
     }
     const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
     const int64_t total = static_cast<int64_t>(NB) * Ho * Wo * Cout;
-    conv3x3_direct_thread_kernel<<<grid_for(total, 256) * 4 > 148 * 64 ? 148 * 64 : grid_for(total, 256) * 4, 256, 0,
-                                   st>>>(reinterpret_cast<const __nv_bfloat16*>(x), NB, H, W, Cin,
+    const int tgrid = std::min(grid_for(total, 256) * 4, 148 * 64);
+    IMAGD_CUDA(launch_pdl(conv3x3_direct_thread_kernel, dim3(tgrid), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(x), NB, H, W, Cin,
                                          reinterpret_cast<const __nv_bfloat16*>(w), bias, y, Cout, stride, act,
-                                         out_nchw_f32, reinterpret_cast<const __nv_bfloat16*>(add_nhwc));
-    IMAGD_LAUNCH_CHECK("conv3x3_direct_thread_kernel");
+                                         out_nchw_f32, reinterpret_cast<const __nv_bfloat16*>(add_nhwc)));
     return IMAGD_OK;
 }
 
@@ -434,9 +450,8 @@ int imagd_nchw_f32_to_nhwc_bf16(const float* x, void* y, int NB, int C, int H, i
     using namespace imagd;
     IMAGD_CHECK_ARG(x && y && NB > 0 && C > 0 && Cpad >= C && repeat >= 1, "nchw_to_nhwc: bad args");
     const int64_t total = static_cast<int64_t>(NB) * repeat * H * W * Cpad;
-    nchw_f32_to_nhwc_bf16_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, reinterpret_cast<__nv_bfloat16*>(y), NB, C, H, W, Cpad, repeat);
-    IMAGD_LAUNCH_CHECK("nchw_f32_to_nhwc_bf16_kernel");
+    IMAGD_CUDA(launch_pdl(nchw_f32_to_nhwc_bf16_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+        x, reinterpret_cast<__nv_bfloat16*>(y), NB, C, H, W, Cpad, repeat));
     return IMAGD_OK;
 }
 
@@ -444,9 +459,7 @@ int imagd_timestep_embedding(const float* timesteps, const int32_t* step_ptr, fl
                              imagd_stream stream) {
     using namespace imagd;
     IMAGD_CHECK_ARG(timesteps && out && NB > 0 && dim > 0 && dim % 2 == 0, "timestep_embedding: bad args");
-    timestep_embedding_kernel<<<grid_for(static_cast<int64_t>(NB) * dim, 256), 256, 0,
-                                static_cast<cudaStream_t>(stream)>>>(timesteps, step_ptr, out, NB, dim);
-    IMAGD_LAUNCH_CHECK("timestep_embedding_kernel");
+    IMAGD_CUDA(launch_pdl(timestep_embedding_kernel, dim3(grid_for(static_cast<int64_t>(NB) * dim, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), timesteps, step_ptr, out, NB, dim));
     return IMAGD_OK;
 }
 
@@ -456,9 +469,8 @@ int imagd_linear_small_m(const float* x, int64_t ldx, const void* W, int64_t ldw
     IMAGD_CHECK_ARG(x && W && out && M > 0 && N > 0 && K > 0, "linear_small_m: bad args");
     IMAGD_CHECK_ARG(K % 8 == 0 && ldx % 4 == 0 && ldw % 8 == 0 && aligned16(x) && aligned16(W),
                     "linear_small_m: K / stride alignment");
-    linear_small_m_kernel<<<(N + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, ldx, reinterpret_cast<const __nv_bfloat16*>(W), ldw, bias, out, ldo, M, N, K, act_in, act_out);
-    IMAGD_LAUNCH_CHECK("linear_small_m_kernel");
+    IMAGD_CUDA(launch_pdl(linear_small_m_kernel, dim3((N + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+        x, ldx, reinterpret_cast<const __nv_bfloat16*>(W), ldw, bias, out, ldo, M, N, K, act_in, act_out));
     return IMAGD_OK;
 }
 
@@ -471,9 +483,8 @@ int imagd_cfg_ddim_step(const float* eps_cond, const float* eps_uncond, float gu
     const int64_t total = static_cast<int64_t>(NB) * C * HW;
     int grid = grid_for(total, 256);
     if (grid > 148) grid = 148;
-    cfg_ddim_step_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        eps_cond, eps_uncond, guidance, latents, coef, step_ptr, mask, image_latents, noise, blend_coef, NB, C, HW);
-    IMAGD_LAUNCH_CHECK("cfg_ddim_step_kernel");
+    IMAGD_CUDA(launch_pdl(cfg_ddim_step_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+        eps_cond, eps_uncond, guidance, latents, coef, step_ptr, mask, image_latents, noise, blend_coef, NB, C, HW));
     return IMAGD_OK;
 }
 

@@ -72,6 +72,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tmem_full_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
@@ -104,6 +105,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // predecessor's output (our A operand / residual) and our output buffer are safe from here on
 
     if (warp == 0) {
         if (elect_one()) {
@@ -411,8 +413,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     }
     const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
     dim3 grid(m_tiles, n_tiles, p.splits);
-    gemm_tc_kernel<BLOCK_N, STAGES><<<grid, 192, L::kTotal, stream>>>(tmA, tmB, p);
-    IMAGD_LAUNCH_CHECK("gemm_tc_kernel");
+    IMAGD_CUDA(launch_pdl(gemm_tc_kernel<BLOCK_N, STAGES>, grid, dim3(192), L::kTotal, stream, tmA, tmB, p));
     return IMAGD_OK;
 }
 

@@ -21,6 +21,8 @@ __host__ __device__ inline int gn_chunks(int HW) {
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int HW,
                                                               int C, int groups, int chunks, float* __restrict__ ws,
                                                               int NB, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     // per (pixel-row slot, channel) partials, reduced in a fixed order below -> bit-reproducible statistics
     __shared__ float s_sum[kGnThreads * 8];
     __shared__ float s_sq[kGnThreads * 8];
@@ -113,6 +115,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
                                                        int groups, int chunks, const float* __restrict__ ws,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int fuse_silu, int apply_chunks, int NB) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float s_scale[kGnMaxC];
     __shared__ float s_shift[kGnMaxC];
     const int n = blockIdx.y;
@@ -157,6 +161,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
                                                         __nv_bfloat16* __restrict__ y, int64_t ldy, int rows, int C,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -231,15 +237,13 @@ int imagd_groupnorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int N
     IMAGD_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y), "groupnorm: alignment");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int chunks = gn_chunks(HW);
-    gn_stats_kernel<<<dim3(chunks, NB), kGnThreads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C,
-                                                             groups, chunks, reinterpret_cast<float*>(ws) + kGnCounters, NB, eps);
-    IMAGD_LAUNCH_CHECK("gn_stats_kernel");
+    IMAGD_CUDA(launch_pdl(gn_stats_kernel, dim3(dim3(chunks, NB)), dim3(kGnThreads), 0, st, reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C,
+                                                             groups, chunks, reinterpret_cast<float*>(ws) + kGnCounters, NB, eps));
     int apply_chunks = (HW + 15) / 16;
     if (apply_chunks > 128) apply_chunks = 128;
-    gn_apply_kernel<<<dim3(apply_chunks, NB), 256, 0, st>>>(
+    IMAGD_CUDA(launch_pdl(gn_apply_kernel, dim3(dim3(apply_chunks, NB)), dim3(256), 0, st, 
         reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, HW, C, groups, chunks,
-        reinterpret_cast<const float*>(ws) + kGnCounters, gamma, beta, fuse_silu, apply_chunks, NB);
-    IMAGD_LAUNCH_CHECK("gn_apply_kernel");
+        reinterpret_cast<const float*>(ws) + kGnCounters, gamma, beta, fuse_silu, apply_chunks, NB));
     return IMAGD_OK;
 }
 
@@ -250,10 +254,9 @@ int imagd_layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int r
     IMAGD_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && C <= 2048, "layernorm: C=%d unsupported", C);
     IMAGD_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y), "layernorm: alignment");
     const int wpb = 8;
-    layernorm_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+    IMAGD_CUDA(launch_pdl(layernorm_kernel, dim3((rows + wpb - 1) / wpb), dim3(wpb * 32), 0, static_cast<cudaStream_t>(stream), 
         reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, rows, C, gamma, beta,
-        eps);
-    IMAGD_LAUNCH_CHECK("layernorm_kernel");
+        eps));
     return IMAGD_OK;
 }
 

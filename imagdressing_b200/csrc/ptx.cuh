@@ -63,6 +63,13 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the library is launched with programmaticStreamSerialization: it may start while its predecessor
+// in the stream is still draining, runs its prologue (barrier init, TMEM alloc, descriptor prefetch, smem tables),
+// and must execute pdl_wait() before it touches global memory the predecessor may read or write.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

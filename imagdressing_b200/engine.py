@@ -29,6 +29,9 @@ class DenoiseEngine:
         self.scheduler = scheduler
         self.use_cuda_graph = use_cuda_graph
         self._states = {}
+        self._garment = None
+        self._dummy = {}
+        self._zero_t = None
 
     # ------------------------------------------------------------------ garment pass
     @torch.no_grad()
@@ -36,13 +39,44 @@ class DenoiseEngine:
         """ref-UNet forward at t = 0 with the garment tokens in the text slot; returns the attn1 processor inputs
         (post-LayerNorm hidden states) keyed by processor name (IMAGDressing_v1_pipeline.py:465-479)."""
         ru = self.reference_unet
-        zero_t = torch.zeros(1, device=ref_latents.device, dtype=torch.float32)
-        ru.forward_tokens(ref_latents.float().contiguous(), zero_t, garment_tokens)
-        sa = {}
-        for name, proc in ru.attn_processors.items():
-            if "attn1" in name:
-                sa[name] = proc.cache["hidden_states"]
-        return sa
+        dev = ref_latents.device
+
+        def collect():
+            return {name: proc.cache["hidden_states"] for name, proc in ru.attn_processors.items() if "attn1" in name}
+
+        def run(lat, tok):
+            ru.forward_tokens(lat, self._zero_t, tok)
+
+        if getattr(self, "_zero_t", None) is None or self._zero_t.device != dev:
+            self._zero_t = torch.zeros(1, device=dev, dtype=torch.float32)
+        if not self.use_cuda_graph:
+            run(ref_latents.float().contiguous(), garment_tokens)
+            return collect()
+        key = (tuple(ref_latents.shape), tuple(garment_tokens.shape))
+        g = self._garment
+        if g is None or g["key"] != key:
+            # first call for this shape: eager (packs weights, sizes workspaces), then capture the pass once;
+            # its feature taps are tensors of the graph's pool, so their addresses are stable across images
+            g = dict(key=key, lat=ref_latents.float().contiguous().clone(),
+                     tok=garment_tokens.to(torch.bfloat16).contiguous().clone())
+            run(g["lat"], g["tok"])
+            for proc in ru.attn_processors.values():  # the token K|V projection must be IN the graph: force a miss
+                if hasattr(proc, "invalidate_packed"):
+                    proc.invalidate_packed()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            before = _lib.launch_count
+            with torch.cuda.graph(graph):
+                run(g["lat"], g["tok"])
+            g["launches"] = _lib.launch_count - before
+            _lib.launch_count = before
+            g["graph"], g["sa"] = graph, collect()
+            self._garment = g
+        g["lat"].copy_(ref_latents)
+        g["tok"].copy_(garment_tokens)
+        g["graph"].replay()
+        _lib.launch_count += g["launches"]
+        return g["sa"]
 
     # ------------------------------------------------------------------ one step
     def _step(self, st):
@@ -58,6 +92,33 @@ class DenoiseEngine:
                                        out=st["eps"], sample_repeat=2)
         ops.cfg_ddim_step(eps[:n], eps[n:], st["guidance"], lat, st["coef"], st["step_ptr"], mask=st.get("mask"),
                           image_latents=st.get("image_latents"), noise=st.get("noise"), blend_coef=st.get("blend"))
+
+    def _refresh(self, st) -> bool:
+        """Per-image refresh of the step-invariant projections without running a step. Returns False when a
+        processor outside this package is installed (then the caller runs a full eager step instead)."""
+        from .modeling import Attention
+
+        n = st["n"]
+        jobs = [(self.unet, st["text"], st["kwargs"])]
+        if self.controlnet is not None and st.get("control_cond") is not None:
+            jobs.append((self.controlnet, st["control_text"], {}))
+        for model, _, _ in jobs:
+            for m in model.modules():
+                if isinstance(m, Attention) and not hasattr(m.processor, "_kv2_memo"):
+                    return False
+        for model, text, kw in jobs:
+            for m in model.modules():
+                if isinstance(m, Attention):
+                    proc = m.processor
+                    proc._kv2_memo.clear()  # garment taps are rewritten by a graph replay: identity says nothing
+                    dummy = self._dummy.get(m.query_dim)
+                    if dummy is None or dummy.shape[0] != 2 * n:
+                        dummy = self._dummy[m.query_dim] = torch.empty(2 * n, 1, m.query_dim, device=text.device,
+                                                                       dtype=torch.bfloat16)
+                    proc(m, dummy, encoder_hidden_states=text if m.is_cross else None, _prepare_only=True, **kw)
+        if len(jobs) > 1:
+            self.controlnet.cond_embedding(st["control_cond"], 2 * n)
+        return True
 
     # ------------------------------------------------------------------ sampling
     @torch.no_grad()
@@ -128,13 +189,14 @@ class DenoiseEngine:
                     callback(i, int(timesteps[i]), lat)
             return lat.clone()
 
-        # One eager step on scratch latents refreshes everything that is per-image but step-invariant (text and
-        # garment K/V projections, ControlNet conditioning embedding — recomputed in place, so device addresses
-        # are unchanged), packs weights on first use and sizes workspaces. The step graph is captured once per
-        # configuration and replayed for every step of every later image.
-        self._step(st)
-        lat.copy_(st["lat0"])
-        st["step_ptr"].zero_()
+        # Refresh everything that is per-image but step-invariant (text and garment K/V projections, ControlNet
+        # conditioning embedding) — recomputed IN PLACE, so the device addresses the captured graph holds stay
+        # valid. The first call for a configuration runs one full eager step instead (packs weights, sizes
+        # workspaces) and then captures the step graph, which is replayed for every step of every later image.
+        if st["graph"] is None or not self._refresh(st):
+            self._step(st)
+            lat.copy_(st["lat0"])
+            st["step_ptr"].zero_()
         if st["graph"] is None:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()

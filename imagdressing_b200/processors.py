@@ -109,11 +109,15 @@ class _ProcState:
 
 def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor], *,
                       lora: Optional[dict] = None, lora_scale: float = 0.0,
-                      second: Optional[tuple] = None, text_len: Optional[int] = None) -> torch.Tensor:
+                      second: Optional[tuple] = None, text_len: Optional[int] = None,
+                      prepare_only: bool = False) -> Optional[torch.Tensor]:
     """hidden_states [B, L, C]; returns [B, L, C] in hidden_states.dtype.
 
     second = (source [Bs, Ls, Cs], to_k, to_v, out_scale, n_query_samples[, first, length]): the extra KV stream,
     optionally a [first, first+length) token window of the source.
+    prepare_only: compute (in place) only what is invariant over the denoising steps — the context K|V projection
+    and the second stream's K|V projection — and return None (DenoiseEngine refreshes these once per image and
+    replays a captured CUDA graph for the steps).
     text_len: use only the first text_len context tokens for stream 0 (LoRAIP strips the IP tokens, :811-815).
     """
     in_dtype = hidden_states.dtype
@@ -123,7 +127,9 @@ def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_st
     x = as_bf16(hidden_states)
     lkey = f"{id(proc)}:{lora_scale}" if lora else "base"
 
-    if encoder_hidden_states is None:
+    if encoder_hidden_states is None and prepare_only:
+        q2 = s0 = None
+    elif encoder_hidden_states is None:
         wqkv = attn.packed("qkv:" + lkey, lambda: torch.cat(
             [_merged(attn.to_q, lora and lora["q"], lora_scale), _merged(attn.to_k, lora and lora["k"], lora_scale),
              _merged(attn.to_v, lora and lora["v"], lora_scale)], 0).to(BF16).contiguous())
@@ -132,7 +138,7 @@ def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_st
         s0 = ops.kv_stream(_flat(qkv[..., C:2 * C]), _flat(qkv[..., 2 * C:]), L)
     else:
         wq = attn.packed("q:" + lkey, lambda: _merged(attn.to_q, lora and lora["q"], lora_scale).to(BF16).contiguous())
-        q2 = _flat(ops.gemm(x, wq))
+        q2 = None if prepare_only else _flat(ops.gemm(x, wq))
         ctx_src = encoder_hidden_states
         Lc = ctx_src.shape[1] if text_len is None else text_len
         kv = proc._kv_memo.get(ctx_src, (lkey, Lc))
@@ -161,6 +167,8 @@ def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_st
             raise ValueError(f"second KV stream has batch {kv2.shape[0]} but {n_q} query samples use it")
         length = second[6] if len(second) > 6 else kv2.shape[1] - first
         s1 = _stream_from_kv(kv2, C, length, first, broadcast=bcast, n_query_samples=n_q, out_scale=out_scale)
+    if prepare_only:
+        return None
 
     o = ops.attention(q2, B, L, heads, hd, s0, s1)  # [B*L, C]
 
@@ -195,7 +203,8 @@ class AttnProcessor2_0(_ProcState):
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
                  **kwargs):
-        return attention_forward(self, attn, hidden_states, encoder_hidden_states)
+        return attention_forward(self, attn, hidden_states, encoder_hidden_states,
+                                 prepare_only=kwargs.get("_prepare_only", False))
 
 
 def ref_stream(proc, hidden_states, sa_hidden_states, ref_samples):

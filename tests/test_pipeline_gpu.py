@@ -1,0 +1,112 @@
+"""GPU parity of the whole path through the PUBLIC pipeline classes (dressing_sd.pipelines...IMAGDressing_v1):
+garment pass + CFG denoising loop (CUDA-graph replayed) vs the oracle loop (fp32, reference-style batch-1 calls).
+Small latents / few steps so the oracle finishes in seconds; two different images back to back through the SAME
+pipeline object check that the per-image refresh of the cached projections and the graph replay do not leak state
+from one image to the next. Tolerance: calibrated like test_unet_gpu (bf16 chain): rel-L2 <= 4e-2 after 4 steps."""
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+H = W = 32
+STEPS = 4
+
+
+def hidden_of(name):
+    for k, v in (("mid", 1280), ("up_blocks.1", 1280), ("up_blocks.2", 640), ("up_blocks.3", 320), ("down_blocks.0", 320),
+                 ("down_blocks.1", 640), ("down_blocks.2", 1280)):
+        if name.startswith(k):
+            return v
+    raise KeyError(name)
+
+
+def build(dev, controlnet=False):
+    from adapter.attention_processor import CacheAttnProcessor2_0, CAttnProcessor2_0, RefSAttnProcessor2_0
+    from imagdressing_b200 import modeling
+    from imagdressing_b200.scheduler import DDIMScheduler
+    from oracle import processors as op
+    from oracle import unet as ou
+
+    o, p = ou.UNet2DConditionModel(), modeling.UNet2DConditionModel()
+    o.set_attn_processor({n: (op.RefSAttnProcessor(n, hidden_of(n), scale=1.0) if "attn1" in n else op.CAttnProcessor(n))
+                          for n in o.attn_processors})
+    p.set_attn_processor({n: (RefSAttnProcessor2_0(n, hidden_of(n)) if "attn1" in n else CAttnProcessor2_0(n, hidden_of(n), 768))
+                          for n in p.attn_processors})
+    ro, rp = ou.UNet2DConditionModel(), modeling.UNet2DConditionModel()
+    ro.set_attn_processor({n: op.CacheAttnProcessor() for n in ro.attn_processors})
+    rp.set_attn_processor({n: CacheAttnProcessor2_0() for n in rp.attn_processors})
+    for m, seed in ((o, 0), (ro, 1)):
+        ou.init_synthetic_(m, seed)
+    for m, seed in ((p, 0), (rp, 1)):
+        modeling.init_synthetic_(m, seed)
+    co = cp = None
+    if controlnet:
+        co, cp = ou.ControlNetModel(), modeling.ControlNetModel()
+        ou.init_synthetic_(co, 2)
+        modeling.init_synthetic_(cp, 2)
+        co, cp = co.to(dev).eval(), cp.to(dev).eval()
+    sched = DDIMScheduler(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                          clip_sample=False, set_alpha_to_one=False, steps_offset=1)
+    return (o.to(dev).eval(), ro.to(dev).eval(), co), (p.to(dev).eval(), rp.to(dev).eval(), cp), sched
+
+
+def inputs(dev, seed):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g).to(dev)
+    return dict(latents=r(1, 4, H, W), garment=r(1, 4, H, W) * 0.9, prompt=r(1, 77, 768), negative=r(1, 77, 768),
+                gtok=r(1, 16, 768), pose=torch.rand(1, 3, H * 8, W * 8, generator=g).to(dev))
+
+
+@torch.no_grad()
+def test_base_pipeline_two_images_and_batch(cuda_device):
+    from dressing_sd.pipelines.IMAGDressing_v1_pipeline import IMAGDressing_v1
+    from oracle.pipeline import sample_one
+
+    dev = cuda_device
+    (o, ro, _), (p, rp, _), sched = build(dev)
+    pipe = IMAGDressing_v1(vae=None, reference_unet=rp, unet=p, tokenizer=None, text_encoder=None, image_encoder=None,
+                           ImgProj=None, scheduler=sched, safety_checker=None, feature_extractor=None)
+    refs = []
+    for seed in (42, 43):
+        x = inputs(dev, seed)
+        ref = sample_one(o, ro, x["latents"], x["prompt"], x["negative"], x["gtok"], x["garment"], 7.5, STEPS)
+        out = pipe(prompt=None, null_prompt=None, negative_prompt=None, ref_image=None, width=W * 8, height=H * 8,
+                   num_inference_steps=STEPS, guidance_scale=7.5, image_scale=1.0, output_type="latent",
+                   prompt_embeds=x["prompt"], negative_prompt_embeds=x["negative"], latents=x["latents"],
+                   garment_tokens=x["gtok"], ref_image_latents=x["garment"]).images
+        err = rel_l2(out, ref)
+        print(f"image seed {seed}: final-latent rel-L2 {err:.4f}")
+        assert err < 4e-2
+        refs.append((x, ref))
+    # image 2 must not look like image 1 (no state leaked through the cached projections / graph)
+    assert rel_l2(refs[1][1], refs[0][1]) > 0.3
+    # batch of two different (image, garment) pairs == the two batch-1 results (extension over the reference, B1)
+    xb = {k: torch.cat([refs[0][0][k], refs[1][0][k]]) for k in ("latents", "garment", "prompt", "negative", "gtok")}
+    outb = pipe(prompt=None, null_prompt=None, negative_prompt=None, ref_image=None, width=W * 8, height=H * 8,
+                num_inference_steps=STEPS, guidance_scale=7.5, output_type="latent", prompt_embeds=xb["prompt"],
+                negative_prompt_embeds=xb["negative"], latents=xb["latents"], garment_tokens=xb["gtok"],
+                ref_image_latents=xb["garment"]).images
+    assert rel_l2(outb[0:1], refs[0][1]) < 4e-2 and rel_l2(outb[1:2], refs[1][1]) < 4e-2
+
+
+@torch.no_grad()
+def test_controlnet_pipeline(cuda_device):
+    from dressing_sd.pipelines.IMAGDressing_v1_pipeline_controlnet import IMAGDressing_v1
+    from oracle.pipeline import sample_one
+
+    dev = cuda_device
+    (o, ro, co), (p, rp, cp), sched = build(dev, controlnet=True)
+    pipe = IMAGDressing_v1(vae=None, reference_unet=rp, unet=p, tokenizer=None, text_encoder=None, controlnet=cp,
+                           image_encoder=None, ImgProj=None, scheduler=sched, safety_checker=None, feature_extractor=None)
+    for seed in (44, 45):
+        x = inputs(dev, seed)
+        ref = sample_one(o, ro, x["latents"], x["prompt"], x["negative"], x["gtok"], x["garment"], 7.0, STEPS,
+                         controlnet=co, control_cond=x["pose"], control_scale=0.8)
+        out = pipe(prompt=None, null_prompt=None, negative_prompt=None, ref_image=None, width=W * 8, height=H * 8,
+                   num_inference_steps=STEPS, guidance_scale=7.0, pose_image=x["pose"], output_type="latent",
+                   prompt_embeds=x["prompt"], negative_prompt_embeds=x["negative"], latents=x["latents"],
+                   garment_tokens=x["gtok"], ref_image_latents=x["garment"], controlnet_conditioning_scale=0.8).images
+        err = rel_l2(out, ref)
+        print(f"controlnet image seed {seed}: final-latent rel-L2 {err:.4f}")
+        assert err < 4e-2
