@@ -19,8 +19,8 @@ void set_error(const char* fmt, ...) {
 bool pdl_enabled() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("IMAGD_PDL");
-        v = (e && e[0] == '0') ? 0 : 1;
+        const char* e = getenv("IMAGD_PDL");  // opt-in: measured neutral-to-slightly-negative on the B=1 step
+        v = (e && e[0] == '1') ? 1 : 0;
     }
     return v == 1;
 }

@@ -38,7 +38,7 @@ int cuda_fail(cudaError_t e, const char* what);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
 
-// Launch with the programmatic-dependent-launch attribute (IMAGD_PDL=0 in the environment disables it).
+// Launch, optionally with the programmatic-dependent-launch attribute (IMAGD_PDL=1 in the environment enables it).
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

@@ -181,6 +181,14 @@ class DenoiseEngine:
             st["image_latents"].copy_(image_latents)
             st["noise"].copy_(noise)
         st["step_ptr"].zero_()
+        if sa_hidden_states:
+            # the garment taps are rewritten in place by the captured garment pass: tensor identity/version say
+            # nothing about their contents, so the cached garment K|V projections are always recomputed per image
+            from .modeling import Attention
+
+            for m in self.unet.modules():
+                if isinstance(m, Attention) and hasattr(m.processor, "_kv2_memo"):
+                    m.processor._kv2_memo.clear()
 
         if not self.use_cuda_graph or callback is not None:
             for i in range(S):

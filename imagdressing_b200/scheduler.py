@@ -75,7 +75,6 @@ class DDIMScheduler:
         else:
             raise ValueError(sp)
         self.timesteps = torch.from_numpy(ts).to(device)
-        self._dev = {}
 
     def _alphas(self, t: int):
         prev = t - self.config.num_train_timesteps // self.num_inference_steps
