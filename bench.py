@@ -210,50 +210,60 @@ def pick_cpu_threads():
     return best
 
 
-def cpu_baseline(sample_forwards=2, threads=None):
-    """The fp32 oracle (reference processors restated; oracle/unet.py) on the host cores: `sample_forwards` UNet
-    forwards of the B=1 512x512 workload (half conditional with the garment stream, half unconditional), scaled to
-    101 forwards per image (50 x 2 + 1 garment pass)."""
-    from oracle import processors as op
-    from oracle import unet as ou
+class CpuOracle:
+    """The fp32 oracle (reference processors restated; oracle/unet.py) on the host cores, built once."""
 
-    threads = threads or pick_cpu_threads()
-    torch.set_num_threads(threads)
-    with torch.no_grad():
-        o = ou.UNet2DConditionModel()
-        po = {}
-        for name in o.attn_processors:
-            hidden = {"mid": 1280, "up_blocks.1": 1280, "up_blocks.2": 640, "up_blocks.3": 320, "down_blocks.0": 320,
-                      "down_blocks.1": 640, "down_blocks.2": 1280}[next(k for k in (
-                          "mid", "up_blocks.1", "up_blocks.2", "up_blocks.3", "down_blocks.0", "down_blocks.1",
-                          "down_blocks.2") if name.startswith(k))]
-            po[name] = op.RefSAttnProcessor(name, hidden) if "attn1" in name else op.CAttnProcessor(name, hidden, 768)
-        o.set_attn_processor(po)
-        g = torch.Generator().manual_seed(0)
-        for p in o.parameters():
-            p.copy_(torch.randn(p.shape, generator=g) * 0.02)
-        lat, txt = torch.randn(1, 4, HW, HW, generator=g), torch.randn(1, 77, 768, generator=g)
-        Ls = {320: HW * HW, 640: HW * HW // 4, 1280: HW * HW // 16}
-        sa = {}
-        for name, p in po.items():
-            if "attn1" in name:
-                C = p.to_k_ref.weight.shape[0]
-                Lr = HW * HW // 64 if name.startswith("mid") else Ls[C]
-                sa[name] = torch.randn(1, Lr, C, generator=g)
-        t = torch.tensor(981)
-        o(lat, t, txt)  # warm
-        t0 = time.perf_counter()
-        for i in range(sample_forwards):
-            if i % 2 == 0:
-                o(lat, t, txt, cross_attention_kwargs={"sa_hidden_states": sa})
-            else:
-                o(lat, t, txt)
-        dt = time.perf_counter() - t0
-    per_fwd = dt / sample_forwards
-    img_s = 1.0 / (per_fwd * (2 * STEPS_DDIM + 1))
-    return {"value": round(img_s, 6), "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": f"{sample_forwards} fp32 UNet forwards (B=1, 512x512; alternating hybrid/plain) = {dt:.1f} s, "
-                      f"scaled to {2 * STEPS_DDIM + 1} forwards/image", "s_per_forward": round(per_fwd, 3)}
+    def __init__(self, threads=None):
+        from oracle import processors as op
+        from oracle import unet as ou
+
+        self.threads = threads or pick_cpu_threads()
+        torch.set_num_threads(self.threads)
+        with torch.no_grad():
+            o = ou.UNet2DConditionModel()
+            po = {}
+            for name in o.attn_processors:
+                hidden = {"mid": 1280, "up_blocks.1": 1280, "up_blocks.2": 640, "up_blocks.3": 320, "down_blocks.0": 320,
+                          "down_blocks.1": 640, "down_blocks.2": 1280}[next(k for k in (
+                              "mid", "up_blocks.1", "up_blocks.2", "up_blocks.3", "down_blocks.0", "down_blocks.1",
+                              "down_blocks.2") if name.startswith(k))]
+                po[name] = op.RefSAttnProcessor(name, hidden) if "attn1" in name else op.CAttnProcessor(name, hidden, 768)
+            o.set_attn_processor(po)
+            g = torch.Generator().manual_seed(0)
+            for p in o.parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+            self.lat, self.txt = torch.randn(1, 4, HW, HW, generator=g), torch.randn(1, 77, 768, generator=g)
+            Ls = {320: HW * HW, 640: HW * HW // 4, 1280: HW * HW // 16}
+            self.sa = {}
+            for name, p in po.items():
+                if "attn1" in name:
+                    C = p.to_k_ref.weight.shape[0]
+                    Lr = HW * HW // 64 if name.startswith("mid") else Ls[C]
+                    self.sa[name] = torch.randn(1, Lr, C, generator=g)
+            self.t = torch.tensor(981)
+            self.o = o
+            o(self.lat, self.t, self.txt)  # warm
+
+    def run(self, sample_forwards=2):
+        """`sample_forwards` UNet forwards of the B=1 512x512 workload (alternating hybrid / plain), scaled to the
+        101 forwards of one image (50 x 2 + 1 garment pass)."""
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            for i in range(sample_forwards):
+                if i % 2 == 0:
+                    self.o(self.lat, self.t, self.txt, cross_attention_kwargs={"sa_hidden_states": self.sa})
+                else:
+                    self.o(self.lat, self.t, self.txt)
+            dt = time.perf_counter() - t0
+        per_fwd = dt / sample_forwards
+        img_s = 1.0 / (per_fwd * (2 * STEPS_DDIM + 1))
+        return {"value": round(img_s, 6), "unit": "images/s", "cores": self.threads, "kind": "port",
+                "sample": f"{sample_forwards} fp32 UNet forwards (B=1, 512x512; alternating hybrid/plain) = {dt:.1f} s, "
+                          f"scaled to {2 * STEPS_DDIM + 1} forwards/image", "s_per_forward": round(per_fwd, 3)}
+
+
+def cpu_baseline(sample_forwards=4, threads=None):
+    return CpuOracle(threads).run(sample_forwards)
 
 
 # ------------------------------------------------------------------------------------------------ main
@@ -268,8 +278,9 @@ def main():
             return
         ms = []
         cb = None
+        oracle = CpuOracle()
         for i in range(a.warmup + a.steps):
-            cb = cpu_baseline(sample_forwards=2)
+            cb = oracle.run(sample_forwards=2)
             if i >= a.warmup:
                 ms.append(1000.0 / cb["value"])
         v = 1000.0 / (sum(ms) / len(ms))
@@ -299,14 +310,12 @@ def main():
     pipe = build_product(dev)
     x_dev = synth_inputs(B, dev, rank)
     x_host = synth_inputs(B, dev, rank, pinned=True)
-    gather_buf = torch.empty(world * B, 4, HW, HW, device=dev) if world > 1 else None
+    from imagdressing_b200.parallel import gather_latents
 
     def one_step(x):
         out = run_pipe(pipe, x)
-        if world > 1:  # the single collective of the path: all-gather of the output latents over NVLink
-            dist.all_gather_into_tensor(gather_buf, out.contiguous())
-            return gather_buf
-        return out
+        # the single collective of the path: all-gather of the output latents (NCCL over NVLink); no-op at N=1
+        return gather_latents(out.contiguous(), world * B)
 
     def one_step_e2e():
         x = {k: v.to(dev, non_blocking=True) for k, v in x_host.items()}
