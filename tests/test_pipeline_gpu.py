@@ -110,3 +110,87 @@ def test_controlnet_pipeline(cuda_device):
         err = rel_l2(out, ref)
         print(f"controlnet image seed {seed}: final-latent rel-L2 {err:.4f}")
         assert err < 4e-2
+
+
+@torch.no_grad()
+def test_ipa_controlnet_pipeline_with_face_tokens(cuda_device):
+    """Config-3 path: LoraRefS (attn1) + LoRAIP (attn2, rank-16 LoRA here, 77 text + 4 face tokens) + ControlNet,
+    scales set through the pipeline's set_scale / set_ipa_scale exactly as the reference does (ipa_controlnet.py:433-438)."""
+    from adapter.attention_processor import CacheAttnProcessor2_0, LoraRefSAttnProcessor2_0, LoRAIPAttnProcessor2_0
+    from dressing_sd.pipelines.IMAGDressing_v1_pipeline_ipa_controlnet import IMAGDressing_v1
+    from imagdressing_b200 import modeling
+    from imagdressing_b200.scheduler import DDIMScheduler
+    from oracle import processors as op
+    from oracle import unet as ou
+    from oracle.pipeline import sample_one
+
+    dev = cuda_device
+    o, p = ou.UNet2DConditionModel(), modeling.UNet2DConditionModel()
+    o.set_attn_processor({n: (op.LoraRefSAttnProcessor(n, hidden_of(n), rank=16, lora_scale=0.2, scale=0.9) if "attn1" in n
+                              else op.LoRAIPAttnProcessor(hidden_of(n), 768, rank=16, lora_scale=0.3, scale=0.8, num_tokens=4))
+                          for n in o.attn_processors})
+    p.set_attn_processor({n: (LoraRefSAttnProcessor2_0(n, hidden_of(n), rank=16) if "attn1" in n
+                              else LoRAIPAttnProcessor2_0(hidden_of(n), 768, rank=16, num_tokens=4))
+                          for n in p.attn_processors})
+    ro, rp = ou.UNet2DConditionModel(), modeling.UNet2DConditionModel()
+    ro.set_attn_processor({n: op.CacheAttnProcessor() for n in ro.attn_processors})
+    rp.set_attn_processor({n: CacheAttnProcessor2_0() for n in rp.attn_processors})
+    co, cp = ou.ControlNetModel(), modeling.ControlNetModel()
+    for m, seed in ((o, 0), (ro, 1), (co, 2)):
+        ou.init_synthetic_(m, seed)
+    for m, seed in ((p, 0), (rp, 1), (cp, 2)):
+        modeling.init_synthetic_(m, seed)
+    # (init_synthetic_ also fills the LoRA `up` matrices, which the reference zero-initialises, so LoRA is exercised)
+    o, ro, co = o.to(dev).eval(), ro.to(dev).eval(), co.to(dev).eval()
+    p, rp, cp = p.to(dev).eval(), rp.to(dev).eval(), cp.to(dev).eval()
+    p.invalidate_packed()
+    sched = DDIMScheduler(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                          clip_sample=False, set_alpha_to_one=False, steps_offset=1)
+    pipe = IMAGDressing_v1(vae=None, reference_unet=rp, unet=p, tokenizer=None, text_encoder=None, controlnet=cp,
+                           image_encoder=None, ImgProj=None, ip_ckpt=None, scheduler=sched, safety_checker=None,
+                           feature_extractor=None)
+    x = inputs(dev, 46)
+    gq = torch.Generator().manual_seed(47)
+    face, face_null = torch.randn(1, 4, 768, generator=gq).to(dev), torch.randn(1, 4, 768, generator=gq).to(dev) * 0.1
+    ref = sample_one(o, ro, x["latents"], torch.cat([x["prompt"], face], 1), torch.cat([x["negative"], face_null], 1),
+                     x["gtok"], x["garment"], 7.0, STEPS, controlnet=co, control_cond=x["pose"], control_scale=1.0,
+                     control_text=(x["prompt"], x["negative"]))
+    out = pipe(prompt=None, null_prompt=None, negative_prompt=None, ref_image=None, width=W * 8, height=H * 8,
+               num_inference_steps=STEPS, guidance_scale=7.0, pose_image=x["pose"], image_scale=0.9, ipa_scale=0.8,
+               s_lora_scale=0.2, c_lora_scale=0.3, output_type="latent", prompt_embeds=x["prompt"],
+               negative_prompt_embeds=x["negative"], latents=x["latents"], garment_tokens=x["gtok"],
+               ref_image_latents=x["garment"], face_tokens=face, face_null_tokens=face_null).images
+    err = rel_l2(out, ref)
+    print(f"ipa+controlnet: final-latent rel-L2 {err:.4f}")
+    assert err < 4e-2
+
+
+@torch.no_grad()
+def test_inpainting_pipeline_blend(cuda_device):
+    """Config-4 path: ControlNet-inpaint loop with the per-step latent blend fused into the CFG+DDIM kernel."""
+    from dressing_sd.pipelines.IMAGDressing_v1_pipeline_controlnet_inpainting import IMAGDressing_v1
+    from oracle.pipeline import sample_one
+
+    dev = cuda_device
+    (o, ro, co), (p, rp, cp), sched = build(dev, controlnet=True)
+    pipe = IMAGDressing_v1(vae=None, reference_unet=rp, unet=p, tokenizer=None, text_encoder=None, controlnet=cp,
+                           image_encoder=None, ImgProj=None, scheduler=sched, safety_checker=None, feature_extractor=None)
+    x = inputs(dev, 48)
+    g = torch.Generator().manual_seed(49)
+    img_lat = torch.randn(1, 4, H, W, generator=g).to(dev)
+    mask = torch.zeros(1, 1, H, W, device=dev)
+    mask[:, :, H // 4: 3 * H // 4, W // 4: 3 * W // 4] = 1.0  # centre rectangle is repainted
+    noise = x["latents"]
+    ref = sample_one(o, ro, noise, x["prompt"], x["negative"], x["gtok"], x["garment"], 5.0, STEPS, controlnet=co,
+                     control_cond=x["pose"], control_scale=0.5, mask=mask, image_latents=img_lat, noise=noise)
+    out = pipe(prompt=None, null_prompt=None, negative_prompt=None, ref_image=None, control_image=x["pose"], height=H * 8,
+               width=W * 8, strength=1.0, num_inference_steps=STEPS, guidance_scale=5.0, latents=noise,
+               prompt_embeds=x["prompt"], negative_prompt_embeds=x["negative"], output_type="latent",
+               controlnet_conditioning_scale=0.5, garment_tokens=x["gtok"], ref_image_latents=x["garment"],
+               image_latents=img_lat, mask_latents=mask).images
+    err = rel_l2(out, ref)
+    print(f"inpainting: final-latent rel-L2 {err:.4f}")
+    assert err < 4e-2
+    # outside the mask the result is exactly the (un-noised at the last step) original latents
+    keep = (mask == 0).expand_as(out)
+    assert rel_l2(out[keep], img_lat[keep]) < 1e-5
