@@ -13,17 +13,15 @@
 // head_dim 40 / 80 / 160 the box over-runs the d extent and the hardware zero-fills, so no padded copies exist
 // in HBM and the MMA K extent is the head dim rounded to 16 (48 / 80 / 160).
 //
-// CTA = 128 queries of one (sample, head). The key axis is walked in 64-key sub-blocks with the score tile
-// DOUBLE-BUFFERED in TMEM: the tensor core computes S(j+1) = Q K(j+1)^T while the softmax warps are still busy
-// with S(j), so the softmax warps (the real bound at head_dim 40: one ex2 per 160 tensor FLOPs) never wait for it.
-// 320 threads:
-//   warps 0-7  softmax: TMEM lane = query row; warps w and w+4 own the same 32 rows and split the 64 score
-//              columns of a sub-block in halves. S is read ONCE with tcgen05.ld and held in 32 registers, the two
-//              half-row maxima meet through 512 bytes of smem, P goes to a double-buffered smem tile in the UMMA
-//              K-major 128B-swizzle layout, O is rescaled in TMEM only when the running max moves
-//   warp 8     TMA producer (K/V ring of 128-key tiles = two sub-blocks)
-//   warp 9     TMEM allocator + tcgen05.mma issuer:  S_b = Q K^T (128x64xhd),  O_s += P_b V (128xhdx64)
-// TMEM columns: S_0 [0,64), S_1 [64,128), O_0 [128, +O_STRIDE), O_1 after it. Two CTAs per SM at head_dim 40 / 64.
+// CTA = 128 queries of one (sample, head). 320 threads:
+//   warps 0-7  softmax: TMEM lane = query row; warps w and w+4 own the same 32 rows and split the 128 score
+//              columns in halves (twice the warps to hide the exp / convert latency — at head_dim 40 the softmax,
+//              not the tensor pipe, bounds the kernel). S is read once with tcgen05.ld and held in registers, the two
+//              half-row maxima meet through 512 bytes of smem, P is written to smem in the UMMA K-major
+//              128B-swizzle layout, O is rescaled in TMEM only when the running max moves
+//   warp 8     TMA producer (K/V ring)
+//   warp 9     TMEM allocator + tcgen05.mma issuer:  S = Q K^T  (128x128xhd),  O_s += P V (128xhdx128)
+// TMEM columns: S [0,128), O_0 [128, +O_STRIDE), O_1 after it. Two CTAs per SM at head_dim 40 / 64.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -52,7 +50,7 @@ struct AttnCfg {
     static constexpr int kVOff = kKOff + KV_STAGES * NATOM * kAtomBytes;
     static constexpr int kPOff = kVOff + KV_STAGES * NATOM * kAtomBytes;
     static constexpr int kBarOff = kPOff + 2 * kAtomBytes;
-    static constexpr int kNumBars = 1 + 3 * KV_STAGES + 7;  // q, k/v/empty per stage, s_full[2], p_full[2], pv_done, o_full, mx_free
+    static constexpr int kNumBars = 1 + 3 * KV_STAGES + 3;
     static constexpr int kMxOff = kBarOff + kNumBars * 8 + 16;  // [2 halves][128 rows] bf16 partial row maxima
     static constexpr int kTotal = kMxOff + 512;
 };
@@ -77,12 +75,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* k_full = q_full + 1;
     uint64_t* v_full = k_full + KV_STAGES;
     uint64_t* kv_empty = v_full + KV_STAGES;
-    uint64_t* s_full = kv_empty + KV_STAGES;  // [2]
-    uint64_t* p_full = s_full + 2;            // [2]
-    uint64_t* pv_done = p_full + 2;
-    uint64_t* o_full = pv_done + 1;
-    uint64_t* mx_free = o_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mx_free + 1);
+    uint64_t* s_full = kv_empty + KV_STAGES;
+    uint64_t* p_full = s_full + 1;
+    uint64_t* o_full = p_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
@@ -91,12 +87,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int h = blockIdx.y;
     const int b = blockIdx.z;
 
-    // stream s: nsb_s 64-key sub-blocks living in nst_s 128-key TMA stages
-    const int len1 = (b < p.nq1) ? p.len1 : 0;
-    const int nsb0 = (p.len0 + 63) / 64, nsb1 = (len1 + 63) / 64;
-    const int nst0 = (p.len0 + 127) / 128, nst1 = (len1 + 127) / 128;
-    const int G = nsb0 + nsb1;   // sub-blocks
-    const int T = nst0 + nst1;   // stages
+    const int nb0 = (p.len0 + 127) / 128;
+    const int nb1 = (b < p.nq1) ? (p.len1 + 127) / 128 : 0;
+    const int T = nb0 + nb1;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmQ);
@@ -108,13 +101,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             mbar_init(&v_full[i], 1);
             mbar_init(&kv_empty[i], 1);
         }
-        mbar_init(&s_full[0], 1);
-        mbar_init(&s_full[1], 1);
-        mbar_init(&p_full[0], 256);
-        mbar_init(&p_full[1], 256);
-        mbar_init(pv_done, 1);
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 256);
         mbar_init(o_full, 1);
-        mbar_init(mx_free, 256);
         fence_barrier_init();
     }
     if (warp == 9) {
@@ -136,8 +125,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
             for (int a = 0; a < NATOM; ++a) tma_load_4d(sQ + a * kAtomBytes, &tmQ, q_full, a * 64, h, q0, b);
             for (int i = 0; i < T; ++i) {
-                const int s = i < nst0 ? 0 : 1;
-                const int j = s ? i - nst0 : i;
+                const int s = i < nb0 ? 0 : 1;
+                const int j = s ? i - nb0 : i;
                 const int st = i % KV_STAGES;
                 const uint32_t ph = (i / KV_STAGES) & 1;
                 const CUtensorMap* mk = s ? &tmK1 : &tmK0;
@@ -157,63 +146,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     } else if (warp == 9) {
         // ------------------------------------------------ MMA issuer
         if (elect_one()) {
-            constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);      // Q (K-major) x K (K-major), 64 keys
+            constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);     // Q (K-major) x K (K-major)
             constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD_MMA, 0, 1);  // P (K-major) x V (MN-major)
-            const uint32_t q_addr = smem_u32(sQ);
-            // sub-block g -> (stream, index in stream, stage, half of the stage)
-            auto locate = [&](int g, int& sidx, int& jj, int& stage) {
-                sidx = g < nsb0 ? 0 : 1;
-                jj = sidx ? g - nsb0 : g;
-                stage = (sidx ? nst0 : 0) + (jj >> 1);
-            };
-            auto issue_qk = [&](int g) {
-                int sidx, jj, stage;
-                locate(g, sidx, jj, stage);
-                const int st = stage % KV_STAGES;
-                if ((jj & 1) == 0) {  // first sub-block of a stage: its K tile must have landed
-                    mbar_wait(&k_full[st], (stage / KV_STAGES) & 1);
-                    tc_fence_after();
-                }
-                const uint32_t k_addr = smem_u32(sK + st * NATOM * kAtomBytes) + (jj & 1) * 64 * 128;
+            mbar_wait(q_full, 0);
+            for (int i = 0; i < T; ++i) {
+                const int s = i < nb0 ? 0 : 1;
+                const int j = s ? i - nb0 : i;
+                const int st = i % KV_STAGES;
+                const uint32_t ph = (i / KV_STAGES) & 1;
+                mbar_wait(&k_full[st], ph);
+                tc_fence_after();
+                const uint32_t q_addr = smem_u32(sQ);
+                const uint32_t k_addr = smem_u32(sK + st * NATOM * kAtomBytes);
 #pragma unroll
                 for (int ks = 0; ks < HD_MMA / 16; ++ks) {
                     const uint32_t off = (ks / 4) * kAtomBytes + (ks % 4) * 32;
-                    umma_bf16(tmem_S + (g & 1) * 64, umma_smem_desc_sw128(q_addr + off, 16, 1024),
+                    umma_bf16(tmem_S, umma_smem_desc_sw128(q_addr + off, 16, 1024),
                               umma_smem_desc_sw128(k_addr + off, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
                 }
-                umma_commit(&s_full[g & 1]);
-            };
-            mbar_wait(q_full, 0);
-            issue_qk(0);
-            for (int g = 0; g < G; ++g) {
-                int sidx, jj, stage;
-                locate(g, sidx, jj, stage);
-                // S(g+1) while the softmax warps work on S(g): buffer (g+1)&1 was released by p_full(g-1). With a
-                // one-stage K/V ring the next stage's tile only lands after PV(g) frees the slot, so a QK that
-                // crosses into a new stage is issued after PV(g) instead.
-                bool early = false;
-                if (g + 1 < G) {
-                    int s2, j2, st2;
-                    locate(g + 1, s2, j2, st2);
-                    early = (KV_STAGES > 1) || (st2 == stage);
-                    if (early) issue_qk(g + 1);
-                }
-                const int st = stage % KV_STAGES;
-                mbar_wait(&p_full[g & 1], (g >> 1) & 1);
-                if ((jj & 1) == 0) mbar_wait(&v_full[st], (stage / KV_STAGES) & 1);
+                umma_commit(s_full);
+                mbar_wait(p_full, i & 1);
+                mbar_wait(&v_full[st], ph);
                 tc_fence_after();
-                const uint32_t p_addr = smem_u32(sP) + (g & 1) * kAtomBytes;
-                const uint32_t v_addr = smem_u32(sV + st * NATOM * kAtomBytes) + (jj & 1) * 64 * 128;
-                const uint32_t o_addr = tmem_O + sidx * C::kOStride;
+                const uint32_t p_addr = smem_u32(sP);
+                const uint32_t v_addr = smem_u32(sV + st * NATOM * kAtomBytes);
+                const uint32_t o_addr = tmem_O + s * C::kOStride;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                    umma_bf16(o_addr, umma_smem_desc_sw128(p_addr + ks * 32, 16, 1024),
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t poff = (ks / 4) * kAtomBytes + (ks % 4) * 32;
+                    umma_bf16(o_addr, umma_smem_desc_sw128(p_addr + poff, 16, 1024),
                               umma_smem_desc_sw128(v_addr + ks * 2048, kAtomBytes, 1024), idesc_o,
-                              (jj > 0 || ks > 0) ? 1u : 0u);
-                umma_commit(pv_done);
-                const int nsb = sidx ? nsb1 : nsb0;
-                if ((jj & 1) == 1 || jj == nsb - 1) umma_commit(&kv_empty[st]);  // last sub-block of the stage
-                if (g + 1 < G && !early) issue_qk(g + 1);
+                              (j > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(&kv_empty[st]);
             }
             umma_commit(o_full);
         }
@@ -225,59 +190,58 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint32_t lane_addr = static_cast<uint32_t>(lg * 32) << 16;
         __nv_bfloat16* mxbuf = reinterpret_cast<__nv_bfloat16*>(smem + C::kMxOff);
         float m_run = -INFINITY, l_run = 0.f, l_first = 0.f;
-        const uint32_t p_row = smem_u32(sP) + (r >> 3) * 1024 + (r & 7) * 128;
+        const uint32_t p_row = smem_u32(sP) + half * kAtomBytes + (r >> 3) * 1024 + (r & 7) * 128;
         const uint32_t rx = r & 7;
         // this thread's share of the O columns (16-column chunks) for the in-TMEM rescale and the epilogue
         constexpr int kChunks = HD_MMA / 16;
         const int ch_begin = half == 0 ? 0 : (kChunks + 1) / 2;
         const int ch_end = half == 0 ? (kChunks + 1) / 2 : kChunks;
-        const float sc = p.scale_log2;
 
-        for (int g = 0; g < G; ++g) {
-            const int s = g < nsb0 ? 0 : 1;
-            const int jj = s ? g - nsb0 : g;
-            if (jj == 0 && g > 0) {
+        for (int i = 0; i < T; ++i) {
+            const int s = i < nb0 ? 0 : 1;
+            const int j = s ? i - nb0 : i;
+            if (j == 0 && i > 0) {
                 l_first = l_run;
                 m_run = -INFINITY;
                 l_run = 0.f;
             }
-            const int valid = min(64, (s ? len1 : p.len0) - jj * 64) - half * 32;  // valid columns among my 32
-            mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+            const int valid = min(128, (s ? p.len1 : p.len0) - j * 128) - half * 64;  // valid columns in my half (may be <= 0)
+            mbar_wait(s_full, i & 1);
             tc_fence_after();
 
-            uint32_t v[32];  // my 32 scores of this row: read from TMEM once, kept in registers
-            tmem_ld32(tmem_S + lane_addr + (g & 1) * 64 + half * 32, v);
-            tmem_ld_wait();
+            // pass 1: maximum of my 64 columns, 32 at a time (registers are the scarce resource: 2 CTAs x 320
+            // threads per SM leaves 102 each, and there is no L1 left to absorb spills next to 226 KB of smem)
             float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-            if (valid >= 32) {
 #pragma unroll
-                for (int k = 0; k < 32; k += 4) {
-                    mx0 = fmaxf(mx0, __uint_as_float(v[k]));
-                    mx1 = fmaxf(mx1, __uint_as_float(v[k + 1]));
-                    mx2 = fmaxf(mx2, __uint_as_float(v[k + 2]));
-                    mx3 = fmaxf(mx3, __uint_as_float(v[k + 3]));
+            for (int cc = 0; cc < 2; ++cc) {
+                uint32_t v[32];
+                tmem_ld32(tmem_S + lane_addr + half * 64 + cc * 32, v);
+                tmem_ld_wait();
+                if (valid >= 64) {
+#pragma unroll
+                    for (int k = 0; k < 32; k += 4) {
+                        mx0 = fmaxf(mx0, __uint_as_float(v[k]));
+                        mx1 = fmaxf(mx1, __uint_as_float(v[k + 1]));
+                        mx2 = fmaxf(mx2, __uint_as_float(v[k + 2]));
+                        mx3 = fmaxf(mx3, __uint_as_float(v[k + 3]));
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        if (cc * 32 + k < valid) mx0 = fmaxf(mx0, __uint_as_float(v[k]));
                 }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 32; ++k)
-                    if (k < valid) mx0 = fmaxf(mx0, __uint_as_float(v[k]));
             }
-            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sc;
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
             // Any m >= the true row max keeps exp2(s - m) <= 1, so the two half-row threads only have to agree on
-            // one: each publishes its maximum rounded UP to bf16 and both take the larger. mx_free guards the single
-            // exchange buffer: nobody overwrites it before all 256 threads have read the previous sub-block's maxima.
+            // one: each publishes its maximum rounded UP to bf16 and both take the larger.
             const __nv_bfloat16 mine = __float2bfloat16_ru(mx);
-            if (g > 0) mbar_wait(mx_free, (g - 1) & 1);
             mxbuf[half * 128 + r] = mine;
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const float m_blk = fmaxf(__bfloat162float(mine), __bfloat162float(mxbuf[(half ^ 1) * 128 + r]));
-            mbar_arrive(mx_free);
             const float m_new = fmaxf(m_run, m_blk);
-            const float alpha = ex2_approx(m_run - m_new);  // 0 on the first sub-block of a stream
-            if (jj > 0 && __any_sync(0xffffffffu, m_new > m_run)) {
-                // rescale my chunks of this stream's O accumulator in TMEM; PV(g-1) must have retired first
-                mbar_wait(pv_done, (g - 1) & 1);
-                tc_fence_after();
+            const float alpha = ex2_approx(m_run - m_new);  // 0 on the first block of a stream
+            if (j > 0 && __any_sync(0xffffffffu, m_new > m_run)) {
+                // rescale my chunks of this stream's O accumulator in TMEM
                 const uint32_t o_addr = tmem_O + s * C::kOStride + lane_addr;
 #pragma unroll 1
                 for (int c = ch_begin; c < ch_end; ++c) {
@@ -292,35 +256,42 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             m_run = m_new;
 
-            // P = exp2(S*scale - m) for my 32 columns -> my half of the 64-wide swizzled P atom (buffer g & 1)
+            // pass 2: P = exp2(S*scale - m) for my 64 columns -> one 64-wide swizzled atom of the P tile
             float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-            const uint32_t p_base = p_row + (g & 1) * kAtomBytes;
+            const float sc = p.scale_log2;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float e[8];
-                if (valid >= 32) {
+            for (int cc = 0; cc < 2; ++cc) {
+                uint32_t v[32];
+                tmem_ld32(tmem_S + lane_addr + half * 64 + cc * 32, v);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) e[k] = ex2_approx(__uint_as_float(v[q * 8 + k]) * sc - m_new);
-                } else {
+                for (int q = 0; q < 4; ++q) {
+                    float e[8];
+                    if (valid >= 64) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        e[k] = (q * 8 + k < valid) ? ex2_approx(__uint_as_float(v[q * 8 + k]) * sc - m_new) : 0.f;
+                        for (int k = 0; k < 8; ++k) e[k] = ex2_approx(__uint_as_float(v[q * 8 + k]) * sc - m_new);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            e[k] = (cc * 32 + q * 8 + k < valid) ? ex2_approx(__uint_as_float(v[q * 8 + k]) * sc - m_new)
+                                                                : 0.f;
+                    }
+                    sum0 += e[0] + e[4];
+                    sum1 += e[1] + e[5];
+                    sum2 += e[2] + e[6];
+                    sum3 += e[3] + e[7];
+                    const uint32_t chunk = static_cast<uint32_t>(cc * 4 + q) ^ rx;
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16),
+                                 "r"(pack_bf16x2(e[0], e[1])), "r"(pack_bf16x2(e[2], e[3])),
+                                 "r"(pack_bf16x2(e[4], e[5])), "r"(pack_bf16x2(e[6], e[7]))
+                                 : "memory");
                 }
-                sum0 += e[0] + e[4];
-                sum1 += e[1] + e[5];
-                sum2 += e[2] + e[6];
-                sum3 += e[3] + e[7];
-                const uint32_t chunk = static_cast<uint32_t>(half * 4 + q) ^ rx;
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_base + chunk * 16),
-                             "r"(pack_bf16x2(e[0], e[1])), "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])),
-                             "r"(pack_bf16x2(e[6], e[7]))
-                             : "memory");
             }
             l_run = l_run * alpha + ((sum0 + sum1) + (sum2 + sum3));
 
             fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor core (async proxy)
             tc_fence_before();
-            mbar_arrive(&p_full[g & 1]);
+            mbar_arrive(p_full);
         }
 
         // ---- epilogue: out = w0 * O0 / l0 + w1 * O1 / l1 (row sums of the two half-row threads meet in the idle P tile)
@@ -333,7 +304,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const float lf = l_first + lbuf[((half ^ 1) * 2 + 0) * 128 + r];
         const float lr = l_run + lbuf[((half ^ 1) * 2 + 1) * 128 + r];
         float w0, w1 = 0.f;
-        const int nb1 = nsb1;
         if (nb1 > 0) {
             w0 = p.oscale0 / lf;
             w1 = p.oscale1 / lr;
