@@ -40,16 +40,25 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat1
 #pragma unroll
         for (int k = 0; k < 8; ++k) sum[k] = sq[k] = 0.f;
         const __nv_bfloat16* base = x + (static_cast<int64_t>(n) * HW) * ldx + cv * 8;
-        for (int pix = p_begin + prow; pix < p_end; pix += rows) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<int64_t>(pix) * ldx));
-            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+        for (int pix = p_begin + prow; pix < p_end; pix += rows * 4) {
+            uint4 v[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float a = bf16lo(u[k]), b = bf16hi(u[k]);
-                sum[2 * k] += a;
-                sq[2 * k] += a * a;
-                sum[2 * k + 1] += b;
-                sq[2 * k + 1] += b * b;
+            for (int t = 0; t < 4; ++t) {
+                v[t] = make_uint4(0u, 0u, 0u, 0u);  // zeros add nothing to either sum
+                if (pix + t * rows < p_end)
+                    v[t] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<int64_t>(pix + t * rows) * ldx));
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const uint32_t u[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float a = bf16lo(u[k]), b = bf16hi(u[k]);
+                    sum[2 * k] += a;
+                    sq[2 * k] += a * a;
+                    sum[2 * k + 1] += b;
+                    sq[2 * k + 1] += b * b;
+                }
             }
         }
 #pragma unroll
@@ -135,86 +144,139 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
     const int p_begin = blockIdx.x * ppc;
     const int p_end = min(HW, p_begin + ppc);
     const int total = (p_end - p_begin) * CV;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int pix = p_begin + idx / CV;
-        const int c0 = (idx % CV) * 8;
-        const int64_t row = static_cast<int64_t>(n) * HW + pix;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + c0));
-        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-        float f[8];
+    constexpr int U = 4;  // independent 128-bit loads in flight per thread
+    for (int base = threadIdx.x; base < total; base += blockDim.x * U) {
+        uint4 v[U];
+        int c0s[U];
+        int64_t rowsv[U];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            f[2 * k] = bf16lo(u[k]) * s_scale[c0 + 2 * k] + s_shift[c0 + 2 * k];
-            f[2 * k + 1] = bf16hi(u[k]) * s_scale[c0 + 2 * k + 1] + s_shift[c0 + 2 * k + 1];
+        for (int t = 0; t < U; ++t) {
+            const int idx = base + t * blockDim.x;
+            v[t] = make_uint4(0u, 0u, 0u, 0u);
+            c0s[t] = 0;
+            rowsv[t] = 0;
+            if (idx < total) {
+                c0s[t] = (idx % CV) * 8;
+                rowsv[t] = static_cast<int64_t>(n) * HW + p_begin + idx / CV;
+                v[t] = __ldg(reinterpret_cast<const uint4*>(x + rowsv[t] * ldx + c0s[t]));
+            }
         }
-        if (fuse_silu) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] = silu(f[k]);
+        for (int t = 0; t < U; ++t) {
+            if (base + t * static_cast<int>(blockDim.x) >= total) break;
+            const uint32_t u[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
+            const int c0 = c0s[t];
+            float f[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                f[2 * k] = bf16lo(u[k]) * s_scale[c0 + 2 * k] + s_shift[c0 + 2 * k];
+                f[2 * k + 1] = bf16hi(u[k]) * s_scale[c0 + 2 * k + 1] + s_shift[c0 + 2 * k + 1];
+            }
+            if (fuse_silu) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = silu(f[k]);
+            }
+            *reinterpret_cast<uint4*>(y + rowsv[t] * ldy + c0) = make_uint4(
+                pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
         }
-        *reinterpret_cast<uint4*>(y + row * ldy + c0) =
-            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
     }
 }
 
-// One warp per row; C <= 2048, C % 8 == 0.
+// LayerNorm: one warp normalises R rows at a time (R x VPL independent 128-bit loads in flight per lane — the rows are
+// only 640 B..2.5 KB, so memory-level parallelism, not arithmetic, sets the speed). C <= 2048, C % 8 == 0.
+template <int VPL, int R>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
                                                         __nv_bfloat16* __restrict__ y, int64_t ldy, int rows, int C,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps) {
     pdl_launch_dependents();
     pdl_wait();
-    const int row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    const int row0 = (blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5)) * R;
     const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
+    if (row0 >= rows) return;
     const int CV = C / 8;
-    float f[8][8];
-    float sum = 0.f;
+    uint4 raw[R][VPL];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int cv = lane + i * 32;
-        if (cv < CV) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx + cv * 8));
-            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int cv = lane + i * 32;
+            raw[r][i] = make_uint4(0u, 0u, 0u, 0u);
+            if (cv < CV && row0 + r < rows)
+                raw[r][i] = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row0 + r) * ldx + cv * 8));
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (row0 + r >= rows) break;
+        float f[VPL][8];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const uint32_t u[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 f[i][2 * k] = bf16lo(u[k]);
                 f[i][2 * k + 1] = bf16hi(u[k]);
-                sum += f[i][2 * k] + f[i][2 * k + 1];
+                sum += f[i][2 * k] + f[i][2 * k + 1];  // lanes beyond CV hold zeros
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum / static_cast<float>(C);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            if (lane + i * 32 < CV) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float d = f[i][k] - mean;
+                    sq += d * d;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = rsqrtf(sq / static_cast<float>(C) + eps);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int cv = lane + i * 32;
+            if (cv < CV) {
+                float o[8];
+                float g[8], b[8];
+                if (gamma) {
+                    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8));
+                    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8 + 4));
+                    g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) g[k] = 1.f;
+                }
+                if (beta) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8 + 4));
+                    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) b[k] = 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = (f[i][k] - mean) * rstd * g[k] + b[k];
+                *reinterpret_cast<uint4*>(y + static_cast<int64_t>(row0 + r) * ldy + cv * 8) =
+                    make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
             }
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum / static_cast<float>(C);
-    float sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int cv = lane + i * 32;
-        if (cv < CV) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float d = f[i][k] - mean;
-                sq += d * d;
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    const float rstd = rsqrtf(sq / static_cast<float>(C) + eps);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int cv = lane + i * 32;
-        if (cv < CV) {
-            float o[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int c = cv * 8 + k;
-                o[k] = (f[i][k] - mean) * rstd * (gamma ? __ldg(gamma + c) : 1.f) + (beta ? __ldg(beta + c) : 0.f);
-            }
-            *reinterpret_cast<uint4*>(y + static_cast<int64_t>(row) * ldy + cv * 8) =
-                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-        }
-    }
+}
+
+template <int VPL, int R>
+static int launch_ln(const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int C, const float* gamma,
+                     const float* beta, float eps, cudaStream_t st) {
+    const int rows_per_block = 8 * R;
+    IMAGD_CUDA(launch_pdl(layernorm_kernel<VPL, R>, dim3((rows + rows_per_block - 1) / rows_per_block), dim3(256), 0, st,
+                          reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, rows, C,
+                          gamma, beta, eps));
+    return IMAGD_OK;
 }
 
 }  // namespace imagd
@@ -253,11 +315,14 @@ int imagd_layernorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int r
     IMAGD_CHECK_ARG(x && y, "layernorm: null pointer");
     IMAGD_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && C <= 2048, "layernorm: C=%d unsupported", C);
     IMAGD_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y), "layernorm: alignment");
-    const int wpb = 8;
-    IMAGD_CUDA(launch_pdl(layernorm_kernel, dim3((rows + wpb - 1) / wpb), dim3(wpb * 32), 0, static_cast<cudaStream_t>(stream), 
-        reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, rows, C, gamma, beta,
-        eps));
-    return IMAGD_OK;
+    IMAGD_CHECK_ARG((!gamma || aligned16(gamma)) && (!beta || aligned16(beta)), "layernorm: gamma/beta alignment");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int vpl = (C / 8 + 31) / 32;
+    if (vpl <= 2) return launch_ln<2, 4>(x, ldx, y, ldy, rows, C, gamma, beta, eps, st);
+    if (vpl <= 3) return launch_ln<3, 4>(x, ldx, y, ldy, rows, C, gamma, beta, eps, st);
+    if (vpl <= 5) return launch_ln<5, 2>(x, ldx, y, ldy, rows, C, gamma, beta, eps, st);
+    return launch_ln<8, 1>(x, ldx, y, ldy, rows, C, gamma, beta, eps, st);
+
 }
 
 }  // extern "C"
