@@ -106,7 +106,7 @@ def load() -> ctypes.CDLL:
 
 
 # kernels launched through the C ABI (bench.py reports it as gpu_launches); graph replays add their node count
-LAUNCHES = {"imagd_gemm_bf16": 1, "imagd_conv3x3_bf16": 1, "imagd_attention_bf16": 1, "imagd_groupnorm_bf16": 2,
+LAUNCHES = {"imagd_gemm_bf16": 1, "imagd_conv3x3_bf16": 1, "imagd_attention_bf16": 1, "imagd_groupnorm_bf16": 1,
             "imagd_layernorm_bf16": 1, "imagd_concat_add_bf16": 1, "imagd_upsample2x_bf16": 1,
             "imagd_im2col3x3_s2_bf16": 1, "imagd_conv3x3_direct_bf16": 1, "imagd_nchw_f32_to_nhwc_bf16": 1,
             "imagd_timestep_embedding": 1, "imagd_linear_small_m": 1, "imagd_cfg_ddim_step": 1}

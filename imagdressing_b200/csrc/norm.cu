@@ -1,5 +1,5 @@
-// GroupNorm (+SiLU) and LayerNorm over token-major bf16 activations. HBM-bound: every element is read with
-// 128-bit loads, statistics are fp32, and the grid is sized to cover all 148 SMs even at batch 1.
+// GroupNorm (+SiLU) and LayerNorm over token-major bf16 activations. HBM/L2-bound: every element is read with
+// 128-bit loads, statistics are fp32 with fixed-order (bit-reproducible) reductions.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -9,30 +9,42 @@ constexpr int kGnMaxC = 2560;
 constexpr int kGnThreads = 512;
 constexpr int kGnCounters = 1024;  // max samples per call
 
-__host__ __device__ inline int gn_chunks(int HW) {
+// Chunks (CTAs) per sample. Every CTA of the launch must be resident at once (the kernel contains a sample-wide
+// rendezvous), so the grid is capped at 2 CTAs per SM — the occupancy __launch_bounds__(512, 2) guarantees.
+__host__ __device__ inline int gn_chunks(int HW, int NB) {
     int c = (HW + 31) / 32;
-    return c < 1 ? 1 : (c > 64 ? 64 : c);
+    const int cap = (148 * 2) / (NB > 0 ? NB : 1);
+    if (c > 64) c = 64;
+    if (c > cap) c = cap;
+    return c < 1 ? 1 : c;
 }
 
-// Workspace layout: [kGnCounters uint arrival counters (zero-initialised once by the caller; re-armed by the kernel)]
-// | [NB*chunks*groups*2] partial {sum, sum of squares} | [NB*groups*2] final {mean, rstd}.
-// The last block of a sample to finish folds the partials in a fixed order
-// (bit-reproducible) so the apply kernel reads 2 numbers per group instead of re-reducing `chunks` partials per CTA.
-__global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int HW,
-                                                              int C, int groups, int chunks, float* __restrict__ ws,
-                                                              int NB, float eps) {
+// ONE kernel per GroupNorm(+SiLU): phase 1 each CTA reduces its pixel chunk to per-group {sum, sum of squares};
+// the CTAs of a sample then meet at an arrival counter in L2 (all CTAs are co-resident: grid <= 2 per SM), every CTA
+// folds the sample's partials in a fixed order (bit-reproducible) and phase 2 normalises the same pixel chunk it just
+// read (still in L1/L2). Replaces a stats kernel + an apply kernel: one launch, no re-reduction chain, no gap.
+// Workspace: [kGnCounters uints: per sample {arrived, departed}, zero-initialised ONCE by the caller, re-armed here]
+// | [NB*chunks*groups*2] partials.
+__global__ void __launch_bounds__(kGnThreads, 2) groupnorm_fused_kernel(
+    const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y, int64_t ldy, int HW, int C,
+    int groups, int chunks, float* __restrict__ ws, const float* __restrict__ gamma, const float* __restrict__ beta,
+    float eps, int fuse_silu) {
     pdl_launch_dependents();
     pdl_wait();
-    // per (pixel-row slot, channel) partials, reduced in a fixed order below -> bit-reproducible statistics
-    __shared__ float s_sum[kGnThreads * 8];
-    __shared__ float s_sq[kGnThreads * 8];
+    __shared__ float s_a[kGnThreads * 8];  // phase 1: per (row slot, channel) sums      | phase 2: per-channel scale
+    __shared__ float s_b[kGnThreads * 8];  // phase 1: per (row slot, channel) sum of sq | phase 2: per-channel shift
+    __shared__ float s_mean[64];
+    __shared__ float s_rstd[64];
     const int n = blockIdx.y, chunk = blockIdx.x;
     const int CV = C / 8;
     const int rows = kGnThreads / CV;  // pixel rows processed per iteration (>= 1 since C <= 2560 < 8*512)
     const int ppc = (HW + chunks - 1) / chunks;
     const int p_begin = chunk * ppc;
     const int p_end = min(HW, p_begin + ppc);
+    const int cpg = C / groups;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws) - kGnCounters + 2 * n;
 
+    // ---------------- phase 1: partial statistics of my pixel chunk
     const int cv = threadIdx.x % CV;
     const int prow = threadIdx.x / CV;
     if (prow < rows) {
@@ -63,95 +75,98 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const __nv_bfloat1
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            s_sum[prow * C + cv * 8 + k] = sum[k];
-            s_sq[prow * C + cv * 8 + k] = sq[k];
+            s_a[prow * C + cv * 8 + k] = sum[k];
+            s_b[prow * C + cv * 8 + k] = sq[k];
         }
     }
     __syncthreads();
-    // fold the row slots into slot 0 (fixed order)
-    for (int c = threadIdx.x; c < C; c += kGnThreads) {
-        float a = s_sum[c], b = s_sq[c];
+    for (int c = threadIdx.x; c < C; c += kGnThreads) {  // fold the row slots (fixed order)
+        float a = s_a[c], b = s_b[c];
         for (int r = 1; r < rows; ++r) {
-            a += s_sum[r * C + c];
-            b += s_sq[r * C + c];
+            a += s_a[r * C + c];
+            b += s_b[r * C + c];
         }
-        s_sum[c] = a;
-        s_sq[c] = b;
+        s_a[c] = a;
+        s_b[c] = b;
     }
     __syncthreads();
-    const int cpg = C / groups;
     for (int g = threadIdx.x; g < groups; g += kGnThreads) {
         float a = 0.f, b = 0.f;
         for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-            a += s_sum[c];
-            b += s_sq[c];
+            a += s_a[c];
+            b += s_b[c];
         }
         float* dst = ws + ((static_cast<int64_t>(n) * chunks + chunk) * groups + g) * 2;
         __stcg(dst, a);
         __stcg(dst + 1, b);
     }
-    // ---- last block of this sample finalizes
-    float* fin = ws + static_cast<int64_t>(NB) * chunks * groups * 2;
-    unsigned int* counters = reinterpret_cast<unsigned int*>(ws) - kGnCounters;
-    __shared__ unsigned int s_last;
+    // ---------------- rendezvous of the sample's CTAs
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int old = atomicAdd(&counters[n], 1u);
-        s_last = (old == static_cast<unsigned int>(chunks - 1)) ? 1u : 0u;
-        if (s_last) counters[n] = 0u;  // re-arm
+        atomicAdd(&counters[0], 1u);
+        unsigned int spins = 0;
+        while (*reinterpret_cast<volatile unsigned int*>(&counters[0]) < static_cast<unsigned int>(chunks)) {
+            __nanosleep(64);
+            if (++spins > (1u << 22)) {
+                printf("imagd: groupnorm rendezvous timeout (sample %d chunk %d of %d)\n", n, chunk, chunks);
+                __trap();
+            }
+        }
+        __threadfence();
+        // last CTA to leave re-arms both counters for the next launch
+        if (atomicAdd(&counters[1], 1u) == static_cast<unsigned int>(chunks - 1)) {
+            counters[1] = 0u;
+            __threadfence();
+            counters[0] = 0u;
+        }
     }
     __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    for (int g = threadIdx.x; g < groups; g += kGnThreads) {
+    // ---------------- every CTA folds the sample's partials (fixed order) -> mean / rstd
+    if (threadIdx.x < groups) {
+        const int g = threadIdx.x;
         float a = 0.f, b = 0.f;
-        for (int c = 0; c < chunks; ++c) {
-            const float* src = ws + ((static_cast<int64_t>(n) * chunks + c) * groups + g) * 2;
-            a += __ldcg(src);
-            b += __ldcg(src + 1);
+        const float* src = ws + (static_cast<int64_t>(n) * chunks * groups + g) * 2;
+        for (int c = 0; c < chunks; c += 4) {
+            float pa[4], pb[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                pa[t] = pb[t] = 0.f;
+                if (c + t < chunks) {
+                    pa[t] = __ldcg(src + static_cast<int64_t>(c + t) * groups * 2);
+                    pb[t] = __ldcg(src + static_cast<int64_t>(c + t) * groups * 2 + 1);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                a += pa[t];
+                b += pb[t];
+            }
         }
         const float cnt = static_cast<float>(cpg) * static_cast<float>(HW);
         const float mean = a / cnt;
         const float var = fmaxf(b / cnt - mean * mean, 0.f);
-        fin[(static_cast<int64_t>(n) * groups + g) * 2] = mean;
-        fin[(static_cast<int64_t>(n) * groups + g) * 2 + 1] = rsqrtf(var + eps);
-    }
-}
-
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
-                                                       __nv_bfloat16* __restrict__ y, int64_t ldy, int HW, int C,
-                                                       int groups, int chunks, const float* __restrict__ ws,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       int fuse_silu, int apply_chunks, int NB) {
-    pdl_launch_dependents();
-    pdl_wait();
-    __shared__ float s_scale[kGnMaxC];
-    __shared__ float s_shift[kGnMaxC];
-    const int n = blockIdx.y;
-    const int cpg = C / groups;
-    const float* fin = ws + static_cast<int64_t>(NB) * chunks * groups * 2 + static_cast<int64_t>(n) * groups * 2;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / cpg;
-        const float sc = (gamma ? gamma[c] : 1.f) * fin[2 * g + 1];
-        s_scale[c] = sc;
-        s_shift[c] = (beta ? beta[c] : 0.f) - fin[2 * g] * sc;
+        s_mean[g] = mean;
+        s_rstd[g] = rsqrtf(var + eps);
     }
     __syncthreads();
-
-    const int CV = C / 8;
-    const int ppc = (HW + apply_chunks - 1) / apply_chunks;
-    const int p_begin = blockIdx.x * ppc;
-    const int p_end = min(HW, p_begin + ppc);
+    for (int c = threadIdx.x; c < C; c += kGnThreads) {
+        const int g = c / cpg;
+        const float sc = (gamma ? gamma[c] : 1.f) * s_rstd[g];
+        s_a[c] = sc;
+        s_b[c] = (beta ? beta[c] : 0.f) - s_mean[g] * sc;
+    }
+    __syncthreads();
+    // ---------------- phase 2: normalise my pixel chunk
     const int total = (p_end - p_begin) * CV;
     constexpr int U = 4;  // independent 128-bit loads in flight per thread
-    for (int base = threadIdx.x; base < total; base += blockDim.x * U) {
+    for (int base = threadIdx.x; base < total; base += kGnThreads * U) {
         uint4 v[U];
         int c0s[U];
         int64_t rowsv[U];
 #pragma unroll
         for (int t = 0; t < U; ++t) {
-            const int idx = base + t * blockDim.x;
+            const int idx = base + t * kGnThreads;
             v[t] = make_uint4(0u, 0u, 0u, 0u);
             c0s[t] = 0;
             rowsv[t] = 0;
@@ -163,14 +178,14 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
         }
 #pragma unroll
         for (int t = 0; t < U; ++t) {
-            if (base + t * static_cast<int>(blockDim.x) >= total) break;
+            if (base + t * kGnThreads >= total) break;
             const uint32_t u[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
             const int c0 = c0s[t];
             float f[8];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                f[2 * k] = bf16lo(u[k]) * s_scale[c0 + 2 * k] + s_shift[c0 + 2 * k];
-                f[2 * k + 1] = bf16hi(u[k]) * s_scale[c0 + 2 * k + 1] + s_shift[c0 + 2 * k + 1];
+                f[2 * k] = bf16lo(u[k]) * s_a[c0 + 2 * k] + s_b[c0 + 2 * k];
+                f[2 * k + 1] = bf16hi(u[k]) * s_a[c0 + 2 * k + 1] + s_b[c0 + 2 * k + 1];
             }
             if (fuse_silu) {
 #pragma unroll
@@ -285,27 +300,22 @@ extern "C" {
 
 int64_t imagd_groupnorm_ws_bytes(int NB, int HW, int C, int groups) {
     (void)C;
-    return (imagd::kGnCounters + static_cast<int64_t>(NB) * imagd::gn_chunks(HW) * groups * 2 +
-            static_cast<int64_t>(NB) * groups * 2) * sizeof(float);
+    return (imagd::kGnCounters + static_cast<int64_t>(NB) * imagd::gn_chunks(HW, NB) * groups * 2) * sizeof(float);
 }
 
 int imagd_groupnorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int NB, int HW, int C, int groups,
                          const float* gamma, const float* beta, float eps, int fuse_silu, void* ws, imagd_stream stream) {
     using namespace imagd;
     IMAGD_CHECK_ARG(x && y && ws, "groupnorm: null pointer");
-    IMAGD_CHECK_ARG(NB > 0 && NB <= kGnCounters && HW > 0 && C > 0 && C % 8 == 0 && C <= kGnMaxC,
+    IMAGD_CHECK_ARG(NB > 0 && 2 * NB <= kGnCounters && NB <= 148 * 2 && HW > 0 && C > 0 && C % 8 == 0 && C <= kGnMaxC,
                     "groupnorm: NB=%d C=%d unsupported", NB, C);
     IMAGD_CHECK_ARG(groups > 0 && groups <= 64 && C % groups == 0, "groupnorm: groups=%d", groups);
     IMAGD_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y), "groupnorm: alignment");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int chunks = gn_chunks(HW);
-    IMAGD_CUDA(launch_pdl(gn_stats_kernel, dim3(dim3(chunks, NB)), dim3(kGnThreads), 0, st, reinterpret_cast<const __nv_bfloat16*>(x), ldx, HW, C,
-                                                             groups, chunks, reinterpret_cast<float*>(ws) + kGnCounters, NB, eps));
-    int apply_chunks = (HW + 15) / 16;
-    if (apply_chunks > 128) apply_chunks = 128;
-    IMAGD_CUDA(launch_pdl(gn_apply_kernel, dim3(dim3(apply_chunks, NB)), dim3(256), 0, st, 
-        reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, HW, C, groups, chunks,
-        reinterpret_cast<const float*>(ws) + kGnCounters, gamma, beta, fuse_silu, apply_chunks, NB));
+    const int chunks = gn_chunks(HW, NB);
+    IMAGD_CUDA(launch_pdl(groupnorm_fused_kernel, dim3(chunks, NB), dim3(kGnThreads), 0, st,
+                          reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, HW, C,
+                          groups, chunks, reinterpret_cast<float*>(ws) + kGnCounters, gamma, beta, eps, fuse_silu));
     return IMAGD_OK;
 }
 

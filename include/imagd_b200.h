@@ -106,7 +106,8 @@ int imagd_attention_bf16(const void* q, int64_t q_ld, void* out, int64_t out_ld,
 
 /* ---- normalisation ---- */
 /* GroupNorm over [NB, HW, C] (token-major) with optional fused SiLU; workspace ws (imagd_groupnorm_ws_bytes; its first
- * 4 KB are arrival counters that the caller zero-initialises ONCE) holds the partial sums and final statistics.
+ * 4 KB are arrival counters that the caller zero-initialises ONCE) holds the per-chunk partial sums. One launch:
+ * the CTAs of a sample rendezvous through those counters (grid <= 2 CTAs per SM, so all are co-resident).
  * Replaces ResnetBlock2D.norm1/norm2 + nonlinearity, Transformer2DModel.norm, conv_norm_out (diffusers-0.24). */
 int64_t imagd_groupnorm_ws_bytes(int NB, int HW, int C, int groups);
 int imagd_groupnorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int NB, int HW, int C, int groups,

@@ -46,7 +46,7 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     rc = lib.imagd_gemm_bf16(None, 0, None, 0, None, 0, 0, 0, 0, None, None)
     assert rc == -1
     assert b"gemm" in lib.imagd_last_error()
-    assert lib.imagd_groupnorm_ws_bytes(2, 4096, 320, 32) == (1024 + 2 * 64 * 32 * 2 + 2 * 32 * 2) * 4
+    assert lib.imagd_groupnorm_ws_bytes(2, 4096, 320, 32) == (1024 + 2 * 64 * 32 * 2) * 4
 
 
 def test_no_silent_fallback_when_library_missing(monkeypatch, tmp_path):
