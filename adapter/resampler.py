@@ -44,11 +44,6 @@ def _f32(p):
 
 
 def _bf(p):
-    """GEMM weight -> bf16, TILED64 layout (packed lazily on the device the module lives on)."""
-    return ops.tile_weight(p.detach().to(BF16).contiguous())
-
-
-def _bf_plain(p):
     return p.detach().to(BF16).contiguous()
 
 
@@ -162,8 +157,8 @@ class ProjPlusModel(nn.Module):
     def forward(self, id_embeds, clip_embeds, shortcut=False, scale=1.0):
         in_dtype = id_embeds.dtype
         p0, p2 = self.proj[0], self.proj[2]
-        h = ops.linear_small_m(id_embeds.float().contiguous(), _bf_plain(p0.weight), _f32(p0.bias), act_out=ACT_GELU)
-        h = ops.linear_small_m(h, _bf_plain(p2.weight), _f32(p2.bias))
+        h = ops.linear_small_m(id_embeds.float().contiguous(), _bf(p0.weight), _f32(p0.bias), act_out=ACT_GELU)
+        h = ops.linear_small_m(h, _bf(p2.weight), _f32(p2.bias))
         x = h.reshape(-1, self.num_tokens, self.cross_attention_dim).to(BF16)
         x = ops.layernorm(x.contiguous(), _f32(self.norm.weight), _f32(self.norm.bias))
         out = self.perceiver_resampler(x, clip_embeds)

@@ -29,7 +29,6 @@ class Epilogue(Structure):
         ("ldr", c_int64),
         ("alpha", c_float),
         ("out_fp32", c_int32),
-        ("w_tiled", c_int32),
     ]
 
 
@@ -53,8 +52,6 @@ SIGNATURES = {
     "imagd_version": (c_int, []),
     "imagd_last_error": (c_char_p, []),
     "imagd_device_check": (c_int, []),
-    "imagd_tiled64_bytes": (c_int64, [c_int, c_int]),
-    "imagd_pack_weight_tiled64": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "imagd_gemm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                                 POINTER(Epilogue), c_void_p]),
     "imagd_gemm_debug_force": (c_int, [c_int, c_int, c_int]),

@@ -42,9 +42,6 @@ struct GemmParams {
     int kb_per_split;
     float* ws;
     unsigned int* counters;
-    // TILED64 weights (NULL: B comes through the tmB tensor map)
-    const uint8_t* wt;
-    int n_atoms;  // ceil(N / 8)
 };
 
 constexpr int kBlockM = 128;
@@ -117,10 +114,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int stage = i % STAGES;
                 const uint32_t phase = (i / STAGES) & 1;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                // tiled weights: the last N tile may hold fewer than BLOCK_N rows (its stale smem rows feed only
-                // output columns the epilogue masks)
-                const uint32_t b_rows = p.wt ? static_cast<uint32_t>(min(BLOCK_N, p.n_atoms * 8 - n_blk * BLOCK_N)) : BLOCK_N;
-                mbar_arrive_expect_tx(&full_bar[stage], kABytes + b_rows * 128u);
+                mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
                 const int tap = kb / p.kb_per_tap;
                 const int kc = kb - tap * p.kb_per_tap;
                 int dx = 0, dy = 0;
@@ -131,11 +125,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint8_t* sa = smem + stage * L::kStageBytes;
                 uint8_t* sb = sa + kABytes;
                 tma_load_4d(sa, &tmA, &full_bar[stage], kc * kBlockK, x0 + dx, y0 + dy, n0);
-                if (p.wt)
-                    bulk_load(sb, p.wt + (static_cast<int64_t>(kb) * p.n_atoms + n_blk * (BLOCK_N / 8)) * 1024, b_rows * 128u,
-                              &full_bar[stage]);
-                else
-                    tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.cin + kc * kBlockK, n_blk * BLOCK_N);
+                tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.cin + kc * kBlockK, n_blk * BLOCK_N);
             }
         }
     } else if (warp == 1) {
@@ -441,8 +431,8 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
         ep.alpha = 1.0f;
     }
     IMAGD_CHECK_ARG(A && Wt && D, "gemm: null pointer");
-    IMAGD_CHECK_ARG(Cin % 8 == 0 && lda % 8 == 0 && (ep.w_tiled || ldw % 8 == 0),
-                    "gemm: K=%d lda=%lld ldw=%lld must be multiples of 8", Cin, (long long)lda, (long long)ldw);
+    IMAGD_CHECK_ARG(Cin % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K=%d lda=%lld ldw=%lld must be multiples of 8",
+                    Cin, (long long)lda, (long long)ldw);
     IMAGD_CHECK_ARG(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
     IMAGD_CHECK_ARG(taps == 1 || Cin % 64 == 0, "conv3x3: Cin=%d must be a multiple of 64", Cin);
     const bool geglu = ep.act == IMAGD_ACT_GEGLU;
@@ -492,8 +482,6 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
     p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
     p.ws = nullptr;
     p.counters = nullptr;
-    p.wt = ep.w_tiled ? reinterpret_cast<const uint8_t*>(Wt) : nullptr;
-    p.n_atoms = (N + 7) / 8;
     if (p.splits > 1) {
         int rc = ensure_scratch(&p.ws, &p.counters);
         if (rc != IMAGD_OK) return rc;
@@ -514,15 +502,12 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
         int rc = make_tmap_bf16(&tmA, A, 4, dims, strides, box);
         if (rc != IMAGD_OK) return rc;
     }
-    if (!ep.w_tiled) {
+    {
         uint64_t dims[2] = {static_cast<uint64_t>(taps) * Cin, static_cast<uint64_t>(N)};
         uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
         uint32_t box[2] = {kBlockK, static_cast<uint32_t>(cfg.bn)};
         int rc = make_tmap_bf16(&tmB, Wt, 2, dims, strides, box);
         if (rc != IMAGD_OK) return rc;
-    } else {
-        tmB = tmA;  // unused by the kernel
-        IMAGD_CHECK_ARG(aligned16(Wt), "gemm: tiled weight pointer alignment");
     }
     switch (cfg.bn * 100 + cfg.stages) {
         case 6404: return launch_gemm<64, 4>(tmA, tmB, p, m_tiles, stream);
@@ -539,46 +524,9 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
     }
 }
 
-__global__ void pack_tiled64_kernel(const __nv_bfloat16* __restrict__ W, int64_t ldw, int N, int K,
-                                    __nv_bfloat16* __restrict__ out, int64_t total_chunks, int n_atoms) {
-    // one 16-byte chunk per thread: out chunk index -> (kb, atom, r, pc)
-    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total_chunks;
-         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int pc = static_cast<int>(idx & 7);
-        const int r = static_cast<int>((idx >> 3) & 7);
-        const int64_t atom = idx >> 6;
-        const int na = static_cast<int>(atom % n_atoms);
-        const int kb = static_cast<int>(atom / n_atoms);
-        const int n = na * 8 + r;
-        const int k0 = kb * 64 + ((pc ^ r) << 3);
-        __nv_bfloat16 v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-            v[e] = (n < N && k0 + e < K) ? W[static_cast<int64_t>(n) * ldw + k0 + e] : __float2bfloat16(0.f);
-        *reinterpret_cast<uint4*>(out + idx * 8) = *reinterpret_cast<const uint4*>(v);
-    }
-}
-
 }  // namespace imagd
 
 extern "C" {
-
-int64_t imagd_tiled64_bytes(int N, int K) {
-    return static_cast<int64_t>((K + 63) / 64) * ((N + 7) / 8) * 1024;
-}
-
-int imagd_pack_weight_tiled64(const void* W, int64_t ldw, int N, int K, void* out, imagd_stream stream) {
-    using namespace imagd;
-    IMAGD_CHECK_ARG(W && out && N > 0 && K > 0 && aligned16(out), "pack_weight_tiled64: bad args");
-    const int n_atoms = (N + 7) / 8;
-    const int64_t chunks = static_cast<int64_t>((K + 63) / 64) * n_atoms * 64;
-    int grid = static_cast<int>(std::min<int64_t>((chunks + 255) / 256, 148 * 32));
-    pack_tiled64_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(W), ldw, N, K, reinterpret_cast<__nv_bfloat16*>(out), chunks, n_atoms);
-    IMAGD_LAUNCH_CHECK("pack_tiled64_kernel");
-    return IMAGD_OK;
-}
-
 
 int imagd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd, int M, int N, int K,
                     const imagd_epilogue* ep, imagd_stream stream) {

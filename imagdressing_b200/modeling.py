@@ -55,11 +55,6 @@ def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
     return w.detach().permute(0, 2, 3, 1).reshape(co, 9 * ci).to(BF16).contiguous()
 
 
-def _tw(w: torch.Tensor):
-    """bf16 [N, K] weight -> TILED64 layout for the tensor-core GEMM/conv (contiguous HBM slab per k-block)."""
-    return ops.tile_weight(w if w.dtype == BF16 else w.detach().to(BF16).contiguous())
-
-
 def pack_geglu(w: torch.Tensor, b: torch.Tensor):
     """GEGLU.proj [2F, K] (value rows then gate rows) -> per 128 rows: 64 value + their 64 gate rows."""
     F2, K = w.shape
@@ -131,14 +126,11 @@ class Attention(nn.Module):
         self._pk = {}
         return super()._apply(fn, *a, **k)
 
-    def packed(self, key: str, build, tile: bool = False):
-        """Cache of derived weights (fused q/k/v, LoRA-merged, ...). `key` must encode every mutable input.
-        tile=True stores the GEMM weight in the TILED64 layout."""
+    def packed(self, key: str, build):
+        """Cache of derived weights (fused q/k/v, LoRA-merged, ...). `key` must encode every mutable input."""
         t = self._pk.get(key)
         if t is None:
             t = build()
-            if tile:
-                t = ops.tile_weight(t)
             self._pk[key] = t
         return t
 
@@ -178,7 +170,7 @@ class BasicTransformerBlock(nn.Module, _Packed):
             w1, b1 = pack_geglu(self.ff.net[0].proj.weight, self.ff.net[0].proj.bias)
             self._pk = dict(
                 ln=[(_f32(n.weight), _f32(n.bias)) for n in (self.norm1, self.norm2, self.norm3)],
-                w1=_tw(w1), b1=b1, w2=_tw(_bf(self.ff.net[2].weight)), b2=_f32(self.ff.net[2].bias))
+                w1=w1, b1=b1, w2=_bf(self.ff.net[2].weight), b2=_f32(self.ff.net[2].bias))
         return self._pk
 
     def _attend(self, attn: Attention, normed, residual, ctx, kw):
@@ -216,8 +208,8 @@ class Transformer2DModel(nn.Module, _Packed):
         if self._pk is None:
             c = self.proj_in.weight.shape[0]
             self._pk = dict(gn=(_f32(self.norm.weight), _f32(self.norm.bias)),
-                            wi=_tw(_bf(self.proj_in.weight.reshape(c, c))), bi=_f32(self.proj_in.bias),
-                            wo=_tw(_bf(self.proj_out.weight.reshape(c, c))), bo=_f32(self.proj_out.bias))
+                            wi=_bf(self.proj_in.weight.reshape(c, c)), bi=_f32(self.proj_in.bias),
+                            wo=_bf(self.proj_out.weight.reshape(c, c)), bo=_f32(self.proj_out.bias))
         return self._pk
 
     def run(self, x: torch.Tensor, ctx, kw) -> torch.Tensor:
@@ -251,12 +243,12 @@ class ResnetBlock2D(nn.Module, _Packed):
 
     def _packed(self):
         if self._pk is None:
-            pk = dict(gn1=(_f32(self.norm1.weight), _f32(self.norm1.bias)), w1=_tw(pack_conv3x3(self.conv1.weight)),
+            pk = dict(gn1=(_f32(self.norm1.weight), _f32(self.norm1.bias)), w1=pack_conv3x3(self.conv1.weight),
                       b1=_f32(self.conv1.bias), gn2=(_f32(self.norm2.weight), _f32(self.norm2.bias)),
-                      w2=_tw(pack_conv3x3(self.conv2.weight)), b2=_f32(self.conv2.bias))
+                      w2=pack_conv3x3(self.conv2.weight), b2=_f32(self.conv2.bias))
             if self.conv_shortcut is not None:
                 co, ci = self.conv_shortcut.weight.shape[:2]
-                pk["ws"] = _tw(_bf(self.conv_shortcut.weight.reshape(co, ci)))
+                pk["ws"] = _bf(self.conv_shortcut.weight.reshape(co, ci))
                 pk["bs"] = _f32(self.conv_shortcut.bias)
             self._pk = pk
         return self._pk
@@ -283,7 +275,7 @@ class Downsample2D(nn.Module, _Packed):
 
     def run(self, x):
         if self._pk is None:
-            self._pk = dict(w=_tw(pack_conv3x3(self.conv.weight)), b=_f32(self.conv.bias))
+            self._pk = dict(w=pack_conv3x3(self.conv.weight), b=_f32(self.conv.bias))
         NB, H, W, C = x.shape
         col = ops.im2col3x3_s2(x)
         return ops.gemm(col, self._pk["w"], bias=self._pk["b"])  # [NB, H/2, W/2, C]
@@ -301,7 +293,7 @@ class Upsample2D(nn.Module, _Packed):
 
     def run(self, x):
         if self._pk is None:
-            self._pk = dict(w=_tw(pack_conv3x3(self.conv.weight)), b=_f32(self.conv.bias))
+            self._pk = dict(w=pack_conv3x3(self.conv.weight), b=_f32(self.conv.bias))
         return ops.conv3x3(ops.upsample2x(x), self._pk["w"], bias=self._pk["b"])
 
 
@@ -699,9 +691,9 @@ class ControlNetModel(_ModelBase):
             self._cn_pk = dict(
                 wi=pack_conv3x3(self.conv_in.weight), bi=_f32(self.conv_in.bias),
                 ce=[(pack_conv3x3(c.weight), _f32(c.bias), c.stride[0]) for c in convs],
-                zw=[_tw(_bf(c.weight.reshape(c.weight.shape[0], -1))) for c in self.controlnet_down_blocks],
+                zw=[_bf(c.weight.reshape(c.weight.shape[0], -1)) for c in self.controlnet_down_blocks],
                 zb=[_f32(c.bias) for c in self.controlnet_down_blocks],
-                mw=_tw(_bf(self.controlnet_mid_block.weight.reshape(self.controlnet_mid_block.weight.shape[0], -1))),
+                mw=_bf(self.controlnet_mid_block.weight.reshape(self.controlnet_mid_block.weight.shape[0], -1)),
                 mb=_f32(self.controlnet_mid_block.bias))
         return self._cn_pk
 

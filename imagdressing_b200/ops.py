@@ -50,54 +50,21 @@ def _epilogue(bias, rowvec, rows_per_group, residual, act, alpha, out_fp32) -> E
     return ep
 
 
-class TiledW:
-    """A weight matrix [N, K] repacked into the TILED64 layout (include/imagd_b200.h): 1 KB atoms of 8 rows x 64
-    columns, pre-swizzled, so a GEMM k-block reads one contiguous slab of HBM."""
-
-    __slots__ = ("data", "N", "K")
-
-    def __init__(self, data: torch.Tensor, N: int, K: int):
-        self.data, self.N, self.K = data, N, K
-
-    @property
-    def shape(self):
-        return (self.N, self.K)
-
-
-def tile_weight(w: torch.Tensor) -> TiledW:
-    """bf16 [N, K] (row stride arbitrary, CUDA) -> TiledW."""
-    lib = _lib.load()
-    assert w.dtype == BF16 and w.dim() == 2 and w.stride(1) == 1 and w.is_cuda
-    N, K = w.shape
-    out = torch.empty(lib.imagd_tiled64_bytes(N, K), device=w.device, dtype=torch.uint8)
-    _lib.check(lib.imagd_pack_weight_tiled64(w.data_ptr(), w.stride(0), N, K, out.data_ptr(), _stream()),
-               "imagd_pack_weight_tiled64")
-    return TiledW(out, N, K)
-
-
-def _wargs(w):
-    """(pointer, ldw, N, K, tiled flag) of a plain or tiled weight."""
-    if isinstance(w, TiledW):
-        return w.data.data_ptr(), 0, w.N, w.K, 1
-    assert w.dtype == BF16
-    return w.data_ptr(), w.stride(0), w.shape[0], w.shape[1], 0
-
-
-def gemm(a: torch.Tensor, w, *, out: Optional[torch.Tensor] = None, bias=None, rowvec=None,
+def gemm(a: torch.Tensor, w: torch.Tensor, *, out: Optional[torch.Tensor] = None, bias=None, rowvec=None,
          rows_per_group: int = 0, residual=None, act: int = ACT_NONE, alpha: float = 1.0,
          out_fp32: bool = False) -> torch.Tensor:
     """out[M, N] = epilogue(a[M, K] @ w[N, K]^T); a / w / residual bf16, bias / rowvec fp32."""
     lib = _lib.load()
     M, K, lda = _rows2d(a)
-    wptr, ldw, N, Kw, tiled = _wargs(w)
-    assert Kw == K and a.dtype == BF16
+    N, Kw = w.shape
+    assert Kw == K and a.dtype == BF16 and w.dtype == BF16
     n_out = N // 2 if act == ACT_GEGLU else N
     if out is None:
         out = torch.empty(*a.shape[:-1], n_out, device=a.device, dtype=torch.float32 if out_fp32 else BF16)
     ldd = _rows2d(out)[2]
     ep = _epilogue(bias, rowvec, rows_per_group, residual, act, alpha, out_fp32)
-    ep.w_tiled = tiled
-    rc = lib.imagd_gemm_bf16(a.data_ptr(), lda, wptr, ldw, out.data_ptr(), ldd, M, N, K, ctypes.byref(ep), _stream())
+    rc = lib.imagd_gemm_bf16(a.data_ptr(), lda, w.data_ptr(), w.stride(0), out.data_ptr(), ldd, M, N, K,
+                             ctypes.byref(ep), _stream())
     _lib.check(rc, "imagd_gemm_bf16")
     return out
 
@@ -108,13 +75,12 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, out: Optional[torch.Tensor] = N
     lib = _lib.load()
     NB, H, W, Cin = x.shape
     assert x.is_contiguous() and x.dtype == BF16
-    wptr, _, Cout, Kw, tiled = _wargs(w)
-    assert Kw == 9 * Cin
+    Cout = w.shape[0]
+    assert w.shape[1] == 9 * Cin
     if out is None:
         out = torch.empty(NB, H, W, Cout, device=x.device, dtype=BF16)
     ep = _epilogue(bias, rowvec, H * W, residual, act, 1.0, False)
-    ep.w_tiled = tiled
-    rc = lib.imagd_conv3x3_bf16(x.data_ptr(), Cin, NB, H, W, Cin, wptr, out.data_ptr(), out.shape[-1], Cout,
+    rc = lib.imagd_conv3x3_bf16(x.data_ptr(), Cin, NB, H, W, Cin, w.data_ptr(), out.data_ptr(), out.shape[-1], Cout,
                                 ctypes.byref(ep), _stream())
     _lib.check(rc, "imagd_conv3x3_bf16")
     return out

@@ -132,13 +132,12 @@ def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_st
     elif encoder_hidden_states is None:
         wqkv = attn.packed("qkv:" + lkey, lambda: torch.cat(
             [_merged(attn.to_q, lora and lora["q"], lora_scale), _merged(attn.to_k, lora and lora["k"], lora_scale),
-             _merged(attn.to_v, lora and lora["v"], lora_scale)], 0).to(BF16).contiguous(), tile=True)
+             _merged(attn.to_v, lora and lora["v"], lora_scale)], 0).to(BF16).contiguous())
         qkv = ops.gemm(x, wqkv)  # [B, L, 3C]
         q2 = _flat(qkv[..., :C])
         s0 = ops.kv_stream(_flat(qkv[..., C:2 * C]), _flat(qkv[..., 2 * C:]), L)
     else:
-        wq = attn.packed("q:" + lkey, lambda: _merged(attn.to_q, lora and lora["q"], lora_scale).to(BF16).contiguous(),
-                         tile=True)
+        wq = attn.packed("q:" + lkey, lambda: _merged(attn.to_q, lora and lora["q"], lora_scale).to(BF16).contiguous())
         q2 = None if prepare_only else _flat(ops.gemm(x, wq))
         ctx_src = encoder_hidden_states
         Lc = ctx_src.shape[1] if text_len is None else text_len
@@ -146,7 +145,7 @@ def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_st
         if kv is None:
             wkv = attn.packed("kv:" + lkey, lambda: torch.cat(
                 [_merged(attn.to_k, lora and lora["k"], lora_scale), _merged(attn.to_v, lora and lora["v"], lora_scale)],
-                0).to(BF16).contiguous(), tile=True)
+                0).to(BF16).contiguous())
             ctx = as_bf16(ctx_src, proc._ctx_memo)
             buf = proc._kv_memo.reusable((*ctx.shape[:-1], 2 * C))
             kv = proc._kv_memo.put(ctx_src, ops.gemm(ctx, wkv, out=buf), (lkey, Lc))  # [B, Lctx, 2C]
@@ -159,7 +158,7 @@ def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_st
         first = second[5] if len(second) > 5 else 0
         kv2 = proc._kv2_memo.get(src, id(to_k))
         if kv2 is None:
-            w2 = attn.packed(f"kv2:{id(to_k)}", lambda: torch.cat([_w(to_k), _w(to_v)], 0).to(BF16).contiguous(), tile=True)
+            w2 = attn.packed(f"kv2:{id(to_k)}", lambda: torch.cat([_w(to_k), _w(to_v)], 0).to(BF16).contiguous())
             src_bf = as_bf16(src, proc._g_memo)
             buf = proc._kv2_memo.reusable((*src_bf.shape[:-1], 2 * C))
             kv2 = proc._kv2_memo.put(src, ops.gemm(src_bf, w2, out=buf), id(to_k))
@@ -173,8 +172,7 @@ def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_st
 
     o = ops.attention(q2, B, L, heads, hd, s0, s1)  # [B*L, C]
 
-    wo = attn.packed("o:" + lkey, lambda: _merged(attn.to_out[0], lora and lora["out"], lora_scale).to(BF16).contiguous(),
-                     tile=True)
+    wo = attn.packed("o:" + lkey, lambda: _merged(attn.to_out[0], lora and lora["out"], lora_scale).to(BF16).contiguous())
     bo = attn.packed("bo", lambda: attn.to_out[0].bias.detach().float().contiguous())
     residual = attn._fused_residual
     if residual is not None and residual.dtype == BF16 and residual.shape == hidden_states.shape:

@@ -51,16 +51,7 @@ typedef struct imagd_epilogue {
     int64_t ldr;
     float alpha;            /* 1.0f for plain */
     int32_t out_fp32;       /* 0: bf16 output, 1: fp32 output */
-    int32_t w_tiled;        /* 0: W is row-major [N, ldw]; 1: W is in the TILED64 layout (imagd_pack_weight_tiled64) */
 } imagd_epilogue;
-
-/* TILED64 weight layout: the [N, K] matrix cut into 8-row x 64-column atoms of 1 KB stored as
- * [ceil(K/64)][ceil(N/8)][8 rows][8 x 16-byte chunks], chunk c of row r at position c ^ r (the 128-byte shared-memory
- * swizzle UMMA reads), zero padded. A 128 x BN x 64 k-block of the GEMM then needs ONE contiguous BN*128-byte read
- * (cp.async.bulk) instead of BN separate 128-byte rows K*2 bytes apart — weight streaming at small batch is bound by
- * HBM row locality, not by bytes. */
-int64_t imagd_tiled64_bytes(int N, int K);
-int imagd_pack_weight_tiled64(const void* W, int64_t ldw, int N, int K, void* out, imagd_stream stream);
 
 /* D[M,N] = A[M,K] * W[N,K]^T (+ epilogue).  tcgen05 tensor cores, TMA-fed, fp32 accumulation in TMEM.
  * Replaces every nn.Linear / 1x1 conv on the path: attn.to_q/to_k/to_v/to_out, to_k_ref/to_v_ref
