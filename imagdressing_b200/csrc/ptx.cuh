@@ -36,22 +36,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or ~10 ms pass) instead of
+// spinning — a spinning producer / MMA warp would steal issue slots from the softmax / epilogue warps on its SMSP.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, P;\n\t}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a pipeline bug traps (launch error) instead of hanging the GPU box.
+// Bounded wait: a pipeline bug traps (launch error) after ~2 s instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t tries = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) {
+        if (++tries > 200u) {
             printf("imagd: mbarrier timeout block(%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,
                    blockIdx.z, threadIdx.x, smem_u32(bar), parity);
             __trap();
