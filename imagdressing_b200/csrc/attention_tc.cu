@@ -62,6 +62,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
                     const __grid_constant__ CUtensorMap tmV1, const AttnParams p) {
     using C = AttnCfg<HD_MMA, NATOM, KV_STAGES>;
+    // HD_MMA == 48 only serves head_dim 40: columns 40..47 of every V tile are TMA zero fill. Column 40 is set to 1.0
+    // in shared memory, so O[:, 40] accumulates sum(P) on the tensor core — with exactly the bf16 rounding and the
+    // rescaling the output columns see — and the softmax warps neither add up nor exchange row sums.
+    constexpr bool kOnes = (HD_MMA == 48);
     extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
         printf("imagd: dynamic shared memory base %u is not 1024-byte aligned\n", smem_u32(smem));
@@ -144,16 +148,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
         }
     } else if (warp == 9) {
-        // ------------------------------------------------ MMA issuer
-        if (elect_one()) {
-            constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);     // Q (K-major) x K (K-major)
-            constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD_MMA, 0, 1);  // P (K-major) x V (MN-major)
-            mbar_wait(q_full, 0);
-            for (int i = 0; i < T; ++i) {
-                const int s = i < nb0 ? 0 : 1;
-                const int j = s ? i - nb0 : i;
-                const int st = i % KV_STAGES;
-                const uint32_t ph = (i / KV_STAGES) & 1;
+        // ------------------------------------------------ MMA issuer (the whole warp plants the ones column in V)
+        const bool leader = elect_one();
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);     // Q (K-major) x K (K-major)
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD_MMA, 0, 1);  // P (K-major) x V (MN-major)
+        if (leader) mbar_wait(q_full, 0);
+        __syncwarp();
+        for (int i = 0; i < T; ++i) {
+            const int s = i < nb0 ? 0 : 1;
+            const int j = s ? i - nb0 : i;
+            const int st = i % KV_STAGES;
+            const uint32_t ph = (i / KV_STAGES) & 1;
+            if (leader) {
                 mbar_wait(&k_full[st], ph);
                 tc_fence_after();
                 const uint32_t q_addr = smem_u32(sQ);
@@ -165,8 +171,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                               umma_smem_desc_sw128(k_addr + off, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
                 }
                 umma_commit(s_full);
-                mbar_wait(p_full, i & 1);
+            }
+            if constexpr (kOnes) {
+                // V[:, 40] = 1.0 (bf16 0x3F80): column 40 = 16-byte chunk 5 (swizzled by row), element 0. Overlaps softmax.
                 mbar_wait(&v_full[st], ph);
+                const uint32_t v_tile = smem_u32(sV + st * NATOM * kAtomBytes);
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const uint32_t row = lane + rr * 32;
+                    const uint32_t addr = v_tile + (row >> 3) * 1024 + (row & 7) * 128 + ((5u ^ (row & 7)) << 4);
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<unsigned short>(0x3F80)) : "memory");
+                }
+                fence_proxy_async_smem();
+            }
+            __syncwarp();
+            if (leader) {
+                mbar_wait(p_full, i & 1);
+                if constexpr (!kOnes) mbar_wait(&v_full[st], ph);
                 tc_fence_after();
                 const uint32_t p_addr = smem_u32(sP);
                 const uint32_t v_addr = smem_u32(sV + st * NATOM * kAtomBytes);
@@ -180,8 +201,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 }
                 umma_commit(&kv_empty[st]);
             }
-            umma_commit(o_full);
+            __syncwarp();
         }
+        if (leader) umma_commit(o_full);
     } else {
         // ------------------------------------------------ softmax / correction / epilogue (warps 0-7)
         const int lg = warp & 3;          // TMEM lane quadrant
@@ -238,7 +260,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             mxbuf[half * 128 + r] = mine;
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const float m_blk = fmaxf(__bfloat162float(mine), __bfloat162float(mxbuf[(half ^ 1) * 128 + r]));
-            const float m_new = fmaxf(m_run, m_blk);
+            // Lazy rescale: keep the old reference max unless the row max grew by more than 2^8. The probabilities are
+            // then bounded by 256 instead of 1 (exact in bf16 / fp32 all the same) and O / the row sum are rescaled
+            // only on the rare big jumps — the final O / l does not depend on which reference was used.
+            float m_new = fmaxf(m_run, m_blk);
+            if (m_new - m_run <= 8.0f) m_new = m_run;  // (-inf on a stream's first block: inf > 8 -> take m_blk)
             const float alpha = ex2_approx(m_run - m_new);  // 0 on the first block of a stream
             if (j > 0 && __any_sync(0xffffffffu, m_new > m_run)) {
                 // rescale my chunks of this stream's O accumulator in TMEM
@@ -276,10 +302,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                             e[k] = (cc * 32 + q * 8 + k < valid) ? ex2_approx(__uint_as_float(v[q * 8 + k]) * sc - m_new)
                                                                 : 0.f;
                     }
-                    sum0 += e[0] + e[4];
-                    sum1 += e[1] + e[5];
-                    sum2 += e[2] + e[6];
-                    sum3 += e[3] + e[7];
+                    if constexpr (!kOnes) {
+                        sum0 += e[0] + e[4];
+                        sum1 += e[1] + e[5];
+                        sum2 += e[2] + e[6];
+                        sum3 += e[3] + e[7];
+                    }
                     const uint32_t chunk = static_cast<uint32_t>(cc * 4 + q) ^ rx;
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16),
                                  "r"(pack_bf16x2(e[0], e[1])), "r"(pack_bf16x2(e[2], e[3])),
@@ -287,7 +315,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                                  : "memory");
                 }
             }
-            l_run = l_run * alpha + ((sum0 + sum1) + (sum2 + sum3));
+            if constexpr (!kOnes) l_run = l_run * alpha + ((sum0 + sum1) + (sum2 + sum3));
 
             fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor core (async proxy)
             tc_fence_before();
@@ -297,12 +325,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // ---- epilogue: out = w0 * O0 / l0 + w1 * O1 / l1 (row sums of the two half-row threads meet in the idle P tile)
         mbar_wait(o_full, 0);
         tc_fence_after();
-        float* lbuf = reinterpret_cast<float*>(sP);  // [2 halves][2 values][128 rows]
-        lbuf[(half * 2 + 0) * 128 + r] = l_first;
-        lbuf[(half * 2 + 1) * 128 + r] = l_run;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float lf = l_first + lbuf[((half ^ 1) * 2 + 0) * 128 + r];
-        const float lr = l_run + lbuf[((half ^ 1) * 2 + 1) * 128 + r];
+        float lf, lr;  // row sums of the first stream / the last stream
+        if constexpr (kOnes) {
+            uint32_t t0[16], t1[16];
+            tmem_ld16(tmem_O + lane_addr + 32, t0);  // columns 32..47 of O_0: element 8 is column 40
+            tmem_ld16(tmem_O + C::kOStride + lane_addr + 32, t1);
+            tmem_ld_wait();
+            lf = __uint_as_float(t0[8]);
+            lr = nb1 > 0 ? __uint_as_float(t1[8]) : lf;
+        } else {
+            float* lbuf = reinterpret_cast<float*>(sP);  // [2 halves][2 values][128 rows]
+            lbuf[(half * 2 + 0) * 128 + r] = l_first;
+            lbuf[(half * 2 + 1) * 128 + r] = l_run;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            lf = l_first + lbuf[((half ^ 1) * 2 + 0) * 128 + r];
+            lr = l_run + lbuf[((half ^ 1) * 2 + 1) * 128 + r];
+        }
         float w0, w1 = 0.f;
         if (nb1 > 0) {
             w0 = p.oscale0 / lf;
