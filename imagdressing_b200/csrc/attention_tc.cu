@@ -231,26 +231,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             mbar_wait(s_full, i & 1);
             tc_fence_after();
 
-            // pass 1: maximum of my 64 columns, 32 at a time (registers are the scarce resource: 2 CTAs x 320
-            // threads per SM leaves 102 each, and there is no L1 left to absorb spills next to 226 KB of smem)
+            // pass 1: maximum of my 64 columns. Both 32-column loads are in flight together (one exposed TMEM round
+            // trip); the second half stays in registers for pass 2, the first half is re-read underneath its arithmetic.
             float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+            uint32_t va[32], vb[32];
+            tmem_ld32(tmem_S + lane_addr + half * 64, va);
+            tmem_ld32(tmem_S + lane_addr + half * 64 + 32, vb);
+            tmem_ld_wait();
+            if (valid >= 64) {
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                uint32_t v[32];
-                tmem_ld32(tmem_S + lane_addr + half * 64 + cc * 32, v);
-                tmem_ld_wait();
-                if (valid >= 64) {
+                for (int k = 0; k < 32; k += 4) {
+                    mx0 = fmaxf(mx0, fmaxf(__uint_as_float(va[k]), __uint_as_float(vb[k])));
+                    mx1 = fmaxf(mx1, fmaxf(__uint_as_float(va[k + 1]), __uint_as_float(vb[k + 1])));
+                    mx2 = fmaxf(mx2, fmaxf(__uint_as_float(va[k + 2]), __uint_as_float(vb[k + 2])));
+                    mx3 = fmaxf(mx3, fmaxf(__uint_as_float(va[k + 3]), __uint_as_float(vb[k + 3])));
+                }
+            } else {
 #pragma unroll
-                    for (int k = 0; k < 32; k += 4) {
-                        mx0 = fmaxf(mx0, __uint_as_float(v[k]));
-                        mx1 = fmaxf(mx1, __uint_as_float(v[k + 1]));
-                        mx2 = fmaxf(mx2, __uint_as_float(v[k + 2]));
-                        mx3 = fmaxf(mx3, __uint_as_float(v[k + 3]));
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 32; ++k)
-                        if (cc * 32 + k < valid) mx0 = fmaxf(mx0, __uint_as_float(v[k]));
+                for (int k = 0; k < 32; ++k) {
+                    if (k < valid) mx0 = fmaxf(mx0, __uint_as_float(va[k]));
+                    if (32 + k < valid) mx1 = fmaxf(mx1, __uint_as_float(vb[k]));
                 }
             }
             const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
@@ -282,14 +282,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             m_run = m_new;
 
-            // pass 2: P = exp2(S*scale - m) for my 64 columns -> one 64-wide swizzled atom of the P tile
+            // pass 2: P = exp2(S*scale - m) for my 64 columns -> one 64-wide swizzled atom of the P tile. Columns 32..63
+            // come from the registers kept since pass 1 while columns 0..31 are being re-read from TMEM.
             float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
             const float sc = p.scale_log2;
+            tmem_ld32(tmem_S + lane_addr + half * 64, va);
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                uint32_t v[32];
-                tmem_ld32(tmem_S + lane_addr + half * 64 + cc * 32, v);
-                tmem_ld_wait();
+            for (int cc = 1; cc >= 0; --cc) {
+                uint32_t(&v)[32] = cc ? vb : va;
+                if (cc == 0) tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float e[8];
