@@ -50,7 +50,7 @@ struct AttnCfg {
     static constexpr int kVOff = kKOff + KV_STAGES * NATOM * kAtomBytes;
     static constexpr int kPOff = kVOff + KV_STAGES * NATOM * kAtomBytes;
     static constexpr int kBarOff = kPOff + 2 * kAtomBytes;
-    static constexpr int kNumBars = 1 + 3 * KV_STAGES + 3;
+    static constexpr int kNumBars = 1 + 3 * KV_STAGES + 5;  // q, k/v/empty per stage, s_full, p_full, o_full, s_free, pv_done
     static constexpr int kMxOff = kBarOff + kNumBars * 8 + 16;  // [2 halves][128 rows] bf16 partial row maxima
     static constexpr int kTotal = kMxOff + 512;
 };
@@ -82,7 +82,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* s_full = kv_empty + KV_STAGES;
     uint64_t* p_full = s_full + 1;
     uint64_t* o_full = p_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+    uint64_t* s_free = o_full + 1;   // all 256 softmax threads hold S(i) in registers: the tensor core may overwrite S
+    uint64_t* pv_done = s_free + 1;  // P.V(i) retired: P may be overwritten, O may be rescaled
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
 
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
@@ -108,6 +110,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_init(s_full, 1);
         mbar_init(p_full, 256);
         mbar_init(o_full, 1);
+        mbar_init(s_free, 256);
+        mbar_init(pv_done, 1);
         fence_barrier_init();
     }
     if (warp == 9) {
@@ -152,25 +156,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const bool leader = elect_one();
         constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);     // Q (K-major) x K (K-major)
         constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD_MMA, 0, 1);  // P (K-major) x V (MN-major)
-        if (leader) mbar_wait(q_full, 0);
+        // S(i+1) = Q K(i+1)^T is issued as soon as the softmax warps hold S(i) in registers (s_free), so the tensor
+        // core computes it underneath softmax(i); P.V(i) follows when P(i) is written. With a one-stage K/V ring
+        // (head_dim 160) the next K tile only lands after P.V(i) frees the slot, so QK(i+1) keeps the old order there.
+        constexpr bool kEarly = KV_STAGES > 1;
+        auto issue_qk = [&](int i) {
+            const int st = i % KV_STAGES;
+            mbar_wait(&k_full[st], (i / KV_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t q_addr = smem_u32(sQ);
+            const uint32_t k_addr = smem_u32(sK + st * NATOM * kAtomBytes);
+#pragma unroll
+            for (int ks = 0; ks < HD_MMA / 16; ++ks) {
+                const uint32_t off = (ks / 4) * kAtomBytes + (ks % 4) * 32;
+                umma_bf16(tmem_S, umma_smem_desc_sw128(q_addr + off, 16, 1024),
+                          umma_smem_desc_sw128(k_addr + off, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
+            }
+            umma_commit(s_full);
+        };
+        if (leader) {
+            mbar_wait(q_full, 0);
+            issue_qk(0);
+        }
         __syncwarp();
         for (int i = 0; i < T; ++i) {
             const int s = i < nb0 ? 0 : 1;
             const int j = s ? i - nb0 : i;
             const int st = i % KV_STAGES;
             const uint32_t ph = (i / KV_STAGES) & 1;
-            if (leader) {
-                mbar_wait(&k_full[st], ph);
+            if (leader && kEarly && i + 1 < T) {
+                mbar_wait(s_free, i & 1);
                 tc_fence_after();
-                const uint32_t q_addr = smem_u32(sQ);
-                const uint32_t k_addr = smem_u32(sK + st * NATOM * kAtomBytes);
-#pragma unroll
-                for (int ks = 0; ks < HD_MMA / 16; ++ks) {
-                    const uint32_t off = (ks / 4) * kAtomBytes + (ks % 4) * 32;
-                    umma_bf16(tmem_S, umma_smem_desc_sw128(q_addr + off, 16, 1024),
-                              umma_smem_desc_sw128(k_addr + off, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
-                }
-                umma_commit(s_full);
+                issue_qk(i + 1);
             }
             if constexpr (kOnes) {
                 // V[:, 40] = 1.0 (bf16 0x3F80): column 40 = 16-byte chunk 5 (swizzled by row), element 0. Overlaps softmax.
@@ -200,6 +217,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                               (j > 0 || ks > 0) ? 1u : 0u);
                 }
                 umma_commit(&kv_empty[st]);
+                umma_commit(pv_done);
+                if (!kEarly && i + 1 < T) {
+                    mbar_wait(s_free, i & 1);  // (already complete: P(i) was written after S(i) was read)
+                    issue_qk(i + 1);
+                }
             }
             __syncwarp();
         }
@@ -231,13 +253,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             mbar_wait(s_full, i & 1);
             tc_fence_after();
 
-            // pass 1: maximum of my 64 columns. Both 32-column loads are in flight together (one exposed TMEM round
-            // trip); the second half stays in registers for pass 2, the first half is re-read underneath its arithmetic.
+            // pass 1: my 64 scores -> registers (both 32-column loads in flight together), S is then released to the
+            // tensor core for the next key block; row maximum
             float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
             uint32_t va[32], vb[32];
             tmem_ld32(tmem_S + lane_addr + half * 64, va);
             tmem_ld32(tmem_S + lane_addr + half * 64 + 32, vb);
             tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_free);  // my 64 scores live in registers from here on
             if (valid >= 64) {
 #pragma unroll
                 for (int k = 0; k < 32; k += 4) {
@@ -266,6 +290,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             float m_new = fmaxf(m_run, m_blk);
             if (m_new - m_run <= 8.0f) m_new = m_run;  // (-inf on a stream's first block: inf > 8 -> take m_blk)
             const float alpha = ex2_approx(m_run - m_new);  // 0 on the first block of a stream
+            if (i > 0) {  // P.V(i-1) must have retired before P is overwritten or O rescaled (normally long done)
+                mbar_wait(pv_done, (i - 1) & 1);
+                tc_fence_after();
+            }
             if (j > 0 && __any_sync(0xffffffffu, m_new > m_run)) {
                 // rescale my chunks of this stream's O accumulator in TMEM
                 const uint32_t o_addr = tmem_O + s * C::kOStride + lane_addr;
@@ -282,15 +310,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             m_run = m_new;
 
-            // pass 2: P = exp2(S*scale - m) for my 64 columns -> one 64-wide swizzled atom of the P tile. Columns 32..63
-            // come from the registers kept since pass 1 while columns 0..31 are being re-read from TMEM.
+            // pass 2: P = exp2(S*scale - m) for my 64 columns (still in registers) -> one 64-wide swizzled atom of P
             float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
             const float sc = p.scale_log2;
-            tmem_ld32(tmem_S + lane_addr + half * 64, va);
 #pragma unroll
-            for (int cc = 1; cc >= 0; --cc) {
+            for (int cc = 0; cc < 2; ++cc) {
                 uint32_t(&v)[32] = cc ? vb : va;
-                if (cc == 0) tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float e[8];
