@@ -35,6 +35,9 @@ __global__ void __launch_bounds__(kGnThreads, 2) groupnorm_fused_kernel(
     __shared__ float s_b[kGnThreads * 8];  // phase 1: per (row slot, channel) sum of sq | phase 2: per-channel shift
     __shared__ float s_mean[64];
     __shared__ float s_rstd[64];
+    extern __shared__ float s_affine[];  // gamma | beta, fetched before the rendezvous (off the critical path)
+    float* s_gamma = s_affine;
+    float* s_beta = s_affine + C;
     const int n = blockIdx.y, chunk = blockIdx.x;
     const int CV = C / 8;
     const int rows = kGnThreads / CV;  // pixel rows processed per iteration (>= 1 since C <= 2560 < 8*512)
@@ -42,6 +45,10 @@ __global__ void __launch_bounds__(kGnThreads, 2) groupnorm_fused_kernel(
     const int p_begin = chunk * ppc;
     const int p_end = min(HW, p_begin + ppc);
     const int cpg = C / groups;
+    for (int c = threadIdx.x; c < C; c += kGnThreads) {
+        s_gamma[c] = gamma ? __ldg(gamma + c) : 1.f;
+        s_beta[c] = beta ? __ldg(beta + c) : 0.f;
+    }
     unsigned int* counters = reinterpret_cast<unsigned int*>(ws) - kGnCounters + 2 * n;
 
     // ---------------- phase 1: partial statistics of my pixel chunk
@@ -107,7 +114,7 @@ __global__ void __launch_bounds__(kGnThreads, 2) groupnorm_fused_kernel(
         atomicAdd(&counters[0], 1u);
         unsigned int spins = 0;
         while (*reinterpret_cast<volatile unsigned int*>(&counters[0]) < static_cast<unsigned int>(chunks)) {
-            __nanosleep(64);
+            __nanosleep(20);
             if (++spins > (1u << 22)) {
                 printf("imagd: groupnorm rendezvous timeout (sample %d chunk %d of %d)\n", n, chunk, chunks);
                 __trap();
@@ -122,39 +129,42 @@ __global__ void __launch_bounds__(kGnThreads, 2) groupnorm_fused_kernel(
         }
     }
     __syncthreads();
-    // ---------------- every CTA folds the sample's partials (fixed order) -> mean / rstd
-    if (threadIdx.x < groups) {
-        const int g = threadIdx.x;
+    // ---------------- every CTA folds the sample's partials -> mean / rstd. All 512 threads fetch in ONE round trip
+    // (thread t: chunk t / groups + k * (512 / groups), group t % groups), then a fixed-order fold in shared memory.
+    {
+        const int per = kGnThreads / groups;  // chunk rows fetched per sweep (>= 8 since groups <= 64)
+        const int g = threadIdx.x % groups, c0 = threadIdx.x / groups;
         float a = 0.f, b = 0.f;
-        const float* src = ws + (static_cast<int64_t>(n) * chunks * groups + g) * 2;
-        for (int c = 0; c < chunks; c += 4) {
-            float pa[4], pb[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                pa[t] = pb[t] = 0.f;
-                if (c + t < chunks) {
-                    pa[t] = __ldcg(src + static_cast<int64_t>(c + t) * groups * 2);
-                    pb[t] = __ldcg(src + static_cast<int64_t>(c + t) * groups * 2 + 1);
-                }
+        if (c0 < per) {
+            const float* src = ws + (static_cast<int64_t>(n) * chunks * groups + g) * 2;
+            for (int c = c0; c < chunks; c += per) {  // <= 8 independent loads per thread (chunks <= 64), issued together
+                const float2 v = __ldcg(reinterpret_cast<const float2*>(src + static_cast<int64_t>(c) * groups * 2));
+                a += v.x;
+                b += v.y;
             }
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                a += pa[t];
-                b += pb[t];
-            }
+            s_a[c0 * groups + g] = a;
+            s_b[c0 * groups + g] = b;
         }
-        const float cnt = static_cast<float>(cpg) * static_cast<float>(HW);
-        const float mean = a / cnt;
-        const float var = fmaxf(b / cnt - mean * mean, 0.f);
-        s_mean[g] = mean;
-        s_rstd[g] = rsqrtf(var + eps);
+        __syncthreads();
+        if (threadIdx.x < groups) {
+            float ta = 0.f, tb = 0.f;
+            for (int r = 0; r < per; ++r) {
+                ta += s_a[r * groups + threadIdx.x];
+                tb += s_b[r * groups + threadIdx.x];
+            }
+            const float cnt = static_cast<float>(cpg) * static_cast<float>(HW);
+            const float mean = ta / cnt;
+            const float var = fmaxf(tb / cnt - mean * mean, 0.f);
+            s_mean[threadIdx.x] = mean;
+            s_rstd[threadIdx.x] = rsqrtf(var + eps);
+        }
+        __syncthreads();
     }
-    __syncthreads();
     for (int c = threadIdx.x; c < C; c += kGnThreads) {
         const int g = c / cpg;
-        const float sc = (gamma ? gamma[c] : 1.f) * s_rstd[g];
+        const float sc = s_gamma[c] * s_rstd[g];
         s_a[c] = sc;
-        s_b[c] = (beta ? beta[c] : 0.f) - s_mean[g] * sc;
+        s_b[c] = s_beta[c] - s_mean[g] * sc;
     }
     __syncthreads();
     // ---------------- phase 2: normalise my pixel chunk
@@ -313,7 +323,12 @@ int imagd_groupnorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int N
     IMAGD_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y), "groupnorm: alignment");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int chunks = gn_chunks(HW, NB);
-    IMAGD_CUDA(launch_pdl(groupnorm_fused_kernel, dim3(chunks, NB), dim3(kGnThreads), 0, st,
+    static bool attr_set = false;
+    if (!attr_set) {  // 33 KB static + up to 20 KB dynamic (gamma | beta) exceeds the 48 KB default
+        IMAGD_CUDA(cudaFuncSetAttribute(groupnorm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set = true;
+    }
+    IMAGD_CUDA(launch_pdl(groupnorm_fused_kernel, dim3(chunks, NB), dim3(kGnThreads), 2 * C * sizeof(float), st,
                           reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, HW, C,
                           groups, chunks, reinterpret_cast<float*>(ws) + kGnCounters, gamma, beta, eps, fuse_silu));
     return IMAGD_OK;
