@@ -254,64 +254,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
-        } else if (!ep.out_fp32) {
-            // ---- coalesced path: each warp transposes its 32 rows x 32 columns of fp32 accumulators through shared
-            // memory (the TMA ring is idle by now), after which lane l owns 4 consecutive columns of rows l/8 + 4i:
-            // a store (and a residual load) instruction then covers 4 rows x 64 contiguous bytes — full 32-byte
-            // sectors — instead of 32 rows x 16 bytes. The epilogue arithmetic happens in the transposed domain.
-            float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 36);  // 36-float row pitch: no bank conflicts
-            const int lr = lane >> 3;        // row within a group of 4
-            const int lc = (lane & 7) * 4;   // my 4 columns within the 32-column chunk
-            // per-row metadata travels by shuffle from the lane that owns the row
-            const int pix_lo = static_cast<int>(pix & 0xffffffffll), pix_hi = static_cast<int>(pix >> 32);
-            const int grp = (ep.rowvec != nullptr && row_ok) ? static_cast<int>(pix / ep.rows_per_group) : 0;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                uint32_t v[32];
-                load_acc(c0, v);
-                const int col = n_blk * BLOCK_N + c0;
-                if (col >= p.N) continue;  // warp-uniform
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(stage + lane * 36 + j) =
-                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                    __uint_as_float(v[j + 3]));
-                __syncwarp();
-                const int cg = col + lc;
-                const bool col_ok = cg < p.N;  // N % 8 == 0 and lc % 4 == 0 -> all 4 columns valid together
-                float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ep.bias && col_ok) bs = __ldg(reinterpret_cast<const float4*>(ep.bias + cg));
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int rr = lr + 4 * i;  // row (within this warp's 32) handled in this iteration
-                    const bool ok = __shfl_sync(0xffffffffu, row_ok ? 1 : 0, rr) != 0;
-                    const int64_t rpix = (static_cast<int64_t>(__shfl_sync(0xffffffffu, pix_hi, rr)) << 32) |
-                                         static_cast<uint32_t>(__shfl_sync(0xffffffffu, pix_lo, rr));
-                    const int rgrp = __shfl_sync(0xffffffffu, grp, rr);
-                    if (!ok || !col_ok) continue;
-                    const float4 a = *reinterpret_cast<const float4*>(stage + rr * 36 + lc);
-                    float f[4] = {alpha * a.x + bs.x, alpha * a.y + bs.y, alpha * a.z + bs.z, alpha * a.w + bs.w};
-                    if (ep.rowvec) {
-                        const float4 rvv = __ldg(reinterpret_cast<const float4*>(ep.rowvec + rgrp * ep.rowvec_ld + cg));
-                        f[0] += rvv.x; f[1] += rvv.y; f[2] += rvv.z; f[3] += rvv.w;
-                    }
-                    if (ep.act == IMAGD_ACT_SILU) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) f[j] = silu(f[j]);
-                    } else if (ep.act == IMAGD_ACT_GELU) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) f[j] = gelu_erf(f[j]);
-                    }
-                    if (ep.residual) {
-                        const uint2 rv = __ldg(reinterpret_cast<const uint2*>(
-                            reinterpret_cast<const __nv_bfloat16*>(ep.residual) + rpix * ep.ldr + cg));
-                        f[0] += bf16lo(rv.x); f[1] += bf16hi(rv.x); f[2] += bf16lo(rv.y); f[3] += bf16hi(rv.y);
-                    }
-                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + rpix * p.ldd + cg) =
-                        make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]));
-                }
-            }
         } else {
 #pragma unroll 1
             for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
