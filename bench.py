@@ -42,6 +42,11 @@ def parse():
     ap.add_argument("--batch", type=int, default=1, help="images per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    # non-default workloads (BASELINE.json configs[2] / configs[3]); the driver's contract run never passes these
+    ap.add_argument("--workload", default="base", choices=["base", "ipa_controlnet", "inpaint"],
+                    help="base = configs[1] (the metric); ipa_controlnet = configs[2]; inpaint = configs[3]")
+    ap.add_argument("--height", type=int, default=512)
+    ap.add_argument("--width", type=int, default=512)
     return ap.parse_args()
 
 
@@ -95,11 +100,17 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ model builders
-def build_product(dev):
-    from adapter.attention_processor import CacheAttnProcessor2_0, CAttnProcessor2_0, RefSAttnProcessor2_0
-    from dressing_sd.pipelines.IMAGDressing_v1_pipeline import IMAGDressing_v1
+def build_product(dev, workload="base"):
+    from adapter.attention_processor import (CacheAttnProcessor2_0, CAttnProcessor2_0, LoraRefSAttnProcessor2_0,
+                                             LoRAIPAttnProcessor2_0, RefSAttnProcessor2_0)
     from imagdressing_b200 import modeling
     from imagdressing_b200.scheduler import DDIMScheduler
+    if workload == "base":
+        from dressing_sd.pipelines.IMAGDressing_v1_pipeline import IMAGDressing_v1
+    elif workload == "ipa_controlnet":
+        from dressing_sd.pipelines.IMAGDressing_v1_pipeline_ipa_controlnet import IMAGDressing_v1
+    else:
+        from dressing_sd.pipelines.IMAGDressing_v1_pipeline_controlnet_inpainting import IMAGDressing_v1
 
     unet = modeling.UNet2DConditionModel().to(dev, torch.bfloat16)
     procs = {}
@@ -110,8 +121,12 @@ def build_product(dev):
             hidden = list(reversed(unet.config.block_out_channels))[int(name[len("up_blocks.")])]
         else:
             hidden = unet.config.block_out_channels[int(name[len("down_blocks.")])]
-        procs[name] = (RefSAttnProcessor2_0(name, hidden) if name.endswith("attn1.processor")
-                       else CAttnProcessor2_0(name, hidden, unet.config.cross_attention_dim))
+        if workload == "ipa_controlnet":  # inference_IMAGdressing_ipa_controlnetpose.py:80-99 (rank-128 LoRA, 4 face tokens)
+            procs[name] = (LoraRefSAttnProcessor2_0(name, hidden) if name.endswith("attn1.processor")
+                           else LoRAIPAttnProcessor2_0(hidden, unet.config.cross_attention_dim, rank=128, num_tokens=4))
+        else:
+            procs[name] = (RefSAttnProcessor2_0(name, hidden) if name.endswith("attn1.processor")
+                           else CAttnProcessor2_0(name, hidden, unet.config.cross_attention_dim))
     unet.set_attn_processor(procs)
     unet.to(dev, torch.bfloat16)
     ref = modeling.UNet2DConditionModel().to(dev, torch.bfloat16)
@@ -120,29 +135,56 @@ def build_product(dev):
     modeling.init_synthetic_fast_(ref, 1)
     sched = DDIMScheduler(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
                           clip_sample=False, set_alpha_to_one=False, steps_offset=1)  # :119-127
+    extra = {}
+    if workload != "base":
+        cn = modeling.ControlNetModel().to(dev, torch.bfloat16)
+        modeling.init_synthetic_fast_(cn, 2)
+        extra["controlnet"] = cn
+        if workload == "ipa_controlnet":
+            extra["ip_ckpt"] = None
+            unet.invalidate_packed()
     pipe = IMAGDressing_v1(vae=None, reference_unet=ref, unet=unet, tokenizer=None, text_encoder=None,
-                           image_encoder=None, ImgProj=None, scheduler=sched, safety_checker=None, feature_extractor=None)
+                           image_encoder=None, ImgProj=None, scheduler=sched, safety_checker=None, feature_extractor=None,
+                           **extra)
     if os.environ.get("IMAGD_NO_GRAPH"):  # profiling aid: every kernel launched eagerly so ncu lists them
         pipe._engine.use_cuda_graph = False
     return pipe
 
 
-def synth_inputs(B, dev, rank=0, pinned=False):
+def synth_inputs(B, dev, rank=0, pinned=False, workload="base", lh=HW, lw=HW):
     """SURVEY.md §8d synthetic inputs; per-rank seeds derive from the global sample index."""
     g = torch.Generator().manual_seed(42 + 1000 * rank)
-    t = dict(latents=torch.randn(B, 4, HW, HW, generator=g), garment=torch.randn(B, 4, HW, HW, generator=g) * 0.18215 * 5,
+    t = dict(latents=torch.randn(B, 4, lh, lw, generator=g), garment=torch.randn(B, 4, lh, lw, generator=g) * 0.18215 * 5,
              prompt=torch.randn(B, 77, 768, generator=g), negative=torch.randn(B, 77, 768, generator=g),
              gtok=torch.randn(B, 16, 768, generator=g))
+    if workload != "base":
+        t["pose"] = torch.rand(B, 3, lh * 8, lw * 8, generator=g)
+    if workload == "ipa_controlnet":
+        t["face"] = torch.randn(B, 4, 768, generator=g)
+        t["face_null"] = torch.randn(B, 4, 768, generator=g) * 0.1
+    if workload == "inpaint":
+        t["image_latents"] = torch.randn(B, 4, lh, lw, generator=g)
+        m = torch.zeros(B, 1, lh, lw)
+        m[:, :, lh // 4: 3 * lh // 4, lw // 4: 3 * lw // 4] = 1.0
+        t["mask"] = m
     if pinned:
         return {k: v.pin_memory() for k, v in t.items()}
     return {k: v.to(dev) for k, v in t.items()}
 
 
-def run_pipe(pipe, x):
-    return pipe(prompt=None, null_prompt=None, negative_prompt=None, ref_image=None, width=HW * 8, height=HW * 8,
-                num_inference_steps=STEPS_DDIM, guidance_scale=GUIDANCE, image_scale=1.0, output_type="latent",
-                prompt_embeds=x["prompt"], negative_prompt_embeds=x["negative"], latents=x["latents"],
-                garment_tokens=x["gtok"], ref_image_latents=x["garment"]).images
+def run_pipe(pipe, x, workload="base"):
+    lh, lw = x["latents"].shape[-2:]
+    kw = dict(prompt=None, null_prompt=None, negative_prompt=None, ref_image=None, width=lw * 8, height=lh * 8,
+              num_inference_steps=STEPS_DDIM, guidance_scale=GUIDANCE, output_type="latent",
+              prompt_embeds=x["prompt"], negative_prompt_embeds=x["negative"], latents=x["latents"],
+              garment_tokens=x["gtok"], ref_image_latents=x["garment"])
+    if workload == "base":
+        return pipe(image_scale=1.0, **kw).images
+    if workload == "ipa_controlnet":
+        return pipe(pose_image=x["pose"], image_scale=1.0, ipa_scale=0.9, s_lora_scale=0.2, c_lora_scale=0.2,
+                    face_tokens=x["face"], face_null_tokens=x["face_null"], **kw).images
+    return pipe(control_image=x["pose"], strength=1.0, controlnet_conditioning_scale=1.0, image_latents=x["image_latents"],
+                mask_latents=x["mask"], **kw).images
 
 
 # ------------------------------------------------------------------------------------------------ roofline legs
@@ -313,13 +355,14 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = a.batch
-    pipe = build_product(dev)
-    x_dev = synth_inputs(B, dev, rank)
-    x_host = synth_inputs(B, dev, rank, pinned=True)
+    lh, lw = a.height // 8, a.width // 8
+    pipe = build_product(dev, a.workload)
+    x_dev = synth_inputs(B, dev, rank, False, a.workload, lh, lw)
+    x_host = synth_inputs(B, dev, rank, True, a.workload, lh, lw)
     from imagdressing_b200.parallel import gather_latents
 
     def one_step(x):
-        out = run_pipe(pipe, x)
+        out = run_pipe(pipe, x, a.workload)
         # the single collective of the path: all-gather of the output latents (NCCL over NVLink); no-op at N=1
         return gather_latents(out.contiguous(), world * B)
 
@@ -367,24 +410,30 @@ def main():
     roofline = dict(roofs[dominant])
     roofline["kernel"] = dominant
     h2d = sum(v.numel() * v.element_size() for v in x_host.values())
-    d2h = world * B * 4 * HW * HW * 4
+    d2h = world * B * 4 * lh * lw * 4
+    standard = a.workload == "base" and (lh, lw) == (HW, HW)
+    wl = {"base": "garment-conditioned sampling (BASELINE.json configs[1])",
+          "ipa_controlnet": "IP-Adapter face tokens (4, rank-128 LoRA processors) + ControlNet-pose residuals "
+                            "(BASELINE.json configs[2])",
+          "inpaint": "ControlNet inpainting path with the fused per-step latent blend (BASELINE.json configs[3])"}[a.workload]
     line = {
-        "metric": "images/sec, 512x512 50-step DDIM garment-conditioned (CFG)",
+        "metric": f"images/sec, {a.height}x{a.width} 50-step DDIM garment-conditioned (CFG)",
         "value": round(value, 4), "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": round(ms_total / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"batch-{B}/GPU 512x512 50-step DDIM garment-conditioned sampling, CFG {GUIDANCE} "
-                               "(BASELINE.json configs[1]); random-init SD1.5 denoising UNet + garment UNet; timed "
-                               "region = garment pass + 50 steps (VAE/CLIP excluded)",
-                   "global_batch": world * B, "latent": [HW, HW], "ddim_steps": STEPS_DDIM, "parallelism": f"dp{world}",
+        "config": {"workload": f"batch-{B}/GPU {a.height}x{a.width} (HxW) 50-step DDIM, CFG {GUIDANCE}: {wl}; random-init "
+                               "SD1.5 denoising UNet + garment UNet; timed region = garment pass + 50 steps "
+                               "(VAE/CLIP excluded)",
+                   "global_batch": world * B, "latent": [lh, lw], "ddim_steps": STEPS_DDIM, "parallelism": f"dp{world}",
                    "l2": "activations+weights (3.4 GB bf16) exceed the 126 MB L2; no explicit flush between steps"},
         "e2e": {"value": round(e2e_v, 4), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clocks,
-        "model_tflops": round(value / world * TFLOP_PER_IMAGE, 1),
-        "model_frac_of_sustained_bf16": round(value / world * TFLOP_PER_IMAGE / tf_sus, 4),
         "roofline": roofline, "kernels": roofs,
     }
-    if not a.no_cpu_baseline and world == 1:
+    if standard:  # the analytic work model is for the base 512x512 workload only
+        line["model_tflops"] = round(value / world * TFLOP_PER_IMAGE, 1)
+        line["model_frac_of_sustained_bf16"] = round(value / world * TFLOP_PER_IMAGE / tf_sus, 4)
+    if not a.no_cpu_baseline and world == 1 and standard:
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line))
     if world > 1:

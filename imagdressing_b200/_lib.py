@@ -56,6 +56,7 @@ SIGNATURES = {
                                 POINTER(Epilogue), c_void_p]),
     "imagd_gemm_debug_force": (c_int, [c_int, c_int, c_int]),
     "imagd_gemm_debug_log": (c_int, [c_int, c_char_p, c_int]),
+    "imagd_gemm_debug_timeline": (c_int, [c_void_p]),
     "imagd_conv3x3_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_int,
                                    POINTER(Epilogue), c_void_p]),
     "imagd_attention_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int,

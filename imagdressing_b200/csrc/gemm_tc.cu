@@ -42,7 +42,16 @@ struct GemmParams {
     int kb_per_split;
     float* ws;
     unsigned int* counters;
+    // debug: when non-null, every CTA records its timeline (imagd_gemm_debug_timeline; tools/gemm_timeline.py)
+    unsigned long long* dbg;
 };
+
+__device__ __forceinline__ void dbg_mark(const GemmParams& p, int slot) {
+    if (p.dbg != nullptr) {
+        const int64_t cta = (static_cast<int64_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        p.dbg[cta * 8 + slot] = static_cast<unsigned long long>(clock64());
+    }
+}
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
@@ -53,12 +62,17 @@ struct GemmSmem {
     static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarOffset = STAGES * kStageBytes;
-    static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16;
+    static constexpr int kVecOffset = (kBarOffset + (2 * STAGES + 1) * 8 + 16 + 15) & ~15;  // float4 reads
+    // epilogue vectors staged once per CTA: bias[BLOCK_N] | row vector[BLOCK_N] (when the tile lies in one row group)
+    static constexpr int kTotal = kVecOffset + 2 * BLOCK_N * 4;
 };
 
 __host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 64 ? 64 : (n <= 128 ? 128 : 256); }
 
-template <int BLOCK_N, int STAGES>
+// LINEAR = the epilogue has no activation and writes bf16 (every conv and most linears of the UNet): straight-line,
+// branch-free column loop with the next TMEM chunk and the next residual chunk in flight. !LINEAR = the generic epilogue
+// (SiLU / GELU / GEGLU / fp32 output).
+template <int BLOCK_N, int STAGES, bool LINEAR>
 __global__ void __launch_bounds__(192, (GemmSmem<BLOCK_N, STAGES>::kTotal <= 112 * 1024) ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     using L = GemmSmem<BLOCK_N, STAGES>;
@@ -71,10 +85,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    float* s_bias = reinterpret_cast<float*>(smem + L::kVecOffset);
+    float* s_rowvec = s_bias + BLOCK_N;
 
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0 && p.dbg != nullptr) {
+        dbg_mark(p, 0);
+        unsigned long long gt;
+        unsigned int smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const int64_t cta = (static_cast<int64_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        p.dbg[cta * 8 + 6] = gt;
+        p.dbg[cta * 8 + 7] = smid;
+    }
 
     // tile coordinates
     const int m_blk = blockIdx.x;
@@ -105,6 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) dbg_mark(p, 1);
     pdl_wait();  // predecessor's output (our A operand / residual) and our output buffer are safe from here on
 
     if (warp == 0) {
@@ -136,6 +163,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t phase = (i / STAGES) & 1;
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
+                if (i == 0) dbg_mark(p, 2);
                 const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
                 const uint32_t sb = sa + kABytes;
 #pragma unroll
@@ -147,6 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
             }
             umma_commit(tmem_full_bar);  // accumulator complete
+            dbg_mark(p, 3);
         }
     } else {
         // ---------------- epilogue ----------------
@@ -159,18 +188,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int64_t pix = (static_cast<int64_t>(n) * p.H + y) * p.W + x;
         const imagd_epilogue& ep = p.ep;
         const float alpha = ep.alpha;
-        const float* rowvec = nullptr;
-        if (ep.rowvec != nullptr && row_ok) rowvec = ep.rowvec + (pix / ep.rows_per_group) * ep.rowvec_ld;
         const __nv_bfloat16* res = nullptr;
         if (ep.residual != nullptr && row_ok)
             res = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + pix * ep.ldr;
+        const bool split = p.splits > 1;
+
+        // ---- while the mainloop runs: stage the per-column vectors in shared memory (every row of the tile reads the
+        // same bias; the row vector too when the whole tile lies in one row group, i.e. one sample) and fetch the first
+        // residual chunk. Loads issued one at a time inside the column loop serialise on L2 latency (measured: the
+        // epilogue took 14-26k clocks vs 5-9k without bias / residual), so everything the loop needs is in flight early.
+        const int col_base = n_blk * BLOCK_N;
+        const float* rowvec = nullptr;   // per-thread global fallback (tile spans several row groups)
+        bool rowvec_shared = false;
+        if (ep.rowvec != nullptr) {
+            const int xl = min(x0 + p.bw, p.W) - 1, yl = min(y0 + p.bh, p.H) - 1, nl = min(n0 + p.bn, p.NB) - 1;
+            const int64_t pix_first = (static_cast<int64_t>(n0) * p.H + y0) * p.W + x0;
+            const int64_t pix_last = (static_cast<int64_t>(nl) * p.H + yl) * p.W + xl;
+            const int64_t g_first = pix_first / ep.rows_per_group;
+            rowvec_shared = g_first == pix_last / ep.rows_per_group;
+            if (rowvec_shared) {
+                const float* src = ep.rowvec + g_first * ep.rowvec_ld;
+                for (int c = threadIdx.x - 64; c < BLOCK_N; c += 128)
+                    s_rowvec[c] = (col_base + c < p.N) ? __ldg(src + col_base + c) : 0.f;
+            } else if (row_ok) {
+                rowvec = ep.rowvec + (pix / ep.rows_per_group) * ep.rowvec_ld;
+            }
+        }
+        if (LINEAR && !rowvec_shared) {  // the straight-line loop always adds the staged vectors: absent = zeros
+            for (int c = threadIdx.x - 64; c < BLOCK_N; c += 128) s_rowvec[c] = 0.f;
+        }
+        if (ep.bias != nullptr) {
+            for (int c = threadIdx.x - 64; c < BLOCK_N; c += 128)
+                s_bias[c] = (col_base + c < p.N) ? __ldg(ep.bias + col_base + c) : 0.f;
+        } else if (LINEAR) {
+            for (int c = threadIdx.x - 64; c < BLOCK_N; c += 128) s_bias[c] = 0.f;
+        }
+        uint4 rcur[4];
+        auto load_res = [&](int c0, uint4(&rv)[4]) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int cg = col_base + c0 + g * 8;
+                rv[g] = (res != nullptr && cg < p.N) ? __ldg(reinterpret_cast<const uint4*>(res + cg))
+                                                     : make_uint4(0u, 0u, 0u, 0u);
+            }
+        };
+        if (!split) load_res(0, rcur);
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // s_bias / s_rowvec visible to the four epilogue warps
 
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
+        if (threadIdx.x == 64) dbg_mark(p, 4);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16);
 
         // ---- split-K rendezvous
-        const bool split = p.splits > 1;
         const int64_t tile_elems = static_cast<int64_t>(kBlockM) * BLOCK_N;
         const int64_t tile_id = static_cast<int64_t>(blockIdx.y) * gridDim.x + blockIdx.x;
         const int64_t n_tiles_total = static_cast<int64_t>(gridDim.x) * gridDim.y;
@@ -199,6 +269,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool last = *reinterpret_cast<volatile uint32_t*>(tmem_slot) != 0u;
             if (!last) goto epilogue_done;
             __threadfence();
+            load_res(0, rcur);
         }
         // accumulator chunk loader: TMEM (single CTA per tile) or the fixed-order sum of the split partials
         auto load_acc = [&](int c0, uint32_t(&v)[32]) {
@@ -223,7 +294,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         };
 
-        if (ep.act == IMAGD_ACT_GEGLU) {
+        if constexpr (LINEAR) {
+            constexpr int NCH = BLOCK_N / 32;
+            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldd + col_base;
+            uint32_t v[2][32];
+            if (!split) tmem_ld32(taddr, v[0]);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int c0 = ch * 32;
+                uint32_t(&vc)[32] = v[ch & 1];
+                if (!split) {
+                    tmem_ld_wait_dep(vc);
+                    if (ch + 1 < NCH) tmem_ld32(taddr + c0 + 32, v[(ch + 1) & 1]);  // next chunk in flight
+                } else {
+                    load_acc(c0, vc);
+                }
+                uint4 rnext[4];
+                if (ch + 1 < NCH) load_res(c0 + 32, rnext);
+                if (row_ok && col_base + c0 < p.N) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int cl = c0 + g * 8;  // tile-local column
+                        float f[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = alpha * __uint_as_float(vc[g * 8 + j]);
+                        {
+                            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cl);
+                            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + cl + 4);
+                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                        }
+                        {
+                            const float4 b0 = *reinterpret_cast<const float4*>(s_rowvec + cl);
+                            const float4 b1 = *reinterpret_cast<const float4*>(s_rowvec + cl + 4);
+                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                        }
+                        if (rowvec && col_base + cl < p.N) {  // rare: the tile spans several samples (deep levels)
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(rowvec + col_base + cl));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(rowvec + col_base + cl + 4));
+                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                        }
+                        const uint4 rv = rcur[g];  // zeros when there is no residual
+                        f[0] += bf16lo(rv.x); f[1] += bf16hi(rv.x); f[2] += bf16lo(rv.y); f[3] += bf16hi(rv.y);
+                        f[4] += bf16lo(rv.z); f[5] += bf16hi(rv.z); f[6] += bf16lo(rv.w); f[7] += bf16hi(rv.w);
+                        if (col_base + cl < p.N)
+                            *reinterpret_cast<uint4*>(orow + cl) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                                            pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+            }
+        } else if (ep.act == IMAGD_ACT_GEGLU) {
             // tile = [64 value | 64 gate]; output columns n_blk*64 + [0, 64)
             if constexpr (BLOCK_N == 128) {
 #pragma unroll 1
@@ -240,10 +364,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             float a0 = alpha * __uint_as_float(va[j]), a1 = alpha * __uint_as_float(va[j + 1]);
                             float g0 = alpha * __uint_as_float(vg[j]), g1 = alpha * __uint_as_float(vg[j + 1]);
                             if (ep.bias) {
-                                a0 += __ldg(ep.bias + pcol + j);
-                                a1 += __ldg(ep.bias + pcol + j + 1);
-                                g0 += __ldg(ep.bias + pcol + 64 + j);
-                                g1 += __ldg(ep.bias + pcol + 64 + j + 1);
+                                const float2 ba = *reinterpret_cast<const float2*>(s_bias + c0 + j);
+                                const float2 bg = *reinterpret_cast<const float2*>(s_bias + 64 + c0 + j);
+                                a0 += ba.x;
+                                a1 += ba.y;
+                                g0 += bg.x;
+                                g1 += bg.y;
                             }
                             packed[j / 2] = pack_bf16x2(a0 * gelu_erf(g0), a1 * gelu_erf(g1));
                         }
@@ -259,8 +385,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
                 uint32_t v[32];
                 load_acc(c0, v);
-                const int col = n_blk * BLOCK_N + c0;
-                if (!row_ok || col >= p.N) continue;
+                uint4 rnext[4];
+                if (c0 + 32 < BLOCK_N) load_res(c0 + 32, rnext);  // in flight while this chunk is processed
+                const int col = col_base + c0;
+                if (row_ok && col < p.N) {
+                // row vector fallback (tile spans several samples): all of the chunk's loads issued together
+                float4 rvv[8];
+                if (rowvec) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        rvv[q] = (col + q * 4 < p.N) ? __ldg(reinterpret_cast<const float4*>(rowvec + col + q * 4))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 // columns are handled in groups of 8 (N % 8 == 0 is enforced on the host)
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
@@ -270,14 +406,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 8; ++j) f[j] = alpha * __uint_as_float(v[g * 8 + j]);
                     if (ep.bias) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + cg));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + cg + 4));
+                        const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0 + g * 8);
+                        const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c0 + g * 8 + 4);
                         f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                         f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                     }
-                    if (rowvec) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(rowvec + cg));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(rowvec + cg + 4));
+                    if (rowvec_shared) {
+                        const float4 b0 = *reinterpret_cast<const float4*>(s_rowvec + c0 + g * 8);
+                        const float4 b1 = *reinterpret_cast<const float4*>(s_rowvec + c0 + g * 8 + 4);
+                        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                        f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                    } else if (rowvec) {
+                        const float4 b0 = rvv[2 * g], b1 = rvv[2 * g + 1];
                         f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                         f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                     }
@@ -289,7 +429,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
                     }
                     if (res) {
-                        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res + cg));
+                        const uint4 rv = rcur[g];
                         f[0] += bf16lo(rv.x); f[1] += bf16hi(rv.x); f[2] += bf16lo(rv.y); f[3] += bf16hi(rv.y);
                         f[4] += bf16lo(rv.z); f[5] += bf16hi(rv.z); f[6] += bf16lo(rv.w); f[7] += bf16hi(rv.w);
                     }
@@ -303,11 +443,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                           pack_bf16x2(f[6], f[7]));
                     }
                 }
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
             }
         }
     }
 
 epilogue_done:
+    if (threadIdx.x == 64) dbg_mark(p, 5);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols_for(BLOCK_N));
@@ -401,24 +545,33 @@ static GemmCfg choose_cfg(int m_tiles, int N, int kb_total, bool geglu) {
     return {bn, deep ? deep_stages(bn) : shallow_stages(bn), splits};
 }
 
-template <int BLOCK_N, int STAGES>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles,
-                       cudaStream_t stream) {
+template <int BLOCK_N, int STAGES, bool LINEAR>
+static int launch_gemm_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles,
+                            cudaStream_t stream) {
     using L = GemmSmem<BLOCK_N, STAGES>;
     static bool attr_set = false;
     if (!attr_set) {
-        IMAGD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        L::kTotal));
+        IMAGD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, STAGES, LINEAR>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
         attr_set = true;
     }
     const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
     dim3 grid(m_tiles, n_tiles, p.splits);
-    IMAGD_CUDA(launch_pdl(gemm_tc_kernel<BLOCK_N, STAGES>, grid, dim3(192), L::kTotal, stream, tmA, tmB, p));
+    IMAGD_CUDA(launch_pdl(gemm_tc_kernel<BLOCK_N, STAGES, LINEAR>, grid, dim3(192), L::kTotal, stream, tmA, tmB, p));
     return IMAGD_OK;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles,
+                       cudaStream_t stream) {
+    const bool linear = p.ep.act == IMAGD_ACT_NONE && !p.ep.out_fp32;
+    return linear ? launch_gemm_impl<BLOCK_N, STAGES, true>(tmA, tmB, p, m_tiles, stream)
+                  : launch_gemm_impl<BLOCK_N, STAGES, false>(tmA, tmB, p, m_tiles, stream);
 }
 
 static int g_force_bn = 0, g_force_stages = 0, g_force_splits = 0;  // test hooks (imagd_gemm_debug_force)
 static int g_log_on = 0;
+static unsigned long long* g_dbg_timeline = nullptr;  // imagd_gemm_debug_timeline
 static std::vector<std::string> g_log;  // unique problem keys seen while logging (tools/gemm_sweep.py)
 
 static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int Cin, int taps, const void* Wt,
@@ -482,6 +635,7 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
     p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
     p.ws = nullptr;
     p.counters = nullptr;
+    p.dbg = g_dbg_timeline;
     if (p.splits > 1) {
         int rc = ensure_scratch(&p.ws, &p.counters);
         if (rc != IMAGD_OK) return rc;
@@ -556,6 +710,11 @@ int imagd_gemm_debug_log(int enable, char* out, int out_bytes) {
         memcpy(out, all.c_str(), all.size() + 1);
     }
     return static_cast<int>(imagd::g_log.size());
+}
+
+int imagd_gemm_debug_timeline(void* device_buf) {
+    imagd::g_dbg_timeline = static_cast<unsigned long long*>(device_buf);
+    return IMAGD_OK;
 }
 
 int imagd_conv3x3_bf16(const void* X, int64_t ldx, int NB, int H, int W, int Cin, const void* Wt, void* Y, int64_t ldy,

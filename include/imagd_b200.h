@@ -68,6 +68,10 @@ int imagd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
  * the state; when `out` is given the recorded lines are copied there. Returns the number of lines. */
 int imagd_gemm_debug_force(int block_n, int stages, int splits);
 int imagd_gemm_debug_log(int enable, char* out, int out_bytes);
+/* Profiling hook: while `device_buf` is non-NULL every GEMM/conv CTA writes 8 x u64 at device_buf[cta_linear * 8]:
+ * clock64 at {kernel entry, prologue done, first operand tile landed, last MMA issued, accumulator ready, epilogue done},
+ * then %globaltimer at entry and %smid. The caller sizes the buffer for the largest grid. NULL switches it off. */
+int imagd_gemm_debug_timeline(void* device_buf);
 
 /* Y[n,y,x,:] = sum_{ky,kx} X[n,y+ky-1,x+kx-1,:] * Wt[:, (ky*3+kx)*Cin : +Cin]^T  (stride 1, zero pad 1) as an
  * implicit GEMM on tcgen05: the 9 shifted activation views are fetched by TMA with out-of-bounds zero fill.

@@ -42,7 +42,7 @@ def build_pair(dev, seed=0, with_ref=True):
     return o.to(dev).eval(), p.to(dev).eval()
 
 
-@pytest.mark.parametrize("hw", [(32, 32), (64, 64)])
+@pytest.mark.parametrize("hw", [(32, 32), (64, 64), (96, 72)])  # 256^2, 512^2 (the metric), 768x576 (configs[3])
 @torch.no_grad()
 def test_unet_garment_and_cfg_batch(cuda_device, hw):
     dev = cuda_device
