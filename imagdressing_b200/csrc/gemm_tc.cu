@@ -353,8 +353,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
                 for (int c0 = 0; c0 < 64; c0 += 32) {
                     uint32_t va[32], vg[32];
-                    load_acc(c0, va);
-                    load_acc(64 + c0, vg);
+                    if (!split) {  // both halves in flight, one wait
+                        tmem_ld32(taddr + c0, va);
+                        tmem_ld32(taddr + 64 + c0, vg);
+                        tmem_ld_wait();
+                    } else {
+                        load_acc(c0, va);
+                        load_acc(64 + c0, vg);
+                    }
                     const int pcol = n_blk * 128 + c0;  // packed column of value; gate at +64
                     const int ocol = n_blk * 64 + c0;
                     if (row_ok && pcol < p.N) {

@@ -1,5 +1,7 @@
 // GroupNorm (+SiLU) and LayerNorm over token-major bf16 activations. HBM/L2-bound: every element is read with
 // 128-bit loads, statistics are fp32 with fixed-order (bit-reproducible) reductions.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -11,10 +13,29 @@ constexpr int kGnCounters = 1024;  // max samples per call
 
 // Chunks (CTAs) per sample. Every CTA of the launch must be resident at once (the kernel contains a sample-wide
 // rendezvous), so the grid is capped at 2 CTAs per SM — the occupancy __launch_bounds__(512, 2) guarantees.
-__host__ __device__ inline int gn_chunks(int HW, int NB) {
-    int c = (HW + 31) / 32;
+static int gn_pixels_per_chunk() {  // tuning knob (IMAGD_GN_PX, default 16: B=1 step 6.14 -> 6.00 ms vs 32, B=8 neutral): smaller = more, shorter CTAs per sample
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("IMAGD_GN_PX");
+        v = e ? atoi(e) : 16;
+        if (v < 4 || v > 256) v = 16;
+    }
+    return v;
+}
+static int gn_max_chunks() {  // IMAGD_GN_MAXCHUNKS, default 64
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("IMAGD_GN_MAXCHUNKS");
+        v = e ? atoi(e) : 64;
+        if (v < 1 || v > 148) v = 64;
+    }
+    return v;
+}
+inline int gn_chunks(int HW, int NB) {
+    const int px = gn_pixels_per_chunk();
+    int c = (HW + px - 1) / px;
     const int cap = (148 * 2) / (NB > 0 ? NB : 1);
-    if (c > 64) c = 64;
+    if (c > gn_max_chunks()) c = gn_max_chunks();
     if (c > cap) c = cap;
     return c < 1 ? 1 : c;
 }
