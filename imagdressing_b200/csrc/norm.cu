@@ -13,7 +13,8 @@ constexpr int kGnCounters = 1024;  // max samples per call
 
 // Chunks (CTAs) per sample. Every CTA of the launch must be resident at once (the kernel contains a sample-wide
 // rendezvous), so the grid is capped at 2 CTAs per SM — the occupancy __launch_bounds__(512, 2) guarantees.
-static int gn_pixels_per_chunk() {  // tuning knob (IMAGD_GN_PX, default 16: B=1 step 6.14 -> 6.00 ms vs 32, B=8 neutral): smaller = more, shorter CTAs per sample
+// Tuning knob IMAGD_GN_PX (default 16: B=1 step 6.14 -> 6.00 ms vs 32, B=8 neutral): smaller = more, shorter CTAs.
+static int gn_pixels_per_chunk() {
     static int v = 0;
     if (v == 0) {
         const char* e = getenv("IMAGD_GN_PX");
