@@ -71,11 +71,17 @@ __host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 64 ? 64 : (
 
 // LINEAR = the epilogue has no activation and writes bf16 (every conv and most linears of the UNet): straight-line,
 // branch-free column loop with the next TMEM chunk and the next residual chunk in flight. !LINEAR = the generic epilogue
-// (SiLU / GELU / GEGLU / fp32 output).
-template <int BLOCK_N, int STAGES, bool LINEAR>
+// (SiLU / GELU / GEGLU / fp32 output). EPI: 0 generic, 1 LINEAR, 2 LINEAR with the output row staged in the (idle)
+// operand ring and written by one bulk copy per row instead of 16-byte stores (opt-in: IMAGD_GEMM_BULK_STORE=1;
+// written at the end of round 1, parity-tested but not yet tuned / made the default).
+template <int BLOCK_N, int STAGES, int EPI>
 __global__ void __launch_bounds__(192, (GemmSmem<BLOCK_N, STAGES>::kTotal <= 112 * 1024) ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     using L = GemmSmem<BLOCK_N, STAGES>;
+    constexpr bool LINEAR = EPI != 0;
+    constexpr bool BULK = EPI == 2;
+    constexpr int kRowStage = BLOCK_N * 2 + 16;  // staged output row stride (bytes): +16 keeps 8 rows on 8 bank groups
+    static_assert(!BULK || 128 * kRowStage <= L::kBarOffset, "output staging must fit in the operand ring");
     extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
         printf("imagd: dynamic shared memory base %u is not 1024-byte aligned\n", smem_u32(smem));
@@ -339,13 +345,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint4 rv = rcur[g];  // zeros when there is no residual
                         f[0] += bf16lo(rv.x); f[1] += bf16hi(rv.x); f[2] += bf16lo(rv.y); f[3] += bf16hi(rv.y);
                         f[4] += bf16lo(rv.z); f[5] += bf16hi(rv.z); f[6] += bf16lo(rv.w); f[7] += bf16hi(rv.w);
-                        if (col_base + cl < p.N)
-                            *reinterpret_cast<uint4*>(orow + cl) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                                                            pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                        const uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                   pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                        if constexpr (BULK) {
+                            *reinterpret_cast<uint4*>(smem + r * kRowStage + cl * 2) = o;  // ring is idle: all MMAs retired
+                        } else {
+                            if (col_base + cl < p.N) *reinterpret_cast<uint4*>(orow + cl) = o;
+                        }
                     }
                 }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+            }
+            if constexpr (BULK) {
+                // each thread ships its own row: generic-proxy writes -> async-proxy read needs the proxy fence only
+                fence_proxy_async_smem();
+                const int valid = min(BLOCK_N, p.N - col_base);
+                if (row_ok && valid > 0) bulk_store_s2g(orow, smem_u32(smem + r * kRowStage), static_cast<uint32_t>(valid) * 2u);
+                bulk_commit();
+                bulk_wait_read0();  // the staging bytes must stay valid until the copy engine has read them
             }
         } else if (ep.act == IMAGD_ACT_GEGLU) {
             // tile = [64 value | 64 gate]; output columns n_blk*64 + [0, 64)
@@ -551,19 +569,19 @@ static GemmCfg choose_cfg(int m_tiles, int N, int kb_total, bool geglu) {
     return {bn, deep ? deep_stages(bn) : shallow_stages(bn), splits};
 }
 
-template <int BLOCK_N, int STAGES, bool LINEAR>
+template <int BLOCK_N, int STAGES, int EPI>
 static int launch_gemm_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles,
                             cudaStream_t stream) {
     using L = GemmSmem<BLOCK_N, STAGES>;
     static bool attr_set = false;
     if (!attr_set) {
-        IMAGD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, STAGES, LINEAR>,
+        IMAGD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, STAGES, EPI>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
         attr_set = true;
     }
     const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
     dim3 grid(m_tiles, n_tiles, p.splits);
-    IMAGD_CUDA(launch_pdl(gemm_tc_kernel<BLOCK_N, STAGES, LINEAR>, grid, dim3(192), L::kTotal, stream, tmA, tmB, p));
+    IMAGD_CUDA(launch_pdl(gemm_tc_kernel<BLOCK_N, STAGES, EPI>, grid, dim3(192), L::kTotal, stream, tmA, tmB, p));
     return IMAGD_OK;
 }
 
@@ -571,8 +589,14 @@ template <int BLOCK_N, int STAGES>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles,
                        cudaStream_t stream) {
     const bool linear = p.ep.act == IMAGD_ACT_NONE && !p.ep.out_fp32;
-    return linear ? launch_gemm_impl<BLOCK_N, STAGES, true>(tmA, tmB, p, m_tiles, stream)
-                  : launch_gemm_impl<BLOCK_N, STAGES, false>(tmA, tmB, p, m_tiles, stream);
+    static int bulk = -1;
+    if (bulk < 0) {
+        const char* e = getenv("IMAGD_GEMM_BULK_STORE");  // opt-in experiment (see the kernel comment)
+        bulk = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!linear) return launch_gemm_impl<BLOCK_N, STAGES, 0>(tmA, tmB, p, m_tiles, stream);
+    return bulk ? launch_gemm_impl<BLOCK_N, STAGES, 2>(tmA, tmB, p, m_tiles, stream)
+                : launch_gemm_impl<BLOCK_N, STAGES, 1>(tmA, tmB, p, m_tiles, stream);
 }
 
 static int g_force_bn = 0, g_force_stages = 0, g_force_splits = 0;  // test hooks (imagd_gemm_debug_force)
