@@ -421,12 +421,7 @@ static int make_head_tmap(CUtensorMap* tm, const void* base, int64_t ld, int hd,
 template <int HD_MMA, int NATOM, int KV_STAGES>
 static int launch_attn(const CUtensorMap* tms, const AttnParams& p, cudaStream_t stream) {
     using C = AttnCfg<HD_MMA, NATOM, KV_STAGES>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        IMAGD_CUDA(cudaFuncSetAttribute(attention_tc_kernel<HD_MMA, NATOM, KV_STAGES>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
-        attr_set = true;
-    }
+    IMAGD_SET_MAX_SMEM((attention_tc_kernel<HD_MMA, NATOM, KV_STAGES>), C::kTotal);
     dim3 grid((p.Lq + 127) / 128, p.heads, p.B);
     IMAGD_CUDA(launch_pdl(attention_tc_kernel<HD_MMA, NATOM, KV_STAGES>, grid, dim3(320), C::kTotal, stream, tms[0],
                           tms[1], tms[2], tms[3], tms[4], p));

@@ -4,6 +4,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cuda.h>
+#include <atomic>
+
 #include <cuda_runtime.h>
 
 #include "../../include/imagd_b200.h"
@@ -25,6 +27,19 @@ int cuda_fail(cudaError_t e, const char* what);
     do {                                                   \
         cudaError_t e__ = (call);                          \
         if (e__ != cudaSuccess) return ::imagd::cuda_fail(e__, #call); \
+    } while (0)
+
+// Opt a kernel into more than 48 KB of dynamic shared memory, once per device (the attribute lives in the device's
+// context; one process may drive several GPUs) and safely from several host threads.
+#define IMAGD_SET_MAX_SMEM(kernel, bytes)                                                               \
+    do {                                                                                                \
+        static std::atomic<bool> done__[16];                                                            \
+        int dev__ = 0;                                                                                  \
+        IMAGD_CUDA(cudaGetDevice(&dev__));                                                              \
+        if (dev__ < 0 || dev__ >= 16 || !done__[dev__].load(std::memory_order_acquire)) {               \
+            IMAGD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
+            if (dev__ >= 0 && dev__ < 16) done__[dev__].store(true, std::memory_order_release);         \
+        }                                                                                               \
     } while (0)
 
 #define IMAGD_LAUNCH_CHECK(name)                               \

@@ -426,11 +426,7 @@ int imagd_conv3x3_direct_bf16(const void* x, int NB, int H, int W, int Cin, cons
     if (Cin == 4 && Cout % 64 == 0 && Cout <= 640 && stride == 1 && act == IMAGD_ACT_NONE && !out_nchw_f32) {
         const int64_t pixels = static_cast<int64_t>(NB) * H * W;
         const size_t smem = static_cast<size_t>(Cout) * 38 * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
-            IMAGD_CUDA(cudaFuncSetAttribute(conv3x3_cin4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 640 * 38 * 4));
-            attr_set = true;
-        }
+        IMAGD_SET_MAX_SMEM(conv3x3_cin4_kernel, 640 * 38 * 4);
         IMAGD_CUDA(launch_pdl(conv3x3_cin4_kernel, dim3(static_cast<int>((pixels + 31) / 32)), dim3(256), smem, st, 
             reinterpret_cast<const __nv_bfloat16*>(x), NB, H, W, reinterpret_cast<const __nv_bfloat16*>(w), bias,
             reinterpret_cast<__nv_bfloat16*>(y), Cout, reinterpret_cast<const __nv_bfloat16*>(add_nhwc)));

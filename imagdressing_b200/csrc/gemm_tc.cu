@@ -14,6 +14,7 @@
 // Two CTAs fit per SM (96 KB smem, <=128 TMEM columns each) so one CTA's epilogue overlaps the other's mainloop.
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -510,13 +511,24 @@ constexpr int kMaxTilesSplit = 1 << 16;
 static float* g_ws[16] = {nullptr};
 static unsigned int* g_counters[16] = {nullptr};
 
-static int ensure_scratch(float** ws, unsigned int** counters) {
+static std::mutex g_scratch_mu;
+
+// Library-owned split-K scratch, one per device, allocated on first use. It is shared by every split-K launch on
+// that device: callers must not run split-K GEMMs concurrently on several streams of one device (documented in
+// include/imagd_b200.h). The first use must not happen inside a stream capture (cudaMalloc is illegal there).
+static int ensure_scratch(float** ws, unsigned int** counters, cudaStream_t stream) {
     int dev = 0;
     IMAGD_CUDA(cudaGetDevice(&dev));
     IMAGD_CHECK_ARG(dev >= 0 && dev < 16, "gemm: device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
     if (!g_ws[dev]) {
         cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-        cudaStreamIsCapturing(cudaStreamLegacy, &st);
+        IMAGD_CUDA(cudaStreamIsCapturing(stream, &st));
+        if (st != cudaStreamCaptureStatusNone) {
+            set_error("gemm: the split-K scratch is allocated on first use, which cannot happen inside a CUDA graph "
+                      "capture; run the same call once eagerly before capturing");
+            return IMAGD_ERR_CUDA;
+        }
         IMAGD_CUDA(cudaMalloc(&g_ws[dev], kWsBytes));
         IMAGD_CUDA(cudaMalloc(&g_counters[dev], kMaxTilesSplit * sizeof(unsigned int)));
         IMAGD_CUDA(cudaMemset(g_counters[dev], 0, kMaxTilesSplit * sizeof(unsigned int)));
@@ -573,12 +585,7 @@ template <int BLOCK_N, int STAGES, int EPI>
 static int launch_gemm_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles,
                             cudaStream_t stream) {
     using L = GemmSmem<BLOCK_N, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        IMAGD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, STAGES, EPI>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-        attr_set = true;
-    }
+    IMAGD_SET_MAX_SMEM((gemm_tc_kernel<BLOCK_N, STAGES, EPI>), L::kTotal);
     const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
     dim3 grid(m_tiles, n_tiles, p.splits);
     IMAGD_CUDA(launch_pdl(gemm_tc_kernel<BLOCK_N, STAGES, EPI>, grid, dim3(192), L::kTotal, stream, tmA, tmB, p));
@@ -667,7 +674,7 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
     p.counters = nullptr;
     p.dbg = g_dbg_timeline;
     if (p.splits > 1) {
-        int rc = ensure_scratch(&p.ws, &p.counters);
+        int rc = ensure_scratch(&p.ws, &p.counters, stream);
         if (rc != IMAGD_OK) return rc;
         const int64_t n_tiles = (N + cfg.bn - 1) / cfg.bn;
         IMAGD_CHECK_ARG(m_tiles64 * n_tiles <= kMaxTilesSplit &&

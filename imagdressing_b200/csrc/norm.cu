@@ -345,11 +345,8 @@ int imagd_groupnorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int N
     IMAGD_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y), "groupnorm: alignment");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int chunks = gn_chunks(HW, NB);
-    static bool attr_set = false;
-    if (!attr_set) {  // 33 KB static + up to 20 KB dynamic (gamma | beta) exceeds the 48 KB default
-        IMAGD_CUDA(cudaFuncSetAttribute(groupnorm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_set = true;
-    }
+    // 33 KB static + up to 20 KB dynamic (gamma | beta) exceeds the 48 KB default
+    IMAGD_SET_MAX_SMEM(groupnorm_fused_kernel, 64 * 1024);
     IMAGD_CUDA(launch_pdl(groupnorm_fused_kernel, dim3(chunks, NB), dim3(kGnThreads), 2 * C * sizeof(float), st,
                           reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, HW, C,
                           groups, chunks, reinterpret_cast<float*>(ws) + kGnCounters, gamma, beta, eps, fuse_silu));

@@ -57,7 +57,11 @@ typedef struct imagd_epilogue {
  * Replaces every nn.Linear / 1x1 conv on the path: attn.to_q/to_k/to_v/to_out, to_k_ref/to_v_ref
  * (adapter/attention_processor.py:568-615,598-601), to_k_ip/to_v_ip (:841-842), Transformer2DModel proj_in/out,
  * FeedForward (diffusers-0.24), Resampler linears (adapter/resampler.py:13-20,45-47,186-188).
- * K % 8 == 0, lda/ldw % 8 == 0, pointers 16-byte aligned. */
+ * K % 8 == 0, lda/ldw % 8 == 0, pointers 16-byte aligned.
+ * Threading: every call only enqueues work on `stream`; it is safe from several host threads. One exception: problems
+ * with few output tiles and a long K run as a deterministic split-K whose fp32 partials live in a library-owned,
+ * per-device scratch (96 MB, allocated at the first such call - which therefore must not happen inside a stream
+ * capture; run the call once eagerly first). Split-K launches of ONE device must be ordered on one stream. */
 int imagd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* D, int64_t ldd, int M, int N,
                     int K, const imagd_epilogue* ep, imagd_stream stream);
 
