@@ -14,6 +14,7 @@ processor registration). Architecture: SURVEY.md Appendix A (diffusers 0.24.0, r
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -39,6 +40,20 @@ class FrozenConfig(dict):
             return self[k]
         except KeyError as e:
             raise AttributeError(k) from e
+
+
+@contextlib.contextmanager
+def skip_default_init():
+    """Construct modules without running nn.Linear / nn.Conv2d default initialisation (kaiming_uniform over 860 M
+    parameters costs ~40 s of CPU per UNet). Only for call sites that overwrite EVERY parameter right after —
+    `load_state_dict`, `init_synthetic_`, `init_synthetic_fast_`, `from_pretrained`; parameters are torch.empty until then."""
+    saved = (nn.Linear.reset_parameters, nn.Conv2d.reset_parameters)
+    nn.Linear.reset_parameters = lambda self: None
+    nn.Conv2d.reset_parameters = lambda self: None
+    try:
+        yield
+    finally:
+        nn.Linear.reset_parameters, nn.Conv2d.reset_parameters = saved
 
 
 def _f32(p: torch.Tensor) -> torch.Tensor:

@@ -140,6 +140,24 @@ def test_synthetic_init_is_identical_for_product_and_oracle():
     assert not torch.equal(q.state_dict()["conv_in.weight"], sp["conv_in.weight"])
 
 
+def test_skip_default_init_gives_the_same_weights_once_initialised():
+    from imagdressing_b200 import modeling
+    from oracle import unet as ou
+
+    cfg = dict(block_out_channels=(32, 64, 64, 64), cross_attention_dim=64, attention_head_dim=8, norm_num_groups=8)
+    saved = torch.nn.Linear.reset_parameters
+    with modeling.skip_default_init():
+        p, o = modeling.UNet2DConditionModel(**cfg), ou.UNet2DConditionModel(**cfg)
+    assert torch.nn.Linear.reset_parameters is saved  # restored
+    q = modeling.UNet2DConditionModel(**cfg)
+    for m in (p, o, q):
+        (ou.init_synthetic_ if m is o else modeling.init_synthetic_)(m, 3)
+    ref = q.state_dict()
+    assert all(torch.equal(v, ref[k]) for k, v in p.state_dict().items())
+    assert all(torch.equal(v, ref[k]) for k, v in o.state_dict().items())
+    assert all(torch.isfinite(v).all() for v in p.state_dict().values())
+
+
 def test_sharding_helpers():
     from imagdressing_b200.parallel import sample_seeds, shard_range
 
