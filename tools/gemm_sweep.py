@@ -3,7 +3,9 @@ denoising step and the ControlNet issue at the given per-GPU batch sizes, time e
 variant on each (L2 flushed between launches, CUDA events, median of 5) and write the winners to
 gpurun_out/gemm_tuning.json / .inc (copy the .inc to imagdressing_b200/csrc/gemm_tuning.inc and rebuild).
 
-    BATCHES=1,2,8 python tools/gemm_sweep.py
+    BATCHES=1,2,8 python tools/gemm_sweep.py          # EPI=1 (default): realistic epilogues — bias + residual on the
+                                                       # linears, bias + time-embedding row vector on the convs, bias on
+                                                       # GEGLU; EPI=0: bare products (how the round-1 table was swept)
 """
 import ctypes
 import json
@@ -22,6 +24,7 @@ dev = torch.device("cuda:0")
 lib = _lib.load()
 flush = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.int32)
 BATCHES = [int(v) for v in os.environ.get("BATCHES", "1").split(",")]
+EPI = os.environ.get("EPI", "1") == "1"
 HW = int(os.environ.get("HW", "64"))
 bench.HW = HW
 
@@ -70,14 +73,18 @@ for (taps, NB, H, W, Cin, N, geglu, m_tiles, kb_total, out_fp32) in sorted(set(k
         x = torch.randn(NB, H, W, Cin, device=dev).bfloat16()
         w = (torch.randn(N, 9 * Cin, device=dev) * 0.02).bfloat16()
         y = torch.empty(NB, H, W, N, device=dev, dtype=torch.bfloat16)
-        fn = lambda: ops.conv3x3(x, w, out=y)
+        bias = torch.randn(N, device=dev) if EPI else None
+        temb = torch.randn(NB, N, device=dev) if EPI else None
+        fn = lambda: ops.conv3x3(x, w, out=y, bias=bias, rowvec=temb)
         flops = 2.0 * NB * H * W * 9 * Cin * N
     else:
         x = torch.randn(W, Cin, device=dev).bfloat16()
         w = (torch.randn(N, Cin, device=dev) * 0.02).bfloat16()
         y = torch.empty(W, N // 2 if geglu else N, device=dev, dtype=torch.float32 if out_fp32 else torch.bfloat16)
         act = ops.ACT_GEGLU if geglu else ops.ACT_NONE
-        fn = lambda: ops.gemm(x, w, out=y, act=act, out_fp32=bool(out_fp32))
+        bias = torch.randn(N, device=dev) if EPI else None
+        res = torch.randn(W, N, device=dev).bfloat16() if (EPI and not geglu and not out_fp32) else None
+        fn = lambda: ops.gemm(x, w, out=y, act=act, out_fp32=bool(out_fp32), bias=bias, residual=res)
         flops = 2.0 * W * Cin * N
     row = {}
     for bn in ((128,) if geglu else (64, 128, 160, 256)):
