@@ -257,6 +257,20 @@ def pick_cpu_threads():
     return best
 
 
+class _no_default_init:
+    """Skip torch's default Linear / Conv2d initialisation while the 860 M-parameter oracle is constructed (tens of
+    seconds of CPU); every parameter is overwritten right after."""
+
+    def __enter__(self):
+        nn = torch.nn
+        self.saved = (nn.Linear.reset_parameters, nn.Conv2d.reset_parameters)
+        nn.Linear.reset_parameters = lambda m: None
+        nn.Conv2d.reset_parameters = lambda m: None
+
+    def __exit__(self, *exc):
+        torch.nn.Linear.reset_parameters, torch.nn.Conv2d.reset_parameters = self.saved
+
+
 class CpuOracle:
     """The fp32 oracle (reference processors restated; oracle/unet.py) on the host cores, built once."""
 
@@ -266,7 +280,7 @@ class CpuOracle:
 
         self.threads = threads or pick_cpu_threads()
         torch.set_num_threads(self.threads)
-        with torch.no_grad():
+        with torch.no_grad(), _no_default_init():
             o = ou.UNet2DConditionModel()
             po = {}
             for name in o.attn_processors:
