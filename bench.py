@@ -100,6 +100,20 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ model builders
+class _no_default_init:
+    """Skip torch's default Linear / Conv2d initialisation while the 860 M-parameter models are constructed (tens of
+    seconds of CPU); every parameter is overwritten right after."""
+
+    def __enter__(self):
+        nn = torch.nn
+        self.saved = (nn.Linear.reset_parameters, nn.Conv2d.reset_parameters)
+        nn.Linear.reset_parameters = lambda m: None
+        nn.Conv2d.reset_parameters = lambda m: None
+
+    def __exit__(self, *exc):
+        torch.nn.Linear.reset_parameters, torch.nn.Conv2d.reset_parameters = self.saved
+
+
 def build_product(dev, workload="base"):
     from adapter.attention_processor import (CacheAttnProcessor2_0, CAttnProcessor2_0, LoraRefSAttnProcessor2_0,
                                              LoRAIPAttnProcessor2_0, RefSAttnProcessor2_0)
@@ -112,7 +126,10 @@ def build_product(dev, workload="base"):
     else:
         from dressing_sd.pipelines.IMAGDressing_v1_pipeline_controlnet_inpainting import IMAGDressing_v1
 
-    unet = modeling.UNet2DConditionModel().to(dev, torch.bfloat16)
+    with _no_default_init():  # every parameter is overwritten by init_synthetic_fast_ below
+        unet = modeling.UNet2DConditionModel().to(dev, torch.bfloat16)
+        ref = modeling.UNet2DConditionModel().to(dev, torch.bfloat16)
+        cn = modeling.ControlNetModel().to(dev, torch.bfloat16) if workload != "base" else None
     procs = {}
     for name in unet.attn_processors.keys():  # inference_IMAGdressing.py:70-85
         if name.startswith("mid_block"):
@@ -129,7 +146,6 @@ def build_product(dev, workload="base"):
                            else CAttnProcessor2_0(name, hidden, unet.config.cross_attention_dim))
     unet.set_attn_processor(procs)
     unet.to(dev, torch.bfloat16)
-    ref = modeling.UNet2DConditionModel().to(dev, torch.bfloat16)
     ref.set_attn_processor({n: CacheAttnProcessor2_0() for n in ref.attn_processors.keys()})  # :90-94
     modeling.init_synthetic_fast_(unet, 0)
     modeling.init_synthetic_fast_(ref, 1)
@@ -137,7 +153,6 @@ def build_product(dev, workload="base"):
                           clip_sample=False, set_alpha_to_one=False, steps_offset=1)  # :119-127
     extra = {}
     if workload != "base":
-        cn = modeling.ControlNetModel().to(dev, torch.bfloat16)
         modeling.init_synthetic_fast_(cn, 2)
         extra["controlnet"] = cn
         if workload == "ipa_controlnet":
@@ -255,20 +270,6 @@ def pick_cpu_threads():
         if dt < best_t:
             best, best_t = n, dt
     return best
-
-
-class _no_default_init:
-    """Skip torch's default Linear / Conv2d initialisation while the 860 M-parameter oracle is constructed (tens of
-    seconds of CPU); every parameter is overwritten right after."""
-
-    def __enter__(self):
-        nn = torch.nn
-        self.saved = (nn.Linear.reset_parameters, nn.Conv2d.reset_parameters)
-        nn.Linear.reset_parameters = lambda m: None
-        nn.Conv2d.reset_parameters = lambda m: None
-
-    def __exit__(self, *exc):
-        torch.nn.Linear.reset_parameters, torch.nn.Conv2d.reset_parameters = self.saved
 
 
 class CpuOracle:
