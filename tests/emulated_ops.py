@@ -1,0 +1,164 @@
+"""Torch emulations of what the C-ABI kernels compute (bf16 storage, fp32 arithmetic), with the SAME Python signatures
+as imagdressing_b200.ops. TEST INFRASTRUCTURE for the CPU suite only: `install(monkeypatch)` swaps them in so the whole
+host mirror (modeling.py / processors.py / adapter/*) can be executed — and compared with the oracle — without a GPU.
+This checks the host WIRING (weight packing, layouts, fused-epilogue arguments, processor handshake, CFG batching); the
+kernels themselves are checked on the GPU against the same oracle."""
+import math
+
+import torch
+import torch.nn.functional as F
+
+BF = torch.bfloat16
+ACT_NONE, ACT_GEGLU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
+
+
+def _act(y, act):
+    if act == ACT_SILU:
+        return F.silu(y)
+    if act == ACT_GELU:
+        return F.gelu(y)
+    return y
+
+
+def _store(y, out):
+    if out is not None:
+        out.copy_(y.reshape(out.shape))
+        return out
+    return y
+
+
+def gemm(a, w, *, out=None, bias=None, rowvec=None, rows_per_group=0, residual=None, act=ACT_NONE, alpha=1.0,
+         out_fp32=False):
+    lead = a.shape[:-1]
+    y = alpha * (a.reshape(-1, a.shape[-1]).float() @ w.float().T)
+    if bias is not None:
+        y = y + bias.float()[None, :]
+    if rowvec is not None:
+        y = y + rowvec.float()[torch.arange(y.shape[0]) // rows_per_group]
+    if act == ACT_GEGLU:  # packed rows: per 128, 64 value then their 64 gate
+        z = y.view(y.shape[0], -1, 2, 64)
+        y = (z[:, :, 0] * F.gelu(z[:, :, 1])).reshape(y.shape[0], -1)
+    else:
+        y = _act(y, act)
+    if residual is not None:
+        y = y + residual.reshape(-1, residual.shape[-1]).float()
+    y = y.reshape(*lead, y.shape[-1])
+    return _store(y if out_fp32 else y.to(BF), out)
+
+
+def _unpack3x3(w, cin):
+    co = w.shape[0]
+    return w.float().view(co, 3, 3, cin).permute(0, 3, 1, 2)
+
+
+def conv3x3(x, w, *, out=None, bias=None, rowvec=None, residual=None, act=ACT_NONE):
+    NB, H, W, Cin = x.shape
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), _unpack3x3(w, Cin), bias.float() if bias is not None else None, padding=1)
+    if rowvec is not None:
+        y = y + rowvec.float()[:, :, None, None]
+    y = _act(y, act).permute(0, 2, 3, 1)
+    if residual is not None:
+        y = y + residual.float()
+    return _store(y.to(BF).contiguous(), out)
+
+
+def conv3x3_direct(x, w, bias, *, stride=1, act=ACT_NONE, out_nchw_f32=False, add=None, out=None):
+    NB, H, W, Cin = x.shape
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), _unpack3x3(w, Cin), bias.float() if bias is not None else None,
+                 stride=stride, padding=1)
+    y = _act(y, act)
+    if add is not None:
+        y = y + add.float().permute(0, 3, 1, 2)
+    if out_nchw_f32:
+        return _store(y.contiguous(), out)
+    return _store(y.permute(0, 2, 3, 1).to(BF).contiguous(), out)
+
+
+def groupnorm(x, gamma, beta, groups, eps, *, silu, out=None, ws=None):
+    y = F.group_norm(x.float().movedim(-1, 1), groups, gamma, beta, eps)
+    if silu:
+        y = F.silu(y)
+    return _store(y.movedim(1, -1).to(BF).contiguous(), out)
+
+
+def layernorm(x, gamma, beta, eps=1e-5, *, out=None):
+    return _store(F.layer_norm(x.float(), (x.shape[-1],), gamma, beta, eps).to(BF), out)
+
+
+class Stream:
+    def __init__(self, k, v, length, sample_rows=0, broadcast=False, n_query_samples=1 << 30, out_scale=1.0):
+        self.k, self.v, self.length, self.sample_rows = k, v, length, sample_rows or length
+        self.broadcast, self.n_query_samples, self.out_scale = broadcast, n_query_samples, out_scale
+
+
+def kv_stream(k, v, length, **kw):
+    return Stream(k, v, length, **kw)
+
+
+def attention(q, B, Lq, heads, head_dim, s0, s1=None, *, sm_scale=None, out=None):
+    C = heads * head_dim
+    scale = sm_scale if sm_scale is not None else head_dim ** -0.5
+    qf = q[:, :C].float().reshape(B, Lq, heads, head_dim).transpose(1, 2)
+
+    def one(s, b):
+        src = 0 if s.broadcast else b
+        rows = slice(src * s.sample_rows, src * s.sample_rows + s.length)
+        k = s.k[rows, :C].float().reshape(s.length, heads, head_dim).transpose(0, 1)
+        v = s.v[rows, :C].float().reshape(s.length, heads, head_dim).transpose(0, 1)
+        return torch.softmax(qf[b] @ k.transpose(1, 2) * scale, -1) @ v
+
+    rows = []
+    for b in range(B):
+        o = one(s0, b)
+        if s1 is not None and b < s1.n_query_samples:
+            o = o + s1.out_scale * one(s1, b)
+        rows.append(o.transpose(0, 1).reshape(Lq, C))
+    return _store(torch.stack(rows).reshape(B * Lq, C).to(BF), out)
+
+
+def concat_add(a, b=None, *, res_a=None, res_b=None, out=None):
+    add = lambda t, r: t if r is None else (t.float() + r.float()).to(BF)
+    parts = [add(a, res_a)] + ([add(b, res_b)] if b is not None else [])
+    return _store(torch.cat(parts, -1).contiguous(), out)
+
+
+def upsample2x(x):
+    return x.repeat_interleave(2, 1).repeat_interleave(2, 2).contiguous()
+
+
+def im2col3x3_s2(x):
+    NB, H, W, C = x.shape
+    cols = F.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)  # [NB, C*9, L], channel-major (c*9 + tap)
+    cols = cols.view(NB, C, 9, H // 2, W // 2).permute(0, 3, 4, 2, 1)          # -> tap-major (tap*C + c)
+    return cols.reshape(NB, H // 2, W // 2, 9 * C).to(BF).contiguous()
+
+
+def nchw_f32_to_nhwc_bf16(x, cpad=None, *, repeat=1, out=None):
+    NB, C, H, W = x.shape
+    y = x.permute(0, 2, 3, 1)
+    if cpad and cpad > C:
+        y = F.pad(y, (0, cpad - C))
+    return _store(y.repeat(repeat, 1, 1, 1).to(BF).contiguous(), out)
+
+
+def timestep_embedding(timesteps, step_ptr, NB, dim, *, out=None):
+    t = timesteps[int(step_ptr[0])] if step_ptr is not None else timesteps[0]
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    args = t.float() * freqs
+    return _store(torch.cat([torch.cos(args), torch.sin(args)])[None].repeat(NB, 1), out)
+
+
+def linear_small_m(x, w, bias, *, act_in=ACT_NONE, act_out=ACT_NONE, out=None):
+    y = _act(x.float(), act_in) @ w.float().T
+    if bias is not None:
+        y = y + bias.float()
+    return _store(_act(y, act_out), out)
+
+
+def install(monkeypatch):
+    from imagdressing_b200 import ops
+
+    for name in ("gemm", "conv3x3", "conv3x3_direct", "groupnorm", "layernorm", "kv_stream", "attention", "concat_add",
+                 "upsample2x", "im2col3x3_s2", "nchw_f32_to_nhwc_bf16", "timestep_embedding", "linear_small_m"):
+        monkeypatch.setattr(ops, name, globals()[name])
