@@ -156,9 +156,25 @@ def linear_small_m(x, w, bias, *, act_in=ACT_NONE, act_out=ACT_NONE, out=None):
     return _store(_act(y, act_out), out)
 
 
+def cfg_ddim_step(eps_cond, eps_uncond, guidance, latents, coef, step_ptr, *, mask=None, image_latents=None, noise=None,
+                  blend_coef=None):
+    i = int(step_ptr[0])
+    c = coef[i]
+    eps = eps_cond if eps_uncond is None else eps_uncond + guidance * (eps_cond - eps_uncond)
+    x0 = (latents - c[1] * eps) / c[0]
+    new = c[2] * x0 + c[3] * eps
+    if mask is not None:  # inpaint blend with the original latents re-noised to the NEXT timestep (last step: clean)
+        b = blend_coef[i]
+        new = (1 - mask) * (b[0] * image_latents + b[1] * noise) + mask * new
+    latents.copy_(new)
+    step_ptr[0] += 1
+    return latents
+
+
 def install(monkeypatch):
     from imagdressing_b200 import ops
 
     for name in ("gemm", "conv3x3", "conv3x3_direct", "groupnorm", "layernorm", "kv_stream", "attention", "concat_add",
-                 "upsample2x", "im2col3x3_s2", "nchw_f32_to_nhwc_bf16", "timestep_embedding", "linear_small_m"):
+                 "upsample2x", "im2col3x3_s2", "nchw_f32_to_nhwc_bf16", "timestep_embedding", "linear_small_m",
+                 "cfg_ddim_step"):
         monkeypatch.setattr(ops, name, globals()[name])
