@@ -27,7 +27,9 @@ def _worker(rank, world, port, global_batch, out_q):
     # stand-in for the per-rank sampler: a deterministic function of the per-sample seed only
     local = torch.stack([torch.randn(4, 8, 8, generator=torch.Generator().manual_seed(s)) for s in seeds])
     full = gather_latents(local, global_batch)
-    out_q.put((rank, lo, hi, full))
+    # by value (numpy pickles its bytes): a torch tensor would travel as a shared-memory handle that the parent may only
+    # open after this process has already exited (seen as a sporadic FileNotFoundError in the parent)
+    out_q.put((rank, lo, hi, full.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -49,7 +51,7 @@ def test_shard_and_gather_world2(global_batch):
     spans = sorted((lo, hi) for _, lo, hi, _ in res)
     assert spans[0][0] == 0 and spans[-1][1] == global_batch and spans[0][1] == spans[1][0]
     for _, _, _, full in res:
-        assert torch.equal(full, want)  # every rank holds the same, rank-count-invariant result
+        assert torch.equal(torch.from_numpy(full), want)  # every rank holds the same, rank-count-invariant result
 
 
 def test_shard_range_covers_everything():
