@@ -141,3 +141,23 @@ def test_lora_and_ip_processors_match_oracle(emu):
     ref = o(lat, t, text, cross_attention_kwargs={"sa_hidden_states": sa})[0]
     out = p(lat, t, text, cross_attention_kwargs={"sa_hidden_states": sa}, return_dict=False)[0]
     assert rel(out, ref) < 2e-2
+
+
+@torch.no_grad()
+def test_resampler_and_projplus_match_oracle(emu):
+    """adapter/resampler.py drop-ins (Perceiver resampler on the GEMM / LayerNorm / attention wrappers) vs the oracle
+    restatement, same state_dict."""
+    from adapter.resampler import ProjPlusModel, Resampler
+
+    torch.manual_seed(0)
+    kw = dict(dim=64, depth=2, dim_head=16, heads=4, num_queries=6, embedding_dim=48, output_dim=32, ff_mult=2)
+    o, p = op.Resampler(**kw), Resampler(**kw)
+    p.load_state_dict(o.state_dict())
+    x = torch.randn(2, 9, 48)
+    assert rel(p(x), o(x)) < 2e-2
+    kw = dict(cross_attention_dim=64, id_embeddings_dim=32, clip_embeddings_dim=48, num_tokens=4)
+    o2, p2 = op.ProjPlusModel(**kw), ProjPlusModel(**kw)
+    p2.load_state_dict(o2.state_dict())
+    ide, clip = torch.randn(2, 32), torch.randn(2, 9, 48)
+    assert rel(p2(ide, clip, shortcut=False), o2(ide, clip, shortcut=False)) < 2e-2
+    assert rel(p2(ide, clip, shortcut=True, scale=0.5), o2(ide, clip, shortcut=True, scale=0.5)) < 2e-2
