@@ -596,11 +596,15 @@ template <int BLOCK_N, int STAGES>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles,
                        cudaStream_t stream) {
     const bool linear = p.ep.act == IMAGD_ACT_NONE && !p.ep.out_fp32;
-    static int bulk = -1;
-    if (bulk < 0) {
-        const char* e = getenv("IMAGD_GEMM_BULK_STORE");  // opt-in experiment (see the kernel comment)
-        bulk = (e && e[0] == '1') ? 1 : 0;
+    // Bulk row stores pay off once the grid covers the chip more than twice (measured round 1: +3 % at batch 8,
+    // slightly negative for <= 1-wave grids). IMAGD_GEMM_BULK_STORE = 0 / 1 forces it off / on.
+    static int bulk_env = -2;
+    if (bulk_env == -2) {
+        const char* e = getenv("IMAGD_GEMM_BULK_STORE");
+        bulk_env = e ? (e[0] == '1' ? 1 : 0) : -1;
     }
+    const int64_t ctas = static_cast<int64_t>(m_tiles) * ((p.N + BLOCK_N - 1) / BLOCK_N) * p.splits;
+    const bool bulk = bulk_env >= 0 ? bulk_env == 1 : ctas > 2 * 148;
     if (!linear) return launch_gemm_impl<BLOCK_N, STAGES, 0>(tmA, tmB, p, m_tiles, stream);
     return bulk ? launch_gemm_impl<BLOCK_N, STAGES, 2>(tmA, tmB, p, m_tiles, stream)
                 : launch_gemm_impl<BLOCK_N, STAGES, 1>(tmA, tmB, p, m_tiles, stream);
