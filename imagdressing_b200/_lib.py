@@ -29,6 +29,14 @@ class Epilogue(Structure):
         ("ldr", c_int64),
         ("alpha", c_float),
         ("out_fp32", c_int32),
+        ("row_stats_out", c_void_p),
+        ("stats_ld", c_int64),
+        ("row_stats_in", c_void_p),
+        ("stats_in_ld", c_int64),
+        ("stats_parts", c_int32),
+        ("ln_dim", c_int32),
+        ("ln_eps", c_float),
+        ("colsum", c_void_p),
     ]
 
 
@@ -57,6 +65,7 @@ SIGNATURES = {
     "imagd_gemm_debug_force": (c_int, [c_int, c_int, c_int]),
     "imagd_gemm_debug_log": (c_int, [c_int, c_char_p, c_int]),
     "imagd_gemm_debug_timeline": (c_int, [c_void_p]),
+    "imagd_gemm_tile_count_n": (c_int, [c_int, c_int, c_int]),
     "imagd_conv3x3_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_int,
                                    POINTER(Epilogue), c_void_p]),
     "imagd_attention_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int,

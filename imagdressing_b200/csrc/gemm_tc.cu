@@ -75,12 +75,17 @@ __host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 64 ? 64 : (
 // (SiLU / GELU / GEGLU / fp32 output). EPI: 0 generic, 1 LINEAR, 2 LINEAR with the output row staged in the (idle)
 // operand ring and written by one bulk copy per row instead of 16-byte stores (opt-in: IMAGD_GEMM_BULK_STORE=1;
 // written at the end of round 1, parity-tested but not yet tuned / made the default).
-template <int BLOCK_N, int STAGES, int EPI>
+// LNM: LayerNorm folding (r2-prep, see include/imagd_b200.h): 0 off, 1 producer (emit per-row {sum, sum of squares}
+// of the rounded outputs, one slot per N tile), 2 consumer (apply rstd * (alpha * acc - mean * colsum) + bias).
+template <int BLOCK_N, int STAGES, int EPI, int LNM>
 __global__ void __launch_bounds__(192, (GemmSmem<BLOCK_N, STAGES>::kTotal <= 112 * 1024) ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     using L = GemmSmem<BLOCK_N, STAGES>;
     constexpr bool LINEAR = EPI != 0;
     constexpr bool BULK = EPI == 2;
+    constexpr bool LN_PRODUCE = LNM == 1;
+    constexpr bool LN_CONSUME = LNM == 2;
+    static_assert(!LN_PRODUCE || LINEAR, "row statistics are emitted by the LINEAR epilogue only");
     constexpr int kRowStage = BLOCK_N * 2 + 16;  // staged output row stride (bytes): +16 keeps 8 rows on 8 bank groups
     static_assert(!BULK || 128 * kRowStage <= L::kBarOffset, "output staging must fit in the operand ring");
     extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -221,7 +226,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 rowvec = ep.rowvec + (pix / ep.rows_per_group) * ep.rowvec_ld;
             }
         }
-        if (LINEAR && !rowvec_shared) {  // the straight-line loop always adds the staged vectors: absent = zeros
+        if constexpr (LN_CONSUME) {  // the row-vector slot carries the folded weight's column sums instead
+            for (int c = threadIdx.x - 64; c < BLOCK_N; c += 128)
+                s_rowvec[c] = (col_base + c < p.N) ? __ldg(ep.colsum + col_base + c) : 0.f;
+        } else if (LINEAR && !rowvec_shared) {  // the straight-line loop always adds the staged vectors: absent = zeros
             for (int c = threadIdx.x - 64; c < BLOCK_N; c += 128) s_rowvec[c] = 0.f;
         }
         if (ep.bias != nullptr) {
@@ -240,6 +248,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         };
         if (!split) load_res(0, rcur);
+        float ln_mean = 0.f, ln_rstd = 0.f;
+        if constexpr (LN_CONSUME) {
+            if (row_ok) {  // fixed-order fold of the producer's per-tile partials -> mean / rstd of my row of A
+                const float2* sp = reinterpret_cast<const float2*>(ep.row_stats_in) + pix * ep.stats_in_ld;
+                float s1 = 0.f, s2 = 0.f;
+                for (int i = 0; i < ep.stats_parts; ++i) {
+                    const float2 t = __ldg(sp + i);
+                    s1 += t.x;
+                    s2 += t.y;
+                }
+                const float inv = 1.0f / static_cast<float>(ep.ln_dim);
+                ln_mean = s1 * inv;
+                ln_rstd = rsqrtf(fmaxf(fmaf(-ln_mean, ln_mean, s2 * inv), 0.f) + ep.ln_eps);
+            }
+        }
+        float st1 = 0.f, st2 = 0.f;  // producer: my row's statistics over this tile's columns
         asm volatile("bar.sync 1, 128;" ::: "memory");  // s_bias / s_rowvec visible to the four epilogue warps
 
         mbar_wait(tmem_full_bar, 0);
@@ -325,19 +349,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         float f[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) f[j] = alpha * __uint_as_float(vc[g * 8 + j]);
-                        {
+                        if constexpr (LN_CONSUME) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cl);
+                            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + cl + 4);
+                            const float4 c0v = *reinterpret_cast<const float4*>(s_rowvec + cl);
+                            const float4 c1v = *reinterpret_cast<const float4*>(s_rowvec + cl + 4);
+                            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                            const float cs[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = fmaf(ln_rstd, fmaf(-ln_mean, cs[j], f[j]), bb[j]);
+                        } else {
                             const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cl);
                             const float4 b1 = *reinterpret_cast<const float4*>(s_bias + cl + 4);
                             f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                             f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                            const float4 r0 = *reinterpret_cast<const float4*>(s_rowvec + cl);
+                            const float4 r1 = *reinterpret_cast<const float4*>(s_rowvec + cl + 4);
+                            f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+                            f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
                         }
-                        {
-                            const float4 b0 = *reinterpret_cast<const float4*>(s_rowvec + cl);
-                            const float4 b1 = *reinterpret_cast<const float4*>(s_rowvec + cl + 4);
-                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                        }
-                        if (rowvec && col_base + cl < p.N) {  // rare: the tile spans several samples (deep levels)
+                        if (!LN_CONSUME && rowvec && col_base + cl < p.N) {  // rare: the tile spans several samples (deep levels)
                             const float4 b0 = __ldg(reinterpret_cast<const float4*>(rowvec + col_base + cl));
                             const float4 b1 = __ldg(reinterpret_cast<const float4*>(rowvec + col_base + cl + 4));
                             f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
@@ -348,6 +379,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         f[4] += bf16lo(rv.z); f[5] += bf16hi(rv.z); f[6] += bf16lo(rv.w); f[7] += bf16hi(rv.w);
                         const uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
                                                    pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                        if constexpr (LN_PRODUCE) {  // statistics of what the consumer will READ: the rounded values
+                            if (col_base + cl < p.N) {
+                                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float lo = bf16lo(ow[j]), hi = bf16hi(ow[j]);
+                                    st1 += lo + hi;
+                                    st2 = fmaf(lo, lo, fmaf(hi, hi, st2));
+                                }
+                            }
+                        }
                         if constexpr (BULK) {
                             *reinterpret_cast<uint4*>(smem + r * kRowStage + cl * 2) = o;  // ring is idle: all MMAs retired
                         } else {
@@ -365,6 +407,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (row_ok && valid > 0) bulk_store_s2g(orow, smem_u32(smem + r * kRowStage), static_cast<uint32_t>(valid) * 2u);
                 bulk_commit();
                 bulk_wait_read0();  // the staging bytes must stay valid until the copy engine has read them
+            }
+            if constexpr (LN_PRODUCE) {
+                if (row_ok)
+                    reinterpret_cast<float2*>(ep.row_stats_out)[pix * ep.stats_ld + n_blk] = make_float2(st1, st2);
             }
         } else if (ep.act == IMAGD_ACT_GEGLU) {
             // tile = [64 value | 64 gate]; output columns n_blk*64 + [0, 64)
@@ -388,7 +434,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < 32; j += 2) {
                             float a0 = alpha * __uint_as_float(va[j]), a1 = alpha * __uint_as_float(va[j + 1]);
                             float g0 = alpha * __uint_as_float(vg[j]), g1 = alpha * __uint_as_float(vg[j + 1]);
-                            if (ep.bias) {
+                            if constexpr (LN_CONSUME) {  // bias (folded) is mandatory here: s_bias always staged
+                                const float2 ba = *reinterpret_cast<const float2*>(s_bias + c0 + j);
+                                const float2 bg = *reinterpret_cast<const float2*>(s_bias + 64 + c0 + j);
+                                const float2 ca = *reinterpret_cast<const float2*>(s_rowvec + c0 + j);
+                                const float2 cg = *reinterpret_cast<const float2*>(s_rowvec + 64 + c0 + j);
+                                a0 = fmaf(ln_rstd, fmaf(-ln_mean, ca.x, a0), ba.x);
+                                a1 = fmaf(ln_rstd, fmaf(-ln_mean, ca.y, a1), ba.y);
+                                g0 = fmaf(ln_rstd, fmaf(-ln_mean, cg.x, g0), bg.x);
+                                g1 = fmaf(ln_rstd, fmaf(-ln_mean, cg.y, g1), bg.y);
+                            } else if (ep.bias) {
                                 const float2 ba = *reinterpret_cast<const float2*>(s_bias + c0 + j);
                                 const float2 bg = *reinterpret_cast<const float2*>(s_bias + 64 + c0 + j);
                                 a0 += ba.x;
@@ -581,14 +636,14 @@ static GemmCfg choose_cfg(int m_tiles, int N, int kb_total, bool geglu) {
     return {bn, deep ? deep_stages(bn) : shallow_stages(bn), splits};
 }
 
-template <int BLOCK_N, int STAGES, int EPI>
+template <int BLOCK_N, int STAGES, int EPI, int LNM = 0>
 static int launch_gemm_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles,
                             cudaStream_t stream) {
     using L = GemmSmem<BLOCK_N, STAGES>;
-    IMAGD_SET_MAX_SMEM((gemm_tc_kernel<BLOCK_N, STAGES, EPI>), L::kTotal);
+    IMAGD_SET_MAX_SMEM((gemm_tc_kernel<BLOCK_N, STAGES, EPI, LNM>), L::kTotal);
     const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
     dim3 grid(m_tiles, n_tiles, p.splits);
-    IMAGD_CUDA(launch_pdl(gemm_tc_kernel<BLOCK_N, STAGES, EPI>, grid, dim3(192), L::kTotal, stream, tmA, tmB, p));
+    IMAGD_CUDA(launch_pdl(gemm_tc_kernel<BLOCK_N, STAGES, EPI, LNM>, grid, dim3(192), L::kTotal, stream, tmA, tmB, p));
     return IMAGD_OK;
 }
 
@@ -596,6 +651,14 @@ template <int BLOCK_N, int STAGES>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles,
                        cudaStream_t stream) {
     const bool linear = p.ep.act == IMAGD_ACT_NONE && !p.ep.out_fp32;
+    // LayerNorm folding variants (plain stores only for now; the bulk-store combination comes after validation)
+    if (p.ep.row_stats_out != nullptr) return launch_gemm_impl<BLOCK_N, STAGES, 1, 1>(tmA, tmB, p, m_tiles, stream);
+    if (p.ep.row_stats_in != nullptr) {
+        if (linear) return launch_gemm_impl<BLOCK_N, STAGES, 1, 2>(tmA, tmB, p, m_tiles, stream);
+        if constexpr (BLOCK_N == 128) return launch_gemm_impl<BLOCK_N, STAGES, 0, 2>(tmA, tmB, p, m_tiles, stream);
+        set_error("gemm: LayerNorm-folded generic epilogue exists for the GEGLU tile (128) only");
+        return IMAGD_ERR_ARG;
+    }
     // Bulk row stores pay off once the grid covers the chip more than twice (measured round 1: +3 % at batch 8,
     // slightly negative for <= 1-wave grids). IMAGD_GEMM_BULK_STORE = 0 / 1 forces it off / on.
     static int bulk_env = -2;
@@ -636,6 +699,17 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
     IMAGD_CHECK_ARG(!ep.bias || aligned16(ep.bias), "gemm: bias alignment");
     IMAGD_CHECK_ARG(!ep.rowvec || (aligned16(ep.rowvec) && ep.rowvec_ld % 4 == 0 && ep.rows_per_group > 0),
                     "gemm: rowvec alignment / rows_per_group");
+    IMAGD_CHECK_ARG(!(ep.row_stats_out && ep.row_stats_in), "gemm: a launch is either a statistics producer or a consumer");
+    IMAGD_CHECK_ARG(!ep.row_stats_out || (ep.act == IMAGD_ACT_NONE && !ep.out_fp32 && ep.stats_ld > 0 &&
+                                          (reinterpret_cast<uintptr_t>(ep.row_stats_out) & 7u) == 0),
+                    "gemm: row_stats_out needs a plain bf16 epilogue, stats_ld > 0 and 8-byte alignment");
+    IMAGD_CHECK_ARG(!ep.row_stats_in ||
+                        (ep.colsum && ep.bias && ep.stats_parts > 0 && ep.stats_in_ld >= ep.stats_parts && ep.ln_dim == Cin &&
+                         taps == 1 && !ep.rowvec && !ep.residual && !ep.out_fp32 &&
+                         (ep.act == IMAGD_ACT_NONE || ep.act == IMAGD_ACT_GEGLU) &&
+                         (reinterpret_cast<uintptr_t>(ep.row_stats_in) & 7u) == 0),
+                    "gemm: LayerNorm-folded consumer needs colsum + folded bias, stats_parts, ln_dim == K, no rowvec / "
+                    "residual / fp32 output, act NONE or GEGLU");
 
     GemmParams p;
     p.taps = taps;
@@ -671,6 +745,9 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
                  kb_total, ep.out_fp32);
         if (std::find(g_log.begin(), g_log.end(), key) == g_log.end()) g_log.push_back(key);
     }
+    IMAGD_CHECK_ARG(!ep.row_stats_out || ep.stats_ld >= (N + cfg.bn - 1) / cfg.bn,
+                    "gemm: stats_ld=%lld is smaller than the %d N tiles of this launch (imagd_gemm_tile_count_n)",
+                    (long long)ep.stats_ld, (N + cfg.bn - 1) / cfg.bn);
     p.splits = cfg.splits;
     p.kb_per_split = (kb_total + cfg.splits - 1) / cfg.splits;
     p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
@@ -751,6 +828,17 @@ int imagd_gemm_debug_log(int enable, char* out, int out_bytes) {
         memcpy(out, all.c_str(), all.size() + 1);
     }
     return static_cast<int>(imagd::g_log.size());
+}
+
+int imagd_gemm_tile_count_n(int M, int N, int K) {
+    using namespace imagd;
+    IMAGD_CHECK_ARG(M > 0 && N > 0 && K > 0, "tile_count_n: bad shape");
+    int bw = 1, bh = 1, bn = 1;
+    choose_pixel_box(M, 1, 1, &bw, &bh, &bn);
+    const int m_tiles = ((M + bw - 1) / bw);
+    GemmCfg cfg = choose_cfg(m_tiles, N, (K + kBlockK - 1) / kBlockK, false);
+    if (g_force_bn) cfg.bn = g_force_bn;
+    return (N + cfg.bn - 1) / cfg.bn;
 }
 
 int imagd_gemm_debug_timeline(void* device_buf) {
