@@ -66,12 +66,17 @@ struct GemmSmem {
     static constexpr int kVecOffset = (kBarOffset + (2 * STAGES + 1) * 8 + 16 + 15) & ~15;  // float4 reads
     // epilogue vectors staged once per CTA: bias[BLOCK_N] | row vector[BLOCK_N] (when the tile lies in one row group)
     static constexpr int kTotal = kVecOffset + 2 * BLOCK_N * 4;
+    // EPI 3 only: four mbarriers (one per epilogue warp) for the bulk-loaded residual rows, after the vectors
+    static constexpr int kResBarOffset = kTotal;  // 16-byte aligned: BLOCK_N * 8 is a multiple of 16
+    static constexpr int kTotalRes = kTotal + 4 * 8;
 };
 
 __host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 64 ? 64 : (n <= 128 ? 128 : 256); }
 
 // LINEAR = the epilogue has no activation and writes bf16 (every conv and most linears of the UNet): straight-line,
 // branch-free column loop with the next TMEM chunk and the next residual chunk in flight. !LINEAR = the generic epilogue
+// EPI 3 (r2-prep, never run): EPI 2 + the residual row arrives by ONE bulk copy into the same staging row (one exposed
+// round trip instead of a chain of per-chunk loads), is added from shared memory and overwritten in place by the output.
 // (SiLU / GELU / GEGLU / fp32 output). EPI: 0 generic, 1 LINEAR, 2 LINEAR with the output row staged in the (idle)
 // operand ring and written by one bulk copy per row instead of 16-byte stores (opt-in: IMAGD_GEMM_BULK_STORE=1;
 // written at the end of round 1, parity-tested but not yet tuned / made the default).
@@ -82,7 +87,8 @@ __global__ void __launch_bounds__(192, (GemmSmem<BLOCK_N, STAGES>::kTotal <= 112
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     using L = GemmSmem<BLOCK_N, STAGES>;
     constexpr bool LINEAR = EPI != 0;
-    constexpr bool BULK = EPI == 2;
+    constexpr bool BULK = EPI == 2 || EPI == 3;
+    constexpr bool BULK_RES = EPI == 3;
     constexpr bool LN_PRODUCE = LNM == 1;
     constexpr bool LN_CONSUME = LNM == 2;
     static_assert(!LN_PRODUCE || LINEAR, "row statistics are emitted by the LINEAR epilogue only");
@@ -133,6 +139,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&empty_bar[i], 1);
         }
         mbar_init(tmem_full_bar, 1);
+        if constexpr (BULK_RES) {
+            uint64_t* res_bar = reinterpret_cast<uint64_t*>(smem + L::kResBarOffset);
+            for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -247,7 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                      : make_uint4(0u, 0u, 0u, 0u);
             }
         };
-        if (!split) load_res(0, rcur);
+        if (!BULK_RES && !split) load_res(0, rcur);
         float ln_mean = 0.f, ln_rstd = 0.f;
         if constexpr (LN_CONSUME) {
             if (row_ok) {  // fixed-order fold of the producer's per-tile partials -> mean / rstd of my row of A
@@ -300,7 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool last = *reinterpret_cast<volatile uint32_t*>(tmem_slot) != 0u;
             if (!last) goto epilogue_done;
             __threadfence();
-            load_res(0, rcur);
+            if (!BULK_RES) load_res(0, rcur);
         }
         // accumulator chunk loader: TMEM (single CTA per tile) or the fixed-order sum of the split partials
         auto load_acc = [&](int c0, uint32_t(&v)[32]) {
@@ -329,7 +339,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             constexpr int NCH = BLOCK_N / 32;
             __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldd + col_base;
             uint32_t v[2][32];
-            if (!split) tmem_ld32(taddr, v[0]);
+            const bool res_staged = BULK_RES && ep.residual != nullptr;  // uniform over the CTA
+            if constexpr (BULK_RES) {
+                if (res_staged) {  // the operand ring is idle (every MMA has retired): my residual row -> my staging row
+                    uint64_t* res_bar = reinterpret_cast<uint64_t*>(smem + L::kResBarOffset) + lane_group;
+                    const int valid_cols = min(BLOCK_N, p.N - col_base);
+                    const unsigned rows_ok = __popc(__ballot_sync(0xffffffffu, row_ok && valid_cols > 0));
+                    if (lane == 0) mbar_arrive_expect_tx(res_bar, rows_ok * static_cast<uint32_t>(valid_cols) * 2u);
+                    __syncwarp();
+                    if (row_ok && valid_cols > 0)
+                        bulk_load_g2s(smem_u32(smem + r * kRowStage), res + col_base, static_cast<uint32_t>(valid_cols) * 2u,
+                                      res_bar);
+                    if (!split) tmem_ld32(taddr, v[0]);  // the first accumulator chunk travels meanwhile
+                    mbar_wait(res_bar, 0);
+                } else if (!split) {
+                    tmem_ld32(taddr, v[0]);
+                }
+            } else {
+                if (!split) tmem_ld32(taddr, v[0]);
+            }
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
                 const int c0 = ch * 32;
@@ -341,7 +369,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     load_acc(c0, vc);
                 }
                 uint4 rnext[4];
-                if (ch + 1 < NCH) load_res(c0 + 32, rnext);
+                if (!BULK_RES && ch + 1 < NCH) load_res(c0 + 32, rnext);
                 if (row_ok && col_base + c0 < p.N) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -374,7 +402,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                             f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                         }
-                        const uint4 rv = rcur[g];  // zeros when there is no residual
+                        uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+                        if constexpr (BULK_RES) {
+                            if (res_staged && col_base + cl < p.N)
+                                rv = *reinterpret_cast<const uint4*>(smem + r * kRowStage + cl * 2);
+                        } else {
+                            rv = rcur[g];  // zeros when there is no residual
+                        }
                         f[0] += bf16lo(rv.x); f[1] += bf16hi(rv.x); f[2] += bf16lo(rv.y); f[3] += bf16hi(rv.y);
                         f[4] += bf16lo(rv.z); f[5] += bf16hi(rv.z); f[6] += bf16lo(rv.w); f[7] += bf16hi(rv.w);
                         const uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
@@ -397,8 +431,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
+                if constexpr (!BULK_RES) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+                    for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+                }
             }
             if constexpr (BULK) {
                 // each thread ships its own row: generic-proxy writes -> async-proxy read needs the proxy fence only
@@ -640,10 +676,11 @@ template <int BLOCK_N, int STAGES, int EPI, int LNM = 0>
 static int launch_gemm_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles,
                             cudaStream_t stream) {
     using L = GemmSmem<BLOCK_N, STAGES>;
-    IMAGD_SET_MAX_SMEM((gemm_tc_kernel<BLOCK_N, STAGES, EPI, LNM>), L::kTotal);
+    constexpr int kSmem = EPI == 3 ? L::kTotalRes : L::kTotal;
+    IMAGD_SET_MAX_SMEM((gemm_tc_kernel<BLOCK_N, STAGES, EPI, LNM>), kSmem);
     const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
     dim3 grid(m_tiles, n_tiles, p.splits);
-    IMAGD_CUDA(launch_pdl(gemm_tc_kernel<BLOCK_N, STAGES, EPI, LNM>, grid, dim3(192), L::kTotal, stream, tmA, tmB, p));
+    IMAGD_CUDA(launch_pdl(gemm_tc_kernel<BLOCK_N, STAGES, EPI, LNM>, grid, dim3(192), kSmem, stream, tmA, tmB, p));
     return IMAGD_OK;
 }
 
@@ -669,8 +706,16 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     const int64_t ctas = static_cast<int64_t>(m_tiles) * ((p.N + BLOCK_N - 1) / BLOCK_N) * p.splits;
     const bool bulk = bulk_env >= 0 ? bulk_env == 1 : ctas > 2 * 148;
     if (!linear) return launch_gemm_impl<BLOCK_N, STAGES, 0>(tmA, tmB, p, m_tiles, stream);
-    return bulk ? launch_gemm_impl<BLOCK_N, STAGES, 2>(tmA, tmB, p, m_tiles, stream)
-                : launch_gemm_impl<BLOCK_N, STAGES, 1>(tmA, tmB, p, m_tiles, stream);
+    if (!bulk) return launch_gemm_impl<BLOCK_N, STAGES, 1>(tmA, tmB, p, m_tiles, stream);
+    // IMAGD_GEMM_BULK_RES=1 (r2-prep, never run): the residual also travels by bulk copy through the staging rows
+    static int bulk_res = -1;
+    if (bulk_res < 0) {
+        const char* e = getenv("IMAGD_GEMM_BULK_RES");
+        bulk_res = (e && e[0] == '1') ? 1 : 0;
+    }
+    const bool res_ok = p.ep.residual != nullptr && p.ep.ldr % 8 == 0;
+    return (bulk_res && res_ok) ? launch_gemm_impl<BLOCK_N, STAGES, 3>(tmA, tmB, p, m_tiles, stream)
+                                : launch_gemm_impl<BLOCK_N, STAGES, 2>(tmA, tmB, p, m_tiles, stream);
 }
 
 static int g_force_bn = 0, g_force_stages = 0, g_force_splits = 0;  // test hooks (imagd_gemm_debug_force)

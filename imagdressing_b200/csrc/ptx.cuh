@@ -67,6 +67,12 @@ __device__ __forceinline__ void bulk_store_s2g(void* gptr, uint32_t smem_addr, u
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gptr), "r"(smem_addr), "r"(bytes)
                  : "memory");
 }
+// 1-D bulk copy global -> shared (async proxy); completes `bytes` of transaction count on `bar`. 16-byte aligned.
+__device__ __forceinline__ void bulk_load_g2s(uint32_t smem_addr, const void* gptr, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr),
+                 "l"(gptr), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() {
