@@ -1,0 +1,14 @@
+#!/bin/bash
+# First GPU call of round 2: validate the r2-prep items cheapest-first, then A/B them on the step. ~6-8 minutes.
+mkdir -p gpurun_out
+set -o pipefail
+echo "== default configuration"
+timeout 300 python -m pytest tests/test_gemm_gpu.py tests/test_norm_elementwise_gpu.py tests/test_attention_gpu.py \
+  tests/test_product_golden_gpu.py -m gpu -x -q --timeout 120 2>&1 | tail -3
+echo "== LayerNorm fold"
+timeout 400 python -m pytest tests/test_ln_fold_gpu.py -m gpu -x -q --timeout 300 -s 2>&1 | tail -8
+echo "== bulk store + bulk residual forced on"
+IMAGD_GEMM_BULK_STORE=1 IMAGD_GEMM_BULK_RES=1 timeout 200 python -m pytest tests/test_gemm_gpu.py -m gpu -x -q --timeout 120 2>&1 | tail -3
+echo "== step A/B"
+timeout 900 python tools/ab_step.py "base:IMAGD_GEMM_BULK_STORE=0" "rule:" "bulkres:IMAGD_GEMM_BULK_RES=1" \
+  "fold:IMAGD_FOLD_LN=1" "fold+bulkres:IMAGD_FOLD_LN=1,IMAGD_GEMM_BULK_RES=1" "pdl:IMAGD_PDL=1" 2>&1 | tee gpurun_out/ab_step.txt
