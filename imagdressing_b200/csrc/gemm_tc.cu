@@ -45,6 +45,9 @@ struct GemmParams {
     unsigned int* counters;
     // debug: when non-null, every CTA records its timeline (imagd_gemm_debug_timeline; tools/gemm_timeline.py)
     unsigned long long* dbg;
+    // persistent kernel (gemm_persist.inc): N tiles per M tile row and total tile count
+    int persist_n_tiles;
+    int persist_total;
 };
 
 __device__ __forceinline__ void dbg_mark(const GemmParams& p, int slot) {
@@ -718,6 +721,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
                                 : launch_gemm_impl<BLOCK_N, STAGES, 2>(tmA, tmB, p, m_tiles, stream);
 }
 
+#include "gemm_persist.inc"
+
 static int g_force_bn = 0, g_force_stages = 0, g_force_splits = 0;  // test hooks (imagd_gemm_debug_force)
 static int g_log_on = 0;
 static unsigned long long* g_dbg_timeline = nullptr;  // imagd_gemm_debug_timeline
@@ -793,6 +798,18 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
     IMAGD_CHECK_ARG(!ep.row_stats_out || ep.stats_ld >= (N + cfg.bn - 1) / cfg.bn,
                     "gemm: stats_ld=%lld is smaller than the %d N tiles of this launch (imagd_gemm_tile_count_n)",
                     (long long)ep.stats_ld, (N + cfg.bn - 1) / cfg.bn);
+    // opt-in persistent kernel: plain bf16 epilogues of multi-wave problems only
+    bool use_persist = false;
+    if (persist_enabled() && ep.act == IMAGD_ACT_NONE && !ep.out_fp32 && !ep.row_stats_out && !ep.row_stats_in &&
+        (!ep.residual || ep.ldr % 8 == 0)) {
+        const int pbn = persist_block_n(N);
+        if (m_tiles64 * ((N + pbn - 1) / pbn) > 2 * 148) {
+            cfg.bn = pbn;
+            cfg.splits = 1;
+            use_persist = true;
+        }
+    }
+    p.persist_n_tiles = p.persist_total = 0;
     p.splits = cfg.splits;
     p.kb_per_split = (kb_total + cfg.splits - 1) / cfg.splits;
     p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
@@ -825,6 +842,13 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
         uint32_t box[2] = {kBlockK, static_cast<uint32_t>(cfg.bn)};
         int rc = make_tmap_bf16(&tmB, Wt, 2, dims, strides, box);
         if (rc != IMAGD_OK) return rc;
+    }
+    if (use_persist) {
+        switch (cfg.bn) {
+            case 160: return launch_persist<160, 3>(tmA, tmB, p, m_tiles, stream);
+            case 128: return launch_persist<128, 4>(tmA, tmB, p, m_tiles, stream);
+            default: return launch_persist<64, 6>(tmA, tmB, p, m_tiles, stream);
+        }
     }
     switch (cfg.bn * 100 + cfg.stages) {
         case 6404: return launch_gemm<64, 4>(tmA, tmB, p, m_tiles, stream);

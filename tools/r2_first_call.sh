@@ -9,6 +9,8 @@ echo "== LayerNorm fold"
 timeout 400 python -m pytest tests/test_ln_fold_gpu.py -m gpu -x -q --timeout 300 -s 2>&1 | tail -8
 echo "== bulk store + bulk residual forced on"
 IMAGD_GEMM_BULK_STORE=1 IMAGD_GEMM_BULK_RES=1 timeout 200 python -m pytest tests/test_gemm_gpu.py -m gpu -x -q --timeout 120 2>&1 | tail -3
+echo "== persistent GEMM"
+IMAGD_GEMM_PERSISTENT=1 timeout 300 python -m pytest tests/test_gemm_persist_gpu.py tests/test_gemm_gpu.py -m gpu -x -q --timeout 200 2>&1 | tail -4
 echo "== step A/B"
 timeout 900 python tools/ab_step.py "base:IMAGD_GEMM_BULK_STORE=0" "rule:" "bulkres:IMAGD_GEMM_BULK_RES=1" \
-  "fold:IMAGD_FOLD_LN=1" "fold+bulkres:IMAGD_FOLD_LN=1,IMAGD_GEMM_BULK_RES=1" "pdl:IMAGD_PDL=1" 2>&1 | tee gpurun_out/ab_step.txt
+  "fold:IMAGD_FOLD_LN=1" "fold+bulkres:IMAGD_FOLD_LN=1,IMAGD_GEMM_BULK_RES=1" "persist:IMAGD_GEMM_PERSISTENT=1" "pdl:IMAGD_PDL=1" 2>&1 | tee gpurun_out/ab_step.txt
