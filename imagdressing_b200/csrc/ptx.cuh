@@ -215,12 +215,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {  // one MUFU.RCP (<= 1 ulp); __frcp_rn adds a range check,
+    float y;                                            // a branch to a slow path and two Newton FMAs per element
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 the result is rounded to): one rcp, one ex2
 // and six FMAs instead of libdevice erff's ~25 instructions — the GEGLU epilogue of the FF GEMMs (M x 4C gates per
 // layer) was bound by erff issue slots, not by the tensor pipe.
 __device__ __forceinline__ float erf_fast(float x) {
     const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));  // argument in [1, inf]: no denormal / zero cases
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
