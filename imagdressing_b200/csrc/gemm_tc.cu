@@ -48,6 +48,7 @@ struct GemmParams {
     // persistent kernel (gemm_persist.inc): N tiles per M tile row and total tile count
     int persist_n_tiles;
     int persist_total;
+    int ups_n_tiles;  // LNM == 3: N tiles per phase (gridDim.y = 4 * ups_n_tiles)
 };
 
 __device__ __forceinline__ void dbg_mark(const GemmParams& p, int slot) {
@@ -94,6 +95,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr bool BULK_RES = EPI == 3;
     constexpr bool LN_PRODUCE = LNM == 1;
     constexpr bool LN_CONSUME = LNM == 2;
+    // LNM == 3 (r2-prep, never run): nearest-2x upsample + 3x3 conv as four 2x2 "phase" convs on the LOW-resolution
+    // input (2.25x fewer MACs, no upsampled tensor): blockIdx.y = phase * n_tiles + n_blk, phase = py * 2 + px; tap
+    // t = ty * 2 + tx reads input pixel (y + py - 1 + ty, x + px - 1 + tx); the weight matrix is [4 * N, 4 * Cin]
+    // (phase-major rows, tap-major columns); output pixel (2y + py, 2x + px) of a [NB, 2H, 2W, N] tensor.
+    constexpr bool UPS = LNM == 3;
     static_assert(!LN_PRODUCE || LINEAR, "row statistics are emitted by the LINEAR epilogue only");
     constexpr int kRowStage = BLOCK_N * 2 + 16;  // staged output row stride (bytes): +16 keeps 8 rows on 8 bank groups
     static_assert(!BULK || 128 * kRowStage <= L::kBarOffset, "output staging must fit in the operand ring");
@@ -125,7 +131,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     // tile coordinates
     const int m_blk = blockIdx.x;
-    const int n_blk = blockIdx.y;
+    const int ups_phase = UPS ? static_cast<int>(blockIdx.y) / p.ups_n_tiles : 0;
+    const int n_blk = UPS ? static_cast<int>(blockIdx.y) % p.ups_n_tiles : static_cast<int>(blockIdx.y);
     const int tx = m_blk % p.tiles_x;
     const int ty = (m_blk / p.tiles_x) % p.tiles_y;
     const int tn = m_blk / (p.tiles_x * p.tiles_y);
@@ -170,14 +177,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int tap = kb / p.kb_per_tap;
                 const int kc = kb - tap * p.kb_per_tap;
                 int dx = 0, dy = 0;
-                if (p.taps == 9) {
+                if constexpr (UPS) {
+                    dy = (ups_phase >> 1) - 1 + (tap >> 1);
+                    dx = (ups_phase & 1) - 1 + (tap & 1);
+                } else if (p.taps == 9) {
                     dy = tap / 3 - 1;
                     dx = tap % 3 - 1;
                 }
                 uint8_t* sa = smem + stage * L::kStageBytes;
                 uint8_t* sb = sa + kABytes;
                 tma_load_4d(sa, &tmA, &full_bar[stage], kc * kBlockK, x0 + dx, y0 + dy, n0);
-                tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.cin + kc * kBlockK, n_blk * BLOCK_N);
+                tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.cin + kc * kBlockK,
+                            (UPS ? ups_phase * p.N : 0) + n_blk * BLOCK_N);
             }
         }
     } else if (warp == 1) {
@@ -210,7 +221,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int y = y0 + (r / p.bw) % p.bh;
         const int n = n0 + r / (p.bw * p.bh);
         const bool row_ok = (x < p.W) && (y < p.H) && (n < p.NB);
-        const int64_t pix = (static_cast<int64_t>(n) * p.H + y) * p.W + x;
+        const int64_t pix = UPS ? (static_cast<int64_t>(n) * (2 * p.H) + (2 * y + (ups_phase >> 1))) * (2 * p.W) +
+                                      (2 * x + (ups_phase & 1))
+                                : (static_cast<int64_t>(n) * p.H + y) * p.W + x;
         const imagd_epilogue& ep = p.ep;
         const float alpha = ep.alpha;
         const __nv_bfloat16* res = nullptr;
@@ -682,7 +695,7 @@ static int launch_gemm_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     constexpr int kSmem = EPI == 3 ? L::kTotalRes : L::kTotal;
     IMAGD_SET_MAX_SMEM((gemm_tc_kernel<BLOCK_N, STAGES, EPI, LNM>), kSmem);
     const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
-    dim3 grid(m_tiles, n_tiles, p.splits);
+    dim3 grid(m_tiles, LNM == 3 ? 4 * n_tiles : n_tiles, p.splits);
     IMAGD_CUDA(launch_pdl(gemm_tc_kernel<BLOCK_N, STAGES, EPI, LNM>, grid, dim3(192), kSmem, stream, tmA, tmB, p));
     return IMAGD_OK;
 }
@@ -691,6 +704,11 @@ template <int BLOCK_N, int STAGES>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles,
                        cudaStream_t stream) {
     const bool linear = p.ep.act == IMAGD_ACT_NONE && !p.ep.out_fp32;
+    if (p.ups_n_tiles > 0) {  // upsample-phase conv: plain bf16 epilogue (bias only), validated by the caller
+        GemmParams q = p;
+        q.ups_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+        return launch_gemm_impl<BLOCK_N, STAGES, 1, 3>(tmA, tmB, q, m_tiles, stream);
+    }
     // LayerNorm folding variants (plain stores only for now; the bulk-store combination comes after validation)
     if (p.ep.row_stats_out != nullptr) return launch_gemm_impl<BLOCK_N, STAGES, 1, 1>(tmA, tmB, p, m_tiles, stream);
     if (p.ep.row_stats_in != nullptr) {
@@ -729,7 +747,8 @@ static unsigned long long* g_dbg_timeline = nullptr;  // imagd_gemm_debug_timeli
 static std::vector<std::string> g_log;  // unique problem keys seen while logging (tools/gemm_sweep.py)
 
 static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int Cin, int taps, const void* Wt,
-                         int64_t ldw, void* D, int64_t ldd, int N, const imagd_epilogue* ep_in, cudaStream_t stream) {
+                         int64_t ldw, void* D, int64_t ldd, int N, const imagd_epilogue* ep_in, cudaStream_t stream,
+                         bool ups_mode = false) {
     imagd_epilogue ep;
     if (ep_in) {
         ep = *ep_in;
@@ -800,7 +819,8 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
                     (long long)ep.stats_ld, (N + cfg.bn - 1) / cfg.bn);
     // opt-in persistent kernel: plain bf16 epilogues of multi-wave problems only
     bool use_persist = false;
-    if (persist_enabled() && ep.act == IMAGD_ACT_NONE && !ep.out_fp32 && !ep.row_stats_out && !ep.row_stats_in &&
+    if (ups_mode) cfg.splits = 1;  // (the split-K scratch is sized for one phase)
+    if (!ups_mode && persist_enabled() && ep.act == IMAGD_ACT_NONE && !ep.out_fp32 && !ep.row_stats_out && !ep.row_stats_in &&
         (!ep.residual || ep.ldr % 8 == 0)) {
         const int pbn = persist_block_n(N);
         if (m_tiles64 * ((N + pbn - 1) / pbn) > 2 * 148) {
@@ -810,6 +830,7 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
         }
     }
     p.persist_n_tiles = p.persist_total = 0;
+    p.ups_n_tiles = ups_mode ? 1 : 0;  // the launcher fills in the real tile count
     p.splits = cfg.splits;
     p.kb_per_split = (kb_total + cfg.splits - 1) / cfg.splits;
     p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
@@ -837,7 +858,7 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
         if (rc != IMAGD_OK) return rc;
     }
     {
-        uint64_t dims[2] = {static_cast<uint64_t>(taps) * Cin, static_cast<uint64_t>(N)};
+        uint64_t dims[2] = {static_cast<uint64_t>(taps) * Cin, static_cast<uint64_t>(N) * (ups_mode ? 4 : 1)};
         uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
         uint32_t box[2] = {kBlockK, static_cast<uint32_t>(cfg.bn)};
         int rc = make_tmap_bf16(&tmB, Wt, 2, dims, strides, box);
@@ -897,6 +918,16 @@ int imagd_gemm_debug_log(int enable, char* out, int out_bytes) {
         memcpy(out, all.c_str(), all.size() + 1);
     }
     return static_cast<int>(imagd::g_log.size());
+}
+
+int imagd_upconv3x3_bf16(const void* X, int64_t ldx, int NB, int H, int W, int Cin, const void* Wt, void* Y, int64_t ldy,
+                         int Cout, const imagd_epilogue* ep, imagd_stream stream) {
+    IMAGD_CHECK_ARG(NB > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && Cin % 64 == 0, "upconv3x3: bad shape");
+    IMAGD_CHECK_ARG(!ep || (!ep->rowvec && !ep->residual && ep->act == IMAGD_ACT_NONE && !ep->out_fp32 &&
+                            !ep->row_stats_out && !ep->row_stats_in),
+                    "upconv3x3: bias-only epilogue");
+    return imagd::run_gemm_like(X, ldx, NB, H, W, Cin, 4, Wt, static_cast<int64_t>(4) * Cin, Y, ldy, Cout, ep,
+                                static_cast<cudaStream_t>(stream), true);
 }
 
 int imagd_gemm_tile_count_n(int M, int N, int K) {

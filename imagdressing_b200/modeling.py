@@ -103,6 +103,31 @@ def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
     return w.detach().permute(0, 2, 3, 1).reshape(co, 9 * ci).to(BF16).contiguous()
 
 
+# Upsample2D + conv as four 2x2 phase convs on the low-resolution input (DESIGN.md section 8 item 4). Off by default.
+UPCONV_PHASE = os.environ.get("IMAGD_UPCONV_PHASE", "0") == "1"
+
+
+def pack_upconv3x3(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> phase weight matrix [4*Cout, 4*Cin] bf16 for nearest-2x upsample followed by the conv:
+    output pixel (2y+py, 2x+px) = sum over taps (ty, tx) of Wp[py,px,ty,tx] . in[y+py-1+ty, x+px-1+tx], where
+    Wp sums the 3x3 taps (ky, kx) whose upsampled source pixel floor((2y+py+ky-1)/2) is that input row (same for x):
+    py = 0: ty 0 <- ky {0}, ty 1 <- ky {1, 2};  py = 1: ty 0 <- ky {0, 1}, ty 1 <- ky {2}."""
+    co, ci = w.shape[:2]
+    w32 = w.detach().float()
+    sel = {(0, 0): [0], (0, 1): [1, 2], (1, 0): [0, 1], (1, 1): [2]}  # (phase bit, tap bit) -> 3x3 indices
+    out = torch.zeros(4, co, 4, ci, dtype=torch.float32, device=w.device)
+    for py in (0, 1):
+        for px in (0, 1):
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    acc = 0
+                    for ky in sel[(py, ty)]:
+                        for kx in sel[(px, tx)]:
+                            acc = acc + w32[:, :, ky, kx]
+                    out[py * 2 + px, :, ty * 2 + tx, :] = acc
+    return out.reshape(4 * co, 4 * ci).to(BF16).contiguous()
+
+
 def pack_geglu(w: torch.Tensor, b: torch.Tensor):
     """GEGLU.proj [2F, K] (value rows then gate rows) -> per 128 rows: 64 value + their 64 gate rows."""
     F2, K = w.shape
@@ -381,6 +406,10 @@ class Upsample2D(nn.Module, _Packed):
     def run(self, x):
         if self._pk is None:
             self._pk = dict(w=pack_conv3x3(self.conv.weight), b=_f32(self.conv.bias))
+            if UPCONV_PHASE and x.shape[-1] % 64 == 0:
+                self._pk["wp"] = pack_upconv3x3(self.conv.weight)
+        if "wp" in self._pk and UPCONV_PHASE:
+            return ops.upconv3x3(x, self._pk["wp"], bias=self._pk["b"])
         return ops.conv3x3(ops.upsample2x(x), self._pk["w"], bias=self._pk["b"])
 
 

@@ -121,6 +121,22 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, out: Optional[torch.Tensor] = N
     return out
 
 
+def upconv3x3(x: torch.Tensor, w_phase: torch.Tensor, *, bias=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Upsample2D (nearest 2x) + 3x3 conv as four 2x2 phase convs on the low-resolution input (modeling.pack_upconv3x3).
+    x: [NB, H, W, Cin] bf16, w_phase: [4*Cout, 4*Cin] bf16 -> [NB, 2H, 2W, Cout]."""
+    lib = _lib.load()
+    NB, H, W, Cin = x.shape
+    assert x.is_contiguous() and x.dtype == BF16 and w_phase.dtype == BF16 and w_phase.shape[1] == 4 * Cin
+    Cout = w_phase.shape[0] // 4
+    if out is None:
+        out = torch.empty(NB, 2 * H, 2 * W, Cout, device=x.device, dtype=BF16)
+    ep = _epilogue(bias, None, 0, None, ACT_NONE, 1.0, False)
+    rc = lib.imagd_upconv3x3_bf16(x.data_ptr(), Cin, NB, H, W, Cin, w_phase.data_ptr(), out.data_ptr(), out.shape[-1], Cout,
+                                  ctypes.byref(ep), _stream())
+    _lib.check(rc, "imagd_upconv3x3_bf16")
+    return out
+
+
 def kv_stream(k: torch.Tensor, v: torch.Tensor, length: int, *, sample_rows: int = 0, broadcast: bool = False,
               n_query_samples: int = 1 << 30, out_scale: float = 1.0) -> KVStream:
     """k / v: 2-D views [rows, C] whose row 0 is the first visited key of sample 0; `sample_rows` = rows between

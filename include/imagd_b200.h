@@ -83,6 +83,12 @@ int imagd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
  * the distinct problems issued ("taps NB H W Cin N geglu m_tiles kb_total out_fp32" per line), 0 stops, -1 leaves
  * the state; when `out` is given the recorded lines are copied there. Returns the number of lines. */
 int imagd_gemm_debug_force(int block_n, int stages, int splits);
+/* r2-prep: Upsample2D (nearest 2x) + its 3x3 conv in one implicit GEMM over the LOW-resolution input: four 2x2 "phase"
+ * convolutions (output pixel (2y+py, 2x+px) sees input rows {y+py-1, y+py} and columns {x+px-1, x+px}); Wt is the
+ * phase weight matrix [4*Cout, 4*Cin]: row = phase*Cout + co (phase = py*2+px), column = tap*Cin + ci (tap = ty*2+tx),
+ * value = sum of the 3x3 taps (ky, kx) that land on that input pixel. X: [NB,H,W,ldx] -> Y: [NB,2H,2W,ldy]. Bias only. */
+int imagd_upconv3x3_bf16(const void* X, int64_t ldx, int NB, int H, int W, int Cin, const void* Wt, void* Y, int64_t ldy,
+                         int Cout, const imagd_epilogue* ep, imagd_stream stream);
 /* Number of N tiles imagd_gemm_bf16 will use for an [M, K] x [N, K]^T problem with a plain (LINEAR) epilogue - the
  * number of row-statistics partials a producer launch writes per row (depends on the table-driven tile choice). */
 int imagd_gemm_tile_count_n(int M, int N, int K);

@@ -80,6 +80,23 @@ def conv3x3(x, w, *, out=None, bias=None, rowvec=None, residual=None, act=ACT_NO
     return _store(y.to(BF).contiguous(), out)
 
 
+def upconv3x3(x, w_phase, *, bias=None, out=None):
+    """Four 2x2 phase convs with the kernel's conventions: phase = py*2+px, tap = ty*2+tx reads (y+py-1+ty, x+px-1+tx)."""
+    NB, H, W, Cin = x.shape
+    Cout = w_phase.shape[0] // 4
+    xin = F.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1))  # zero frame: input row -1 / H, column -1 / W
+    wp = w_phase.float().view(4, Cout, 4, Cin)
+    y = torch.zeros(NB, Cout, 2 * H, 2 * W)
+    for py in (0, 1):
+        for px in (0, 1):
+            k = wp[py * 2 + px].view(Cout, 2, 2, Cin).permute(0, 3, 1, 2)  # [Cout, Cin, ty, tx]
+            win = xin[:, :, py:py + H + 1, px:px + W + 1]  # rows y+py-1 .. y+py (shifted by the pad of 1)
+            y[:, :, py::2, px::2] = F.conv2d(win, k)
+    if bias is not None:
+        y = y + bias.float()[None, :, None, None]
+    return _store(y.permute(0, 2, 3, 1).to(BF).contiguous(), out)
+
+
 def conv3x3_direct(x, w, bias, *, stride=1, act=ACT_NONE, out_nchw_f32=False, add=None, out=None):
     NB, H, W, Cin = x.shape
     y = F.conv2d(x.float().permute(0, 3, 1, 2), _unpack3x3(w, Cin), bias.float() if bias is not None else None,
@@ -194,5 +211,5 @@ def install(monkeypatch):
 
     for name in ("gemm", "conv3x3", "conv3x3_direct", "groupnorm", "layernorm", "kv_stream", "attention", "concat_add",
                  "upsample2x", "im2col3x3_s2", "nchw_f32_to_nhwc_bf16", "timestep_embedding", "linear_small_m",
-                 "cfg_ddim_step", "gemm_tile_count_n"):
+                 "cfg_ddim_step", "gemm_tile_count_n", "upconv3x3"):
         monkeypatch.setattr(ops, name, globals()[name])

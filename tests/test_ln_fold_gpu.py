@@ -88,3 +88,20 @@ def test_unet_eps_with_fold_matches_plain_and_oracle(cuda_device):
     print(f"eps rel-L2 vs oracle: plain {e_plain:.4f}, LayerNorm folded {e_fold:.4f}; folded vs plain {rel_l2(folded, plain):.4f}")
     assert e_fold < max(1.5 * e_plain, 2e-2) and e_fold < 5e-2
     assert torch.equal(folded, again)
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout", [(2, 32, 32, 640, 640), (2, 16, 16, 1280, 1280), (2, 8, 8, 1280, 1280),
+                                             (3, 12, 9, 128, 64)])
+def test_upconv_phase_kernel(cuda_device, NB, H, W, Cin, Cout):
+    """imagd_upconv3x3_bf16 (r2-prep): nearest-2x upsample + conv3x3 as phase convs vs the oracle conv of the upsampled input."""
+    from imagdressing_b200 import modeling, ops
+
+    x = _rand((NB, H, W, Cin), cuda_device, 21).to(BF)
+    w = _rand((Cout, Cin, 3, 3), cuda_device, 22, (9 * Cin) ** -0.5).to(BF)
+    b = _rand((Cout,), cuda_device, 23)
+    up = x.repeat_interleave(2, 1).repeat_interleave(2, 2).contiguous()
+    ref = ops_ref.conv3x3_ref(up, w, b)
+    out = ops.upconv3x3(x, modeling.pack_upconv3x3(w), bias=b)
+    assert out.shape == (NB, 2 * H, 2 * W, Cout)
+    assert rel_l2(out, ref) < 1e-2
+    assert rel_l2(out, ops.conv3x3(ops.upsample2x(x), ops_ref.conv3x3_pack(w), bias=b)) < 1e-2

@@ -13,4 +13,4 @@ echo "== persistent GEMM"
 IMAGD_GEMM_PERSISTENT=1 timeout 300 python -m pytest tests/test_gemm_persist_gpu.py tests/test_gemm_gpu.py -m gpu -x -q --timeout 200 2>&1 | tail -4
 echo "== step A/B"
 timeout 900 python tools/ab_step.py "base:IMAGD_GEMM_BULK_STORE=0" "rule:" "bulkres:IMAGD_GEMM_BULK_RES=1" \
-  "fold:IMAGD_FOLD_LN=1" "fold+bulkres:IMAGD_FOLD_LN=1,IMAGD_GEMM_BULK_RES=1" "persist:IMAGD_GEMM_PERSISTENT=1" "pdl:IMAGD_PDL=1" 2>&1 | tee gpurun_out/ab_step.txt
+  "fold:IMAGD_FOLD_LN=1" "fold+bulkres:IMAGD_FOLD_LN=1,IMAGD_GEMM_BULK_RES=1" "upconv:IMAGD_UPCONV_PHASE=1" "persist:IMAGD_GEMM_PERSISTENT=1" "pdl:IMAGD_PDL=1" 2>&1 | tee gpurun_out/ab_step.txt
