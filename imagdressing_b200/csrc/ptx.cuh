@@ -220,6 +220,20 @@ __device__ __forceinline__ float rcp_approx(float x) {  // one MUFU.RCP (<= 1 ul
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 2^x on the FMA / ALU pipes (r2-prep, never run): round-to-nearest split x = i + f, f in [-0.5, 0.5], cubic for 2^f
+// (max relative error 1.1e-4, far below the bf16 the attention probabilities are rounded to), exponent add through the
+// integer bits of the magic-number sum. Offloads a fraction of the softmax exponentials from the MUFU pipe (16 / clk / SM),
+// which bounds the head-dim-40 attention (profiles/r01_ncu_attention_l0_v25.txt: XU pipe 56 %, tensor pipe 20 %).
+// Domain: x <= 127 (the kernel's arguments are <= 8); x < -126 is clamped (result ~1e-38, i.e. zero for the row sum).
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -126.0f);
+    const float r = x + 12582912.0f;   // 1.5 * 2^23: the integer part lands in the low mantissa bits
+    const float f = x - (r - 12582912.0f);
+    float p = fmaf(0.054592825f, f, 0.24221784f);
+    p = fmaf(p, f, 0.6933686f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
 // erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 the result is rounded to): one rcp, one ex2
 // and six FMAs instead of libdevice erff's ~25 instructions — the GEGLU epilogue of the FF GEMMs (M x 4C gates per
 // layer) was bound by erff issue slots, not by the tensor pipe.

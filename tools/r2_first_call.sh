@@ -14,3 +14,9 @@ IMAGD_GEMM_PERSISTENT=1 timeout 300 python -m pytest tests/test_gemm_persist_gpu
 echo "== step A/B"
 timeout 900 python tools/ab_step.py "base:IMAGD_GEMM_BULK_STORE=0" "rule:" "bulkres:IMAGD_GEMM_BULK_RES=1" \
   "fold:IMAGD_FOLD_LN=1" "fold+bulkres:IMAGD_FOLD_LN=1,IMAGD_GEMM_BULK_RES=1" "upconv:IMAGD_UPCONV_PHASE=1" "persist:IMAGD_GEMM_PERSISTENT=1" "pdl:IMAGD_PDL=1" 2>&1 | tee gpurun_out/ab_step.txt
+# attention exp2 offload (compile-time knob): rebuild with 2 of every 8 exponentials on the FMA pipe, test, time, restore
+echo "== attention exp2 polynomial offload (IMAGD_ATTN_POLY=2)"
+touch imagdressing_b200/csrc/attention_tc.cu && make -s -C imagdressing_b200/csrc EXTRA=-DIMAGD_ATTN_POLY=2 > /dev/null
+timeout 200 python -m pytest tests/test_attention_gpu.py -m gpu -x -q --timeout 120 2>&1 | tail -2
+timeout 300 python tools/ab_step.py "poly2:" 2>&1 | tee -a gpurun_out/ab_step.txt
+touch imagdressing_b200/csrc/attention_tc.cu && make -s -C imagdressing_b200/csrc > /dev/null
