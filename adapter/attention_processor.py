@@ -57,6 +57,8 @@ class CacheAttnProcessor2_0(_ProcState):
     """reference :13-100 — garment-UNet feature tap: stash the processor input (`cache["hidden_states"]`, :34),
     then plain SDPA."""
 
+    _accepts_ln_fold = False  # the tap is the LayerNorm OUTPUT: it has to be materialised for this processor
+
     def __init__(self):
         self._init_state()
         self.cache = {}

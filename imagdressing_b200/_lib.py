@@ -29,6 +29,14 @@ class Epilogue(Structure):
         ("ldr", c_int64),
         ("alpha", c_float),
         ("out_fp32", c_int32),
+        ("row_stats_out", c_void_p),
+        ("stats_ld", c_int64),
+        ("row_stats_in", c_void_p),
+        ("stats_in_ld", c_int64),
+        ("stats_parts", c_int32),
+        ("ln_dim", c_int32),
+        ("ln_eps", c_float),
+        ("colsum", c_void_p),
     ]
 
 
@@ -57,8 +65,11 @@ SIGNATURES = {
     "imagd_gemm_debug_force": (c_int, [c_int, c_int, c_int]),
     "imagd_gemm_debug_log": (c_int, [c_int, c_char_p, c_int]),
     "imagd_gemm_debug_timeline": (c_int, [c_void_p]),
+    "imagd_gemm_tile_count_n": (c_int, [c_int, c_int, c_int]),
     "imagd_conv3x3_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_int,
                                    POINTER(Epilogue), c_void_p]),
+    "imagd_upconv3x3_bf16": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int64, c_int,
+                                     POINTER(Epilogue), c_void_p]),
     "imagd_attention_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int,
                                      POINTER(KVStream), POINTER(KVStream), c_float, c_void_p]),
     "imagd_groupnorm_ws_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
@@ -107,7 +118,7 @@ def load() -> ctypes.CDLL:
 
 
 # kernels launched through the C ABI (bench.py reports it as gpu_launches); graph replays add their node count
-LAUNCHES = {"imagd_gemm_bf16": 1, "imagd_conv3x3_bf16": 1, "imagd_attention_bf16": 1, "imagd_groupnorm_bf16": 1,
+LAUNCHES = {"imagd_gemm_bf16": 1, "imagd_conv3x3_bf16": 1, "imagd_upconv3x3_bf16": 1, "imagd_attention_bf16": 1, "imagd_groupnorm_bf16": 1,
             "imagd_layernorm_bf16": 1, "imagd_concat_add_bf16": 1, "imagd_upsample2x_bf16": 1,
             "imagd_im2col3x3_s2_bf16": 1, "imagd_conv3x3_direct_bf16": 1, "imagd_nchw_f32_to_nhwc_bf16": 1,
             "imagd_timestep_embedding": 1, "imagd_linear_small_m": 1, "imagd_cfg_ddim_step": 1}

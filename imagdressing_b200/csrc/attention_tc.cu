@@ -25,6 +25,10 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#ifndef IMAGD_ATTN_POLY
+#define IMAGD_ATTN_POLY 0  // r2-prep experiment knob: make EXTRA=-DIMAGD_ATTN_POLY=2
+#endif
+
 namespace imagd {
 
 struct AttnParams {
@@ -321,7 +325,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     float e[8];
                     if (valid >= 64) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) e[k] = ex2_approx(__uint_as_float(v[q * 8 + k]) * sc - m_new);
+                        for (int k = 0; k < 8; ++k) {
+                            const float arg = __uint_as_float(v[q * 8 + k]) * sc - m_new;
+                            // IMAGD_ATTN_POLY of every 8 exponentials go to the FMA pipe instead of MUFU (default 0)
+                            e[k] = (k < IMAGD_ATTN_POLY) ? ex2_poly(arg) : ex2_approx(arg);
+                        }
                     } else {
 #pragma unroll
                         for (int k = 0; k < 8; ++k)

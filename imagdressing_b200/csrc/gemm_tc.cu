@@ -45,6 +45,10 @@ struct GemmParams {
     unsigned int* counters;
     // debug: when non-null, every CTA records its timeline (imagd_gemm_debug_timeline; tools/gemm_timeline.py)
     unsigned long long* dbg;
+    // persistent kernel (gemm_persist.inc): N tiles per M tile row and total tile count
+    int persist_n_tiles;
+    int persist_total;
+    int ups_n_tiles;  // LNM == 3: N tiles per phase (gridDim.y = 4 * ups_n_tiles)
 };
 
 __device__ __forceinline__ void dbg_mark(const GemmParams& p, int slot) {
@@ -66,21 +70,37 @@ struct GemmSmem {
     static constexpr int kVecOffset = (kBarOffset + (2 * STAGES + 1) * 8 + 16 + 15) & ~15;  // float4 reads
     // epilogue vectors staged once per CTA: bias[BLOCK_N] | row vector[BLOCK_N] (when the tile lies in one row group)
     static constexpr int kTotal = kVecOffset + 2 * BLOCK_N * 4;
+    // EPI 3 only: four mbarriers (one per epilogue warp) for the bulk-loaded residual rows, after the vectors
+    static constexpr int kResBarOffset = kTotal;  // 16-byte aligned: BLOCK_N * 8 is a multiple of 16
+    static constexpr int kTotalRes = kTotal + 4 * 8;
 };
 
 __host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 64 ? 64 : (n <= 128 ? 128 : 256); }
 
 // LINEAR = the epilogue has no activation and writes bf16 (every conv and most linears of the UNet): straight-line,
 // branch-free column loop with the next TMEM chunk and the next residual chunk in flight. !LINEAR = the generic epilogue
+// EPI 3 (r2-prep, never run): EPI 2 + the residual row arrives by ONE bulk copy into the same staging row (one exposed
+// round trip instead of a chain of per-chunk loads), is added from shared memory and overwritten in place by the output.
 // (SiLU / GELU / GEGLU / fp32 output). EPI: 0 generic, 1 LINEAR, 2 LINEAR with the output row staged in the (idle)
 // operand ring and written by one bulk copy per row instead of 16-byte stores (opt-in: IMAGD_GEMM_BULK_STORE=1;
 // written at the end of round 1, parity-tested but not yet tuned / made the default).
-template <int BLOCK_N, int STAGES, int EPI>
+// LNM: LayerNorm folding (r2-prep, see include/imagd_b200.h): 0 off, 1 producer (emit per-row {sum, sum of squares}
+// of the rounded outputs, one slot per N tile), 2 consumer (apply rstd * (alpha * acc - mean * colsum) + bias).
+template <int BLOCK_N, int STAGES, int EPI, int LNM>
 __global__ void __launch_bounds__(192, (GemmSmem<BLOCK_N, STAGES>::kTotal <= 112 * 1024) ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     using L = GemmSmem<BLOCK_N, STAGES>;
     constexpr bool LINEAR = EPI != 0;
-    constexpr bool BULK = EPI == 2;
+    constexpr bool BULK = EPI == 2 || EPI == 3;
+    constexpr bool BULK_RES = EPI == 3;
+    constexpr bool LN_PRODUCE = LNM == 1;
+    constexpr bool LN_CONSUME = LNM == 2;
+    // LNM == 3 (r2-prep, never run): nearest-2x upsample + 3x3 conv as four 2x2 "phase" convs on the LOW-resolution
+    // input (2.25x fewer MACs, no upsampled tensor): blockIdx.y = phase * n_tiles + n_blk, phase = py * 2 + px; tap
+    // t = ty * 2 + tx reads input pixel (y + py - 1 + ty, x + px - 1 + tx); the weight matrix is [4 * N, 4 * Cin]
+    // (phase-major rows, tap-major columns); output pixel (2y + py, 2x + px) of a [NB, 2H, 2W, N] tensor.
+    constexpr bool UPS = LNM == 3;
+    static_assert(!LN_PRODUCE || LINEAR, "row statistics are emitted by the LINEAR epilogue only");
     constexpr int kRowStage = BLOCK_N * 2 + 16;  // staged output row stride (bytes): +16 keeps 8 rows on 8 bank groups
     static_assert(!BULK || 128 * kRowStage <= L::kBarOffset, "output staging must fit in the operand ring");
     extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -111,7 +131,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     // tile coordinates
     const int m_blk = blockIdx.x;
-    const int n_blk = blockIdx.y;
+    const int ups_phase = UPS ? static_cast<int>(blockIdx.y) / p.ups_n_tiles : 0;
+    const int n_blk = UPS ? static_cast<int>(blockIdx.y) % p.ups_n_tiles : static_cast<int>(blockIdx.y);
     const int tx = m_blk % p.tiles_x;
     const int ty = (m_blk / p.tiles_x) % p.tiles_y;
     const int tn = m_blk / (p.tiles_x * p.tiles_y);
@@ -128,6 +149,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&empty_bar[i], 1);
         }
         mbar_init(tmem_full_bar, 1);
+        if constexpr (BULK_RES) {
+            uint64_t* res_bar = reinterpret_cast<uint64_t*>(smem + L::kResBarOffset);
+            for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -152,14 +177,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int tap = kb / p.kb_per_tap;
                 const int kc = kb - tap * p.kb_per_tap;
                 int dx = 0, dy = 0;
-                if (p.taps == 9) {
+                if constexpr (UPS) {
+                    dy = (ups_phase >> 1) - 1 + (tap >> 1);
+                    dx = (ups_phase & 1) - 1 + (tap & 1);
+                } else if (p.taps == 9) {
                     dy = tap / 3 - 1;
                     dx = tap % 3 - 1;
                 }
                 uint8_t* sa = smem + stage * L::kStageBytes;
                 uint8_t* sb = sa + kABytes;
                 tma_load_4d(sa, &tmA, &full_bar[stage], kc * kBlockK, x0 + dx, y0 + dy, n0);
-                tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.cin + kc * kBlockK, n_blk * BLOCK_N);
+                tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.cin + kc * kBlockK,
+                            (UPS ? ups_phase * p.N : 0) + n_blk * BLOCK_N);
             }
         }
     } else if (warp == 1) {
@@ -192,7 +221,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int y = y0 + (r / p.bw) % p.bh;
         const int n = n0 + r / (p.bw * p.bh);
         const bool row_ok = (x < p.W) && (y < p.H) && (n < p.NB);
-        const int64_t pix = (static_cast<int64_t>(n) * p.H + y) * p.W + x;
+        const int64_t pix = UPS ? (static_cast<int64_t>(n) * (2 * p.H) + (2 * y + (ups_phase >> 1))) * (2 * p.W) +
+                                      (2 * x + (ups_phase & 1))
+                                : (static_cast<int64_t>(n) * p.H + y) * p.W + x;
         const imagd_epilogue& ep = p.ep;
         const float alpha = ep.alpha;
         const __nv_bfloat16* res = nullptr;
@@ -221,7 +252,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 rowvec = ep.rowvec + (pix / ep.rows_per_group) * ep.rowvec_ld;
             }
         }
-        if (LINEAR && !rowvec_shared) {  // the straight-line loop always adds the staged vectors: absent = zeros
+        if constexpr (LN_CONSUME) {  // the row-vector slot carries the folded weight's column sums instead
+            for (int c = threadIdx.x - 64; c < BLOCK_N; c += 128)
+                s_rowvec[c] = (col_base + c < p.N) ? __ldg(ep.colsum + col_base + c) : 0.f;
+        } else if (LINEAR && !rowvec_shared) {  // the straight-line loop always adds the staged vectors: absent = zeros
             for (int c = threadIdx.x - 64; c < BLOCK_N; c += 128) s_rowvec[c] = 0.f;
         }
         if (ep.bias != nullptr) {
@@ -239,7 +273,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                      : make_uint4(0u, 0u, 0u, 0u);
             }
         };
-        if (!split) load_res(0, rcur);
+        if (!BULK_RES && !split) load_res(0, rcur);
+        float ln_mean = 0.f, ln_rstd = 0.f;
+        if constexpr (LN_CONSUME) {
+            if (row_ok) {  // fixed-order fold of the producer's per-tile partials -> mean / rstd of my row of A
+                const float2* sp = reinterpret_cast<const float2*>(ep.row_stats_in) + pix * ep.stats_in_ld;
+                float s1 = 0.f, s2 = 0.f;
+                for (int i = 0; i < ep.stats_parts; ++i) {
+                    const float2 t = __ldg(sp + i);
+                    s1 += t.x;
+                    s2 += t.y;
+                }
+                const float inv = 1.0f / static_cast<float>(ep.ln_dim);
+                ln_mean = s1 * inv;
+                ln_rstd = rsqrtf(fmaxf(fmaf(-ln_mean, ln_mean, s2 * inv), 0.f) + ep.ln_eps);
+            }
+        }
+        float st1 = 0.f, st2 = 0.f;  // producer: my row's statistics over this tile's columns
         asm volatile("bar.sync 1, 128;" ::: "memory");  // s_bias / s_rowvec visible to the four epilogue warps
 
         mbar_wait(tmem_full_bar, 0);
@@ -276,7 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool last = *reinterpret_cast<volatile uint32_t*>(tmem_slot) != 0u;
             if (!last) goto epilogue_done;
             __threadfence();
-            load_res(0, rcur);
+            if (!BULK_RES) load_res(0, rcur);
         }
         // accumulator chunk loader: TMEM (single CTA per tile) or the fixed-order sum of the split partials
         auto load_acc = [&](int c0, uint32_t(&v)[32]) {
@@ -305,7 +355,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             constexpr int NCH = BLOCK_N / 32;
             __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldd + col_base;
             uint32_t v[2][32];
-            if (!split) tmem_ld32(taddr, v[0]);
+            const bool res_staged = BULK_RES && ep.residual != nullptr;  // uniform over the CTA
+            if constexpr (BULK_RES) {
+                if (res_staged) {  // the operand ring is idle (every MMA has retired): my residual row -> my staging row
+                    uint64_t* res_bar = reinterpret_cast<uint64_t*>(smem + L::kResBarOffset) + lane_group;
+                    const int valid_cols = min(BLOCK_N, p.N - col_base);
+                    const unsigned rows_ok = __popc(__ballot_sync(0xffffffffu, row_ok && valid_cols > 0));
+                    if (lane == 0) mbar_arrive_expect_tx(res_bar, rows_ok * static_cast<uint32_t>(valid_cols) * 2u);
+                    __syncwarp();
+                    if (row_ok && valid_cols > 0)
+                        bulk_load_g2s(smem_u32(smem + r * kRowStage), res + col_base, static_cast<uint32_t>(valid_cols) * 2u,
+                                      res_bar);
+                    if (!split) tmem_ld32(taddr, v[0]);  // the first accumulator chunk travels meanwhile
+                    mbar_wait(res_bar, 0);
+                } else if (!split) {
+                    tmem_ld32(taddr, v[0]);
+                }
+            } else {
+                if (!split) tmem_ld32(taddr, v[0]);
+            }
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
                 const int c0 = ch * 32;
@@ -317,7 +385,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     load_acc(c0, vc);
                 }
                 uint4 rnext[4];
-                if (ch + 1 < NCH) load_res(c0 + 32, rnext);
+                if (!BULK_RES && ch + 1 < NCH) load_res(c0 + 32, rnext);
                 if (row_ok && col_base + c0 < p.N) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -325,29 +393,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         float f[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) f[j] = alpha * __uint_as_float(vc[g * 8 + j]);
-                        {
+                        if constexpr (LN_CONSUME) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cl);
+                            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + cl + 4);
+                            const float4 c0v = *reinterpret_cast<const float4*>(s_rowvec + cl);
+                            const float4 c1v = *reinterpret_cast<const float4*>(s_rowvec + cl + 4);
+                            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                            const float cs[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = fmaf(ln_rstd, fmaf(-ln_mean, cs[j], f[j]), bb[j]);
+                        } else {
                             const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cl);
                             const float4 b1 = *reinterpret_cast<const float4*>(s_bias + cl + 4);
                             f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                             f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                            const float4 r0 = *reinterpret_cast<const float4*>(s_rowvec + cl);
+                            const float4 r1 = *reinterpret_cast<const float4*>(s_rowvec + cl + 4);
+                            f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+                            f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
                         }
-                        {
-                            const float4 b0 = *reinterpret_cast<const float4*>(s_rowvec + cl);
-                            const float4 b1 = *reinterpret_cast<const float4*>(s_rowvec + cl + 4);
-                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                        }
-                        if (rowvec && col_base + cl < p.N) {  // rare: the tile spans several samples (deep levels)
+                        if (!LN_CONSUME && rowvec && col_base + cl < p.N) {  // rare: the tile spans several samples (deep levels)
                             const float4 b0 = __ldg(reinterpret_cast<const float4*>(rowvec + col_base + cl));
                             const float4 b1 = __ldg(reinterpret_cast<const float4*>(rowvec + col_base + cl + 4));
                             f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                             f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                         }
-                        const uint4 rv = rcur[g];  // zeros when there is no residual
+                        uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+                        if constexpr (BULK_RES) {
+                            if (res_staged && col_base + cl < p.N)
+                                rv = *reinterpret_cast<const uint4*>(smem + r * kRowStage + cl * 2);
+                        } else {
+                            rv = rcur[g];  // zeros when there is no residual
+                        }
                         f[0] += bf16lo(rv.x); f[1] += bf16hi(rv.x); f[2] += bf16lo(rv.y); f[3] += bf16hi(rv.y);
                         f[4] += bf16lo(rv.z); f[5] += bf16hi(rv.z); f[6] += bf16lo(rv.w); f[7] += bf16hi(rv.w);
                         const uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
                                                    pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                        if constexpr (LN_PRODUCE) {  // statistics of what the consumer will READ: the rounded values
+                            if (col_base + cl < p.N) {
+                                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float lo = bf16lo(ow[j]), hi = bf16hi(ow[j]);
+                                    st1 += lo + hi;
+                                    st2 = fmaf(lo, lo, fmaf(hi, hi, st2));
+                                }
+                            }
+                        }
                         if constexpr (BULK) {
                             *reinterpret_cast<uint4*>(smem + r * kRowStage + cl * 2) = o;  // ring is idle: all MMAs retired
                         } else {
@@ -355,8 +447,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
+                if constexpr (!BULK_RES) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+                    for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
+                }
             }
             if constexpr (BULK) {
                 // each thread ships its own row: generic-proxy writes -> async-proxy read needs the proxy fence only
@@ -365,6 +459,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (row_ok && valid > 0) bulk_store_s2g(orow, smem_u32(smem + r * kRowStage), static_cast<uint32_t>(valid) * 2u);
                 bulk_commit();
                 bulk_wait_read0();  // the staging bytes must stay valid until the copy engine has read them
+            }
+            if constexpr (LN_PRODUCE) {
+                if (row_ok)
+                    reinterpret_cast<float2*>(ep.row_stats_out)[pix * ep.stats_ld + n_blk] = make_float2(st1, st2);
             }
         } else if (ep.act == IMAGD_ACT_GEGLU) {
             // tile = [64 value | 64 gate]; output columns n_blk*64 + [0, 64)
@@ -388,7 +486,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < 32; j += 2) {
                             float a0 = alpha * __uint_as_float(va[j]), a1 = alpha * __uint_as_float(va[j + 1]);
                             float g0 = alpha * __uint_as_float(vg[j]), g1 = alpha * __uint_as_float(vg[j + 1]);
-                            if (ep.bias) {
+                            if constexpr (LN_CONSUME) {  // bias (folded) is mandatory here: s_bias always staged
+                                const float2 ba = *reinterpret_cast<const float2*>(s_bias + c0 + j);
+                                const float2 bg = *reinterpret_cast<const float2*>(s_bias + 64 + c0 + j);
+                                const float2 ca = *reinterpret_cast<const float2*>(s_rowvec + c0 + j);
+                                const float2 cg = *reinterpret_cast<const float2*>(s_rowvec + 64 + c0 + j);
+                                a0 = fmaf(ln_rstd, fmaf(-ln_mean, ca.x, a0), ba.x);
+                                a1 = fmaf(ln_rstd, fmaf(-ln_mean, ca.y, a1), ba.y);
+                                g0 = fmaf(ln_rstd, fmaf(-ln_mean, cg.x, g0), bg.x);
+                                g1 = fmaf(ln_rstd, fmaf(-ln_mean, cg.y, g1), bg.y);
+                            } else if (ep.bias) {
                                 const float2 ba = *reinterpret_cast<const float2*>(s_bias + c0 + j);
                                 const float2 bg = *reinterpret_cast<const float2*>(s_bias + 64 + c0 + j);
                                 a0 += ba.x;
@@ -581,14 +688,15 @@ static GemmCfg choose_cfg(int m_tiles, int N, int kb_total, bool geglu) {
     return {bn, deep ? deep_stages(bn) : shallow_stages(bn), splits};
 }
 
-template <int BLOCK_N, int STAGES, int EPI>
+template <int BLOCK_N, int STAGES, int EPI, int LNM = 0>
 static int launch_gemm_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles,
                             cudaStream_t stream) {
     using L = GemmSmem<BLOCK_N, STAGES>;
-    IMAGD_SET_MAX_SMEM((gemm_tc_kernel<BLOCK_N, STAGES, EPI>), L::kTotal);
+    constexpr int kSmem = EPI == 3 ? L::kTotalRes : L::kTotal;
+    IMAGD_SET_MAX_SMEM((gemm_tc_kernel<BLOCK_N, STAGES, EPI, LNM>), kSmem);
     const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
-    dim3 grid(m_tiles, n_tiles, p.splits);
-    IMAGD_CUDA(launch_pdl(gemm_tc_kernel<BLOCK_N, STAGES, EPI>, grid, dim3(192), L::kTotal, stream, tmA, tmB, p));
+    dim3 grid(m_tiles, LNM == 3 ? 4 * n_tiles : n_tiles, p.splits);
+    IMAGD_CUDA(launch_pdl(gemm_tc_kernel<BLOCK_N, STAGES, EPI, LNM>, grid, dim3(192), kSmem, stream, tmA, tmB, p));
     return IMAGD_OK;
 }
 
@@ -596,15 +704,42 @@ template <int BLOCK_N, int STAGES>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int m_tiles,
                        cudaStream_t stream) {
     const bool linear = p.ep.act == IMAGD_ACT_NONE && !p.ep.out_fp32;
-    static int bulk = -1;
-    if (bulk < 0) {
-        const char* e = getenv("IMAGD_GEMM_BULK_STORE");  // opt-in experiment (see the kernel comment)
-        bulk = (e && e[0] == '1') ? 1 : 0;
+    if (p.ups_n_tiles > 0) {  // upsample-phase conv: plain bf16 epilogue (bias only), validated by the caller
+        GemmParams q = p;
+        q.ups_n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+        return launch_gemm_impl<BLOCK_N, STAGES, 1, 3>(tmA, tmB, q, m_tiles, stream);
     }
+    // LayerNorm folding variants (plain stores only for now; the bulk-store combination comes after validation)
+    if (p.ep.row_stats_out != nullptr) return launch_gemm_impl<BLOCK_N, STAGES, 1, 1>(tmA, tmB, p, m_tiles, stream);
+    if (p.ep.row_stats_in != nullptr) {
+        if (linear) return launch_gemm_impl<BLOCK_N, STAGES, 1, 2>(tmA, tmB, p, m_tiles, stream);
+        if constexpr (BLOCK_N == 128) return launch_gemm_impl<BLOCK_N, STAGES, 0, 2>(tmA, tmB, p, m_tiles, stream);
+        set_error("gemm: LayerNorm-folded generic epilogue exists for the GEGLU tile (128) only");
+        return IMAGD_ERR_ARG;
+    }
+    // Bulk row stores pay off once the grid covers the chip more than twice (measured round 1: +3 % at batch 8,
+    // slightly negative for <= 1-wave grids). IMAGD_GEMM_BULK_STORE = 0 / 1 forces it off / on.
+    static int bulk_env = -2;
+    if (bulk_env == -2) {
+        const char* e = getenv("IMAGD_GEMM_BULK_STORE");
+        bulk_env = e ? (e[0] == '1' ? 1 : 0) : -1;
+    }
+    const int64_t ctas = static_cast<int64_t>(m_tiles) * ((p.N + BLOCK_N - 1) / BLOCK_N) * p.splits;
+    const bool bulk = bulk_env >= 0 ? bulk_env == 1 : ctas > 2 * 148;
     if (!linear) return launch_gemm_impl<BLOCK_N, STAGES, 0>(tmA, tmB, p, m_tiles, stream);
-    return bulk ? launch_gemm_impl<BLOCK_N, STAGES, 2>(tmA, tmB, p, m_tiles, stream)
-                : launch_gemm_impl<BLOCK_N, STAGES, 1>(tmA, tmB, p, m_tiles, stream);
+    if (!bulk) return launch_gemm_impl<BLOCK_N, STAGES, 1>(tmA, tmB, p, m_tiles, stream);
+    // IMAGD_GEMM_BULK_RES=1 (r2-prep, never run): the residual also travels by bulk copy through the staging rows
+    static int bulk_res = -1;
+    if (bulk_res < 0) {
+        const char* e = getenv("IMAGD_GEMM_BULK_RES");
+        bulk_res = (e && e[0] == '1') ? 1 : 0;
+    }
+    const bool res_ok = p.ep.residual != nullptr && p.ep.ldr % 8 == 0;
+    return (bulk_res && res_ok) ? launch_gemm_impl<BLOCK_N, STAGES, 3>(tmA, tmB, p, m_tiles, stream)
+                                : launch_gemm_impl<BLOCK_N, STAGES, 2>(tmA, tmB, p, m_tiles, stream);
 }
+
+#include "gemm_persist.inc"
 
 static int g_force_bn = 0, g_force_stages = 0, g_force_splits = 0;  // test hooks (imagd_gemm_debug_force)
 static int g_log_on = 0;
@@ -612,7 +747,8 @@ static unsigned long long* g_dbg_timeline = nullptr;  // imagd_gemm_debug_timeli
 static std::vector<std::string> g_log;  // unique problem keys seen while logging (tools/gemm_sweep.py)
 
 static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int Cin, int taps, const void* Wt,
-                         int64_t ldw, void* D, int64_t ldd, int N, const imagd_epilogue* ep_in, cudaStream_t stream) {
+                         int64_t ldw, void* D, int64_t ldd, int N, const imagd_epilogue* ep_in, cudaStream_t stream,
+                         bool ups_mode = false) {
     imagd_epilogue ep;
     if (ep_in) {
         ep = *ep_in;
@@ -632,6 +768,17 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
     IMAGD_CHECK_ARG(!ep.bias || aligned16(ep.bias), "gemm: bias alignment");
     IMAGD_CHECK_ARG(!ep.rowvec || (aligned16(ep.rowvec) && ep.rowvec_ld % 4 == 0 && ep.rows_per_group > 0),
                     "gemm: rowvec alignment / rows_per_group");
+    IMAGD_CHECK_ARG(!(ep.row_stats_out && ep.row_stats_in), "gemm: a launch is either a statistics producer or a consumer");
+    IMAGD_CHECK_ARG(!ep.row_stats_out || (ep.act == IMAGD_ACT_NONE && !ep.out_fp32 && ep.stats_ld > 0 &&
+                                          (reinterpret_cast<uintptr_t>(ep.row_stats_out) & 7u) == 0),
+                    "gemm: row_stats_out needs a plain bf16 epilogue, stats_ld > 0 and 8-byte alignment");
+    IMAGD_CHECK_ARG(!ep.row_stats_in ||
+                        (ep.colsum && ep.bias && ep.stats_parts > 0 && ep.stats_in_ld >= ep.stats_parts && ep.ln_dim == Cin &&
+                         taps == 1 && !ep.rowvec && !ep.residual && !ep.out_fp32 &&
+                         (ep.act == IMAGD_ACT_NONE || ep.act == IMAGD_ACT_GEGLU) &&
+                         (reinterpret_cast<uintptr_t>(ep.row_stats_in) & 7u) == 0),
+                    "gemm: LayerNorm-folded consumer needs colsum + folded bias, stats_parts, ln_dim == K, no rowvec / "
+                    "residual / fp32 output, act NONE or GEGLU");
 
     GemmParams p;
     p.taps = taps;
@@ -667,6 +814,23 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
                  kb_total, ep.out_fp32);
         if (std::find(g_log.begin(), g_log.end(), key) == g_log.end()) g_log.push_back(key);
     }
+    IMAGD_CHECK_ARG(!ep.row_stats_out || ep.stats_ld >= (N + cfg.bn - 1) / cfg.bn,
+                    "gemm: stats_ld=%lld is smaller than the %d N tiles of this launch (imagd_gemm_tile_count_n)",
+                    (long long)ep.stats_ld, (N + cfg.bn - 1) / cfg.bn);
+    // opt-in persistent kernel: plain bf16 epilogues of multi-wave problems only
+    bool use_persist = false;
+    if (ups_mode) cfg.splits = 1;  // (the split-K scratch is sized for one phase)
+    if (!ups_mode && persist_enabled() && ep.act == IMAGD_ACT_NONE && !ep.out_fp32 && !ep.row_stats_out && !ep.row_stats_in &&
+        (!ep.residual || ep.ldr % 8 == 0)) {
+        const int pbn = persist_block_n(N);
+        if (m_tiles64 * ((N + pbn - 1) / pbn) > 2 * 148) {
+            cfg.bn = pbn;
+            cfg.splits = 1;
+            use_persist = true;
+        }
+    }
+    p.persist_n_tiles = p.persist_total = 0;
+    p.ups_n_tiles = ups_mode ? 1 : 0;  // the launcher fills in the real tile count
     p.splits = cfg.splits;
     p.kb_per_split = (kb_total + cfg.splits - 1) / cfg.splits;
     p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
@@ -694,11 +858,18 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
         if (rc != IMAGD_OK) return rc;
     }
     {
-        uint64_t dims[2] = {static_cast<uint64_t>(taps) * Cin, static_cast<uint64_t>(N)};
+        uint64_t dims[2] = {static_cast<uint64_t>(taps) * Cin, static_cast<uint64_t>(N) * (ups_mode ? 4 : 1)};
         uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
         uint32_t box[2] = {kBlockK, static_cast<uint32_t>(cfg.bn)};
         int rc = make_tmap_bf16(&tmB, Wt, 2, dims, strides, box);
         if (rc != IMAGD_OK) return rc;
+    }
+    if (use_persist) {
+        switch (cfg.bn) {
+            case 160: return launch_persist<160, 3>(tmA, tmB, p, m_tiles, stream);
+            case 128: return launch_persist<128, 4>(tmA, tmB, p, m_tiles, stream);
+            default: return launch_persist<64, 6>(tmA, tmB, p, m_tiles, stream);
+        }
     }
     switch (cfg.bn * 100 + cfg.stages) {
         case 6404: return launch_gemm<64, 4>(tmA, tmB, p, m_tiles, stream);
@@ -747,6 +918,27 @@ int imagd_gemm_debug_log(int enable, char* out, int out_bytes) {
         memcpy(out, all.c_str(), all.size() + 1);
     }
     return static_cast<int>(imagd::g_log.size());
+}
+
+int imagd_upconv3x3_bf16(const void* X, int64_t ldx, int NB, int H, int W, int Cin, const void* Wt, void* Y, int64_t ldy,
+                         int Cout, const imagd_epilogue* ep, imagd_stream stream) {
+    IMAGD_CHECK_ARG(NB > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && Cin % 64 == 0, "upconv3x3: bad shape");
+    IMAGD_CHECK_ARG(!ep || (!ep->rowvec && !ep->residual && ep->act == IMAGD_ACT_NONE && !ep->out_fp32 &&
+                            !ep->row_stats_out && !ep->row_stats_in),
+                    "upconv3x3: bias-only epilogue");
+    return imagd::run_gemm_like(X, ldx, NB, H, W, Cin, 4, Wt, static_cast<int64_t>(4) * Cin, Y, ldy, Cout, ep,
+                                static_cast<cudaStream_t>(stream), true);
+}
+
+int imagd_gemm_tile_count_n(int M, int N, int K) {
+    using namespace imagd;
+    IMAGD_CHECK_ARG(M > 0 && N > 0 && K > 0, "tile_count_n: bad shape");
+    int bw = 1, bh = 1, bn = 1;
+    choose_pixel_box(M, 1, 1, &bw, &bh, &bn);
+    const int m_tiles = ((M + bw - 1) / bw);
+    GemmCfg cfg = choose_cfg(m_tiles, N, (K + kBlockK - 1) / kBlockK, false);
+    if (g_force_bn) cfg.bn = g_force_bn;
+    return (N + cfg.bn - 1) / cfg.bn;
 }
 
 int imagd_gemm_debug_timeline(void* device_buf) {

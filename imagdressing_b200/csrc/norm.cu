@@ -192,6 +192,10 @@ __global__ void __launch_bounds__(kGnThreads, 2) groupnorm_fused_kernel(
     // ---------------- phase 2: normalise my pixel chunk
     const int total = (p_end - p_begin) * CV;
     constexpr int U = 4;  // independent 128-bit loads in flight per thread
+    // (row, column vector) of flat index idx = row * CV + col, advanced by kGnThreads per vector WITHOUT a division:
+    // the step (kGnThreads / CV, kGnThreads % CV) is loop invariant; a carry keeps col < CV.
+    const int step_row = kGnThreads / CV, step_col = kGnThreads % CV;
+    int walk_row = threadIdx.x / CV, walk_col = threadIdx.x % CV;
     for (int base = threadIdx.x; base < total; base += kGnThreads * U) {
         uint4 v[U];
         int c0s[U];
@@ -200,12 +204,14 @@ __global__ void __launch_bounds__(kGnThreads, 2) groupnorm_fused_kernel(
         for (int t = 0; t < U; ++t) {
             const int idx = base + t * kGnThreads;
             v[t] = make_uint4(0u, 0u, 0u, 0u);
-            c0s[t] = 0;
-            rowsv[t] = 0;
-            if (idx < total) {
-                c0s[t] = (idx % CV) * 8;
-                rowsv[t] = static_cast<int64_t>(n) * HW + p_begin + idx / CV;
-                v[t] = __ldg(reinterpret_cast<const uint4*>(x + rowsv[t] * ldx + c0s[t]));
+            c0s[t] = walk_col * 8;
+            rowsv[t] = static_cast<int64_t>(n) * HW + p_begin + walk_row;
+            if (idx < total) v[t] = __ldg(reinterpret_cast<const uint4*>(x + rowsv[t] * ldx + c0s[t]));
+            walk_row += step_row;
+            walk_col += step_col;
+            if (walk_col >= CV) {
+                walk_col -= CV;
+                ++walk_row;
             }
         }
 #pragma unroll
@@ -242,6 +248,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
     const int lane = threadIdx.x & 31;
     if (row0 >= rows) return;
     const int CV = C / 8;
+    const float inv_c = 1.0f / static_cast<float>(C);  // one IEEE division per thread instead of two per row
     uint4 raw[R][VPL];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float mean = sum / static_cast<float>(C);
+        const float mean = sum * inv_c;
         float sq = 0.f;
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
@@ -284,7 +291,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        const float rstd = rsqrtf(sq / static_cast<float>(C) + eps);
+        const float rstd = rsqrtf(sq * inv_c + eps);
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
             const int cv = lane + i * 32;

@@ -67,6 +67,12 @@ __device__ __forceinline__ void bulk_store_s2g(void* gptr, uint32_t smem_addr, u
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gptr), "r"(smem_addr), "r"(bytes)
                  : "memory");
 }
+// 1-D bulk copy global -> shared (async proxy); completes `bytes` of transaction count on `bar`. 16-byte aligned.
+__device__ __forceinline__ void bulk_load_g2s(uint32_t smem_addr, const void* gptr, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr),
+                 "l"(gptr), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -209,12 +215,31 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {  // one MUFU.RCP (<= 1 ulp); __frcp_rn adds a range check,
+    float y;                                            // a branch to a slow path and two Newton FMAs per element
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// 2^x on the FMA / ALU pipes (r2-prep, never run): round-to-nearest split x = i + f, f in [-0.5, 0.5], cubic for 2^f
+// (max relative error 1.1e-4, far below the bf16 the attention probabilities are rounded to), exponent add through the
+// integer bits of the magic-number sum. Offloads a fraction of the softmax exponentials from the MUFU pipe (16 / clk / SM),
+// which bounds the head-dim-40 attention (profiles/r01_ncu_attention_l0_v25.txt: XU pipe 56 %, tensor pipe 20 %).
+// Domain: x <= 127 (the kernel's arguments are <= 8); x < -126 is clamped (result ~1e-38, i.e. zero for the row sum).
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -126.0f);
+    const float r = x + 12582912.0f;   // 1.5 * 2^23: the integer part lands in the low mantissa bits
+    const float f = x - (r - 12582912.0f);
+    float p = fmaf(0.054592825f, f, 0.24221784f);
+    p = fmaf(p, f, 0.6933686f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
 // erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 the result is rounded to): one rcp, one ex2
 // and six FMAs instead of libdevice erff's ~25 instructions — the GEGLU epilogue of the FF GEMMs (M x 4C gates per
 // layer) was bound by erff issue slots, not by the tensor pipe.
 __device__ __forceinline__ float erf_fast(float x) {
     const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));  // argument in [1, inf]: no denormal / zero cases
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);

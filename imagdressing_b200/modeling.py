@@ -15,6 +15,7 @@ processor registration). Architecture: SURVEY.md Appendix A (diffusers 0.24.0, r
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -56,6 +57,38 @@ def skip_default_init():
         nn.Linear.reset_parameters, nn.Conv2d.reset_parameters = saved
 
 
+# LayerNorm folded into the consuming GEMMs of the transformer blocks. Off by default
+# until validated on hardware; tests flip the module attribute.
+FOLD_LN = os.environ.get("IMAGD_FOLD_LN", "0") == "1"
+
+
+def fold_layernorm(w: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor):
+    """LN(x) W^T + b == rstd * (x W'^T - mean * colsum(W')) + b'  with  W' = W diag(gamma), b' = b + W beta.
+    Returns (W' bf16 [N, K], b' fp32 [N], colsum fp32 [N]); colsum is taken over the ROUNDED W' the tensor core sees."""
+    w32 = w.detach().float()
+    wp = (w32 * gamma.detach().float()[None, :]).to(BF16).contiguous()
+    bp = w32 @ beta.detach().float()
+    if b is not None:
+        bp = bp + b.detach().float()
+    return wp, bp.contiguous(), wp.float().sum(1).contiguous()
+
+
+class _RowStats:
+    """Per-module row-statistics buffers at stable addresses (one per LayerNorm site and row count)."""
+
+    def __init__(self):
+        self._bufs: Dict[tuple, tuple] = {}
+
+    def get(self, site: str, M: int, C: int, device) -> tuple:
+        key = (site, M, str(device))
+        hit = self._bufs.get(key)
+        if hit is None:
+            parts = ops.gemm_tile_count_n(M, C, C)
+            hit = (torch.zeros(M, parts, 2, device=device, dtype=torch.float32), parts)
+            self._bufs[key] = hit
+        return hit
+
+
 def _f32(p: torch.Tensor) -> torch.Tensor:
     return p.detach().float().contiguous()
 
@@ -68,6 +101,31 @@ def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
     """[Cout, Cin, 3, 3] -> tap-major [Cout, 9*Cin] bf16."""
     co, ci = w.shape[:2]
     return w.detach().permute(0, 2, 3, 1).reshape(co, 9 * ci).to(BF16).contiguous()
+
+
+# Upsample2D + conv as four 2x2 phase convs on the low-resolution input (DESIGN.md section 8 item 4). Off by default.
+UPCONV_PHASE = os.environ.get("IMAGD_UPCONV_PHASE", "0") == "1"
+
+
+def pack_upconv3x3(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> phase weight matrix [4*Cout, 4*Cin] bf16 for nearest-2x upsample followed by the conv:
+    output pixel (2y+py, 2x+px) = sum over taps (ty, tx) of Wp[py,px,ty,tx] . in[y+py-1+ty, x+px-1+tx], where
+    Wp sums the 3x3 taps (ky, kx) whose upsampled source pixel floor((2y+py+ky-1)/2) is that input row (same for x):
+    py = 0: ty 0 <- ky {0}, ty 1 <- ky {1, 2};  py = 1: ty 0 <- ky {0, 1}, ty 1 <- ky {2}."""
+    co, ci = w.shape[:2]
+    w32 = w.detach().float()
+    sel = {(0, 0): [0], (0, 1): [1, 2], (1, 0): [0, 1], (1, 1): [2]}  # (phase bit, tap bit) -> 3x3 indices
+    out = torch.zeros(4, co, 4, ci, dtype=torch.float32, device=w.device)
+    for py in (0, 1):
+        for px in (0, 1):
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    acc = 0
+                    for ky in sel[(py, ty)]:
+                        for kx in sel[(px, tx)]:
+                            acc = acc + w32[:, :, ky, kx]
+                    out[py * 2 + px, :, ty * 2 + tx, :] = acc
+    return out.reshape(4 * co, 4 * ci).to(BF16).contiguous()
 
 
 def pack_geglu(w: torch.Tensor, b: torch.Tensor):
@@ -114,6 +172,9 @@ class Attention(nn.Module):
         self.scale = (query_dim // heads) ** -0.5
         self._pk: Dict[str, torch.Tensor] = {}
         self._fused_residual: Optional[torch.Tensor] = None  # set by BasicTransformerBlock, consumed by our processors
+        # LayerNorm fold handshake (same protocol): (LnFold-less tuple) set by the block when hidden_states is the RAW
+        # stream: (stats, parts, gamma, beta, eps, stats_out_for_my_output | None); consumed by attention_forward
+        self._ln_fold = None
         from .processors import AttnProcessor2_0
 
         self.processor = AttnProcessor2_0()
@@ -186,7 +247,16 @@ class BasicTransformerBlock(nn.Module, _Packed):
             self._pk = dict(
                 ln=[(_f32(n.weight), _f32(n.bias)) for n in (self.norm1, self.norm2, self.norm3)],
                 w1=w1, b1=b1, w2=_bf(self.ff.net[2].weight), b2=_f32(self.ff.net[2].bias))
+            if FOLD_LN:  # norm3 folded into the GEGLU projection: fold first, then interleave value / gate rows
+                proj = self.ff.net[0].proj
+                wf = proj.weight.detach().float() * self.norm3.weight.detach().float()[None, :]
+                bf = proj.bias.detach().float() + proj.weight.detach().float() @ self.norm3.bias.detach().float()
+                w1f, b1f = pack_geglu(wf, bf)
+                self._pk.update(w1f=w1f, b1f=b1f, c1f=w1f.float().sum(1).contiguous())
         return self._pk
+
+    def _can_fold(self) -> bool:
+        return FOLD_LN and all(getattr(a.processor, "_accepts_ln_fold", False) for a in (self.attn1, self.attn2))
 
     def _attend(self, attn: Attention, normed, residual, ctx, kw):
         attn._fused_residual = residual
@@ -196,9 +266,30 @@ class BasicTransformerBlock(nn.Module, _Packed):
         attn._fused_residual = None  # foreign processor: add here (bf16)
         return ops.concat_add(out.to(BF16).contiguous(), None, res_a=residual)
 
-    def run(self, x: torch.Tensor, ctx, kw) -> torch.Tensor:
-        """x: [B, L, C] bf16. x += attn1(LN(x)); x += attn2(LN(x), ctx); x += FF(LN(x))  (SURVEY.md A.2)."""
+    def _attend_folded(self, attn: Attention, x, ctx, kw, stats, parts, norm: nn.LayerNorm, stats_next):
+        attn._fused_residual = x
+        attn._ln_fold = (stats, parts, norm.weight, norm.bias, norm.eps, stats_next)
+        out = attn(x, encoder_hidden_states=ctx, **kw)
+        if attn._ln_fold is not None or attn._fused_residual is not None:
+            attn._ln_fold = attn._fused_residual = None
+            raise RuntimeError("processor advertised _accepts_ln_fold but did not consume the LayerNorm fold")
+        return out
+
+    def run(self, x: torch.Tensor, ctx, kw, x_stats=None) -> torch.Tensor:
+        """x: [B, L, C] bf16. x += attn1(LN(x)); x += attn2(LN(x), ctx); x += FF(LN(x))  (SURVEY.md A.2).
+        x_stats = (stats, parts) of x's rows when the producing GEMM emitted them (LayerNorm fold)."""
         pk = self._packed()
+        if x_stats is not None and self._can_fold():
+            B, L, C = x.shape
+            if not hasattr(self, "_row_stats"):
+                self._row_stats = _RowStats()
+            s1, p1 = self._row_stats.get("x1", B * L, C, x.device)
+            s2, p2 = self._row_stats.get("x2", B * L, C, x.device)
+            x1 = self._attend_folded(self.attn1, x, None, kw, x_stats[0], x_stats[1], self.norm1, s1)
+            x2 = self._attend_folded(self.attn2, x1, ctx, kw, s1, p1, self.norm2, s2)
+            h = ops.gemm(x2, pk["w1f"], bias=pk["b1f"], act=ACT_GEGLU,
+                         ln=ops.LnFold(s2, p2, C, self.norm3.eps, pk["c1f"]))
+            return ops.gemm(h, pk["w2"], bias=pk["b2"], residual=x2)
         x = self._attend(self.attn1, ops.layernorm(x, *pk["ln"][0]), x, None, kw)
         x = self._attend(self.attn2, ops.layernorm(x, *pk["ln"][1]), x, ctx, kw)
         h = ops.gemm(ops.layernorm(x, *pk["ln"][2]), pk["w1"], bias=pk["b1"], act=ACT_GEGLU)
@@ -231,9 +322,15 @@ class Transformer2DModel(nn.Module, _Packed):
         pk = self._packed()
         NB, H, W, C = x.shape
         h = ops.groupnorm(x, *pk["gn"], self.groups, 1e-6, silu=False)
-        h = ops.gemm(h, pk["wi"], bias=pk["bi"]).view(NB, H * W, C)
+        x_stats = None
+        if FOLD_LN and all(b._can_fold() for b in self.transformer_blocks):
+            if not hasattr(self, "_row_stats"):
+                self._row_stats = _RowStats()
+            x_stats = self._row_stats.get("x0", NB * H * W, C, x.device)
+        h = ops.gemm(h, pk["wi"], bias=pk["bi"], stats_out=None if x_stats is None else x_stats[0]).view(NB, H * W, C)
         for blk in self.transformer_blocks:
-            h = blk.run(h, ctx, kw)
+            h = blk.run(h, ctx, kw, x_stats)
+            x_stats = None  # (SD1.5 has one block per Transformer2DModel; a second one would need FF-out statistics)
         return ops.gemm(h.view(NB, H, W, C), pk["wo"], bias=pk["bo"], residual=x)
 
 
@@ -309,6 +406,10 @@ class Upsample2D(nn.Module, _Packed):
     def run(self, x):
         if self._pk is None:
             self._pk = dict(w=pack_conv3x3(self.conv.weight), b=_f32(self.conv.bias))
+            if UPCONV_PHASE and x.shape[-1] % 64 == 0:
+                self._pk["wp"] = pack_upconv3x3(self.conv.weight)
+        if "wp" in self._pk and UPCONV_PHASE:
+            return ops.upconv3x3(x, self._pk["wp"], bias=self._pk["b"])
         return ops.conv3x3(ops.upsample2x(x), self._pk["w"], bias=self._pk["b"])
 
 

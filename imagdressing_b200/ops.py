@@ -36,6 +36,25 @@ def _rows2d(t: torch.Tensor) -> Tuple[int, int, int]:
     return rows, t.shape[-1], t.shape[-1]
 
 
+class LnFold:
+    """LayerNorm folded into the consuming GEMM (include/imagd_b200.h): `stats` [M, ld, 2] fp32
+    holds the producer's per-row {sum, sum of squares} partials (`parts` of them), `colsum` [N] the column sums of the
+    gamma-scaled weight; the GEMM's `bias` must be the folded bias b + W beta."""
+
+    __slots__ = ("stats", "parts", "dim", "eps", "colsum")
+
+    def __init__(self, stats: torch.Tensor, parts: int, dim: int, eps: float, colsum: torch.Tensor):
+        self.stats, self.parts, self.dim, self.eps, self.colsum = stats, int(parts), int(dim), float(eps), colsum
+
+
+def gemm_tile_count_n(M: int, N: int, K: int) -> int:
+    """How many row-statistics partials a producer GEMM of this shape writes per row."""
+    n = _lib.load().imagd_gemm_tile_count_n(int(M), int(N), int(K))
+    if n <= 0:
+        _lib.check(n if n < 0 else -1, "imagd_gemm_tile_count_n")
+    return n
+
+
 def _epilogue(bias, rowvec, rows_per_group, residual, act, alpha, out_fp32) -> Epilogue:
     ep = Epilogue()
     ep.bias = _ptr(bias)
@@ -52,8 +71,10 @@ def _epilogue(bias, rowvec, rows_per_group, residual, act, alpha, out_fp32) -> E
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, out: Optional[torch.Tensor] = None, bias=None, rowvec=None,
          rows_per_group: int = 0, residual=None, act: int = ACT_NONE, alpha: float = 1.0,
-         out_fp32: bool = False) -> torch.Tensor:
-    """out[M, N] = epilogue(a[M, K] @ w[N, K]^T); a / w / residual bf16, bias / rowvec fp32."""
+         out_fp32: bool = False, stats_out: Optional[torch.Tensor] = None, ln: Optional[LnFold] = None) -> torch.Tensor:
+    """out[M, N] = epilogue(a[M, K] @ w[N, K]^T); a / w / residual bf16, bias / rowvec fp32.
+    stats_out [M, ld, 2] fp32: also emit per-row {sum, sum of squares} of the rounded outputs, one slot per N tile.
+    ln: the rows of `a` are the RAW input of a LayerNorm that has been folded into `w` / `bias` (LnFold)."""
     lib = _lib.load()
     M, K, lda = _rows2d(a)
     N, Kw = w.shape
@@ -63,6 +84,20 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, out: Optional[torch.Tensor] = None
         out = torch.empty(*a.shape[:-1], n_out, device=a.device, dtype=torch.float32 if out_fp32 else BF16)
     ldd = _rows2d(out)[2]
     ep = _epilogue(bias, rowvec, rows_per_group, residual, act, alpha, out_fp32)
+    if stats_out is not None:
+        assert stats_out.dtype == torch.float32 and stats_out.dim() == 3 and stats_out.shape[0] == M and \
+            stats_out.shape[2] == 2 and stats_out.is_contiguous()
+        ep.row_stats_out = stats_out.data_ptr()
+        ep.stats_ld = stats_out.shape[1]
+    if ln is not None:
+        assert ln.stats.dtype == torch.float32 and ln.stats.shape[0] == M and ln.stats.is_contiguous() and ln.dim == K
+        assert ln.colsum.dtype == torch.float32 and ln.colsum.numel() == N and bias is not None
+        ep.row_stats_in = ln.stats.data_ptr()
+        ep.stats_in_ld = ln.stats.shape[1]
+        ep.stats_parts = ln.parts
+        ep.ln_dim = ln.dim
+        ep.ln_eps = ln.eps
+        ep.colsum = ln.colsum.data_ptr()
     rc = lib.imagd_gemm_bf16(a.data_ptr(), lda, w.data_ptr(), w.stride(0), out.data_ptr(), ldd, M, N, K,
                              ctypes.byref(ep), _stream())
     _lib.check(rc, "imagd_gemm_bf16")
@@ -83,6 +118,22 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, out: Optional[torch.Tensor] = N
     rc = lib.imagd_conv3x3_bf16(x.data_ptr(), Cin, NB, H, W, Cin, w.data_ptr(), out.data_ptr(), out.shape[-1], Cout,
                                 ctypes.byref(ep), _stream())
     _lib.check(rc, "imagd_conv3x3_bf16")
+    return out
+
+
+def upconv3x3(x: torch.Tensor, w_phase: torch.Tensor, *, bias=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Upsample2D (nearest 2x) + 3x3 conv as four 2x2 phase convs on the low-resolution input (modeling.pack_upconv3x3).
+    x: [NB, H, W, Cin] bf16, w_phase: [4*Cout, 4*Cin] bf16 -> [NB, 2H, 2W, Cout]."""
+    lib = _lib.load()
+    NB, H, W, Cin = x.shape
+    assert x.is_contiguous() and x.dtype == BF16 and w_phase.dtype == BF16 and w_phase.shape[1] == 4 * Cin
+    Cout = w_phase.shape[0] // 4
+    if out is None:
+        out = torch.empty(NB, 2 * H, 2 * W, Cout, device=x.device, dtype=BF16)
+    ep = _epilogue(bias, None, 0, None, ACT_NONE, 1.0, False)
+    rc = lib.imagd_upconv3x3_bf16(x.data_ptr(), Cin, NB, H, W, Cin, w_phase.data_ptr(), out.data_ptr(), out.shape[-1], Cout,
+                                  ctypes.byref(ep), _stream())
+    _lib.check(rc, "imagd_upconv3x3_bf16")
     return out
 
 

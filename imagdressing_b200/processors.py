@@ -96,6 +96,10 @@ def _flat(t: torch.Tensor) -> torch.Tensor:
 class _ProcState:
     """Mixin: caches owned by a processor instance."""
 
+    # processors built on attention_forward can take the RAW residual stream + row statistics instead of the
+    # LayerNorm output (Attention._ln_fold); the garment tap (CacheAttnProcessor2_0) needs the normed tensor itself
+    _accepts_ln_fold = True
+
     def _init_state(self):
         self._ctx_memo = TensorMemo()   # context tensor -> bf16 copy
         self._kv_memo = TensorMemo()    # context tensor -> projected K|V
@@ -126,19 +130,42 @@ def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_st
     hd = C // heads
     x = as_bf16(hidden_states)
     lkey = f"{id(proc)}:{lora_scale}" if lora else "base"
+    fold = getattr(attn, "_ln_fold", None)  # (stats, parts, gamma, beta, eps, stats_out): hidden_states is the RAW stream
+    stats_out = None
+    if fold is not None:
+        attn._ln_fold = None  # consumed
+        f_stats, f_parts, f_gamma, f_beta, f_eps, stats_out = fold
+
+        def folded(key, build_w):
+            """(W' bf16, b' fp32, colsum fp32) of a projection that reads LN(hidden_states)."""
+            from .modeling import fold_layernorm
+
+            pk = attn.packed("ln:" + key, lambda: fold_layernorm(build_w(), None, f_gamma, f_beta))
+            return pk, ops.LnFold(f_stats, f_parts, C, f_eps, pk[2])
 
     if encoder_hidden_states is None and prepare_only:
         q2 = s0 = None
     elif encoder_hidden_states is None:
-        wqkv = attn.packed("qkv:" + lkey, lambda: torch.cat(
+        build_qkv = lambda: torch.cat(
             [_merged(attn.to_q, lora and lora["q"], lora_scale), _merged(attn.to_k, lora and lora["k"], lora_scale),
-             _merged(attn.to_v, lora and lora["v"], lora_scale)], 0).to(BF16).contiguous())
-        qkv = ops.gemm(x, wqkv)  # [B, L, 3C]
+             _merged(attn.to_v, lora and lora["v"], lora_scale)], 0)
+        if fold is not None:
+            (wf, bf_, _), ln = folded("qkv:" + lkey, build_qkv)
+            qkv = ops.gemm(x, wf, bias=bf_, ln=ln)
+        else:
+            wqkv = attn.packed("qkv:" + lkey, lambda: build_qkv().to(BF16).contiguous())
+            qkv = ops.gemm(x, wqkv)  # [B, L, 3C]
         q2 = _flat(qkv[..., :C])
         s0 = ops.kv_stream(_flat(qkv[..., C:2 * C]), _flat(qkv[..., 2 * C:]), L)
     else:
-        wq = attn.packed("q:" + lkey, lambda: _merged(attn.to_q, lora and lora["q"], lora_scale).to(BF16).contiguous())
-        q2 = None if prepare_only else _flat(ops.gemm(x, wq))
+        build_q = lambda: _merged(attn.to_q, lora and lora["q"], lora_scale)
+        if prepare_only:
+            q2 = None
+        elif fold is not None:
+            (wf, bf_, _), ln = folded("q:" + lkey, build_q)
+            q2 = _flat(ops.gemm(x, wf, bias=bf_, ln=ln))
+        else:
+            q2 = _flat(ops.gemm(x, attn.packed("q:" + lkey, lambda: build_q().to(BF16).contiguous())))
         ctx_src = encoder_hidden_states
         Lc = ctx_src.shape[1] if text_len is None else text_len
         kv = proc._kv_memo.get(ctx_src, (lkey, Lc))
@@ -177,8 +204,10 @@ def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_st
     residual = attn._fused_residual
     if residual is not None and residual.dtype == BF16 and residual.shape == hidden_states.shape:
         attn._fused_residual = None  # consumed: fused into the out-projection epilogue
-        y = ops.gemm(o, wo, bias=bo, residual=residual.reshape(B * L, C))
+        y = ops.gemm(o, wo, bias=bo, residual=residual.reshape(B * L, C), stats_out=stats_out)
     else:
+        if stats_out is not None:
+            raise RuntimeError("LayerNorm fold needs the residual fused into the out-projection (bf16 stream)")
         y = ops.gemm(o, wo, bias=bo)
     y = y.view(B, L, C)
     return y if in_dtype == BF16 else y.to(in_dtype)

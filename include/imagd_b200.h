@@ -51,6 +51,18 @@ typedef struct imagd_epilogue {
     int64_t ldr;
     float alpha;            /* 1.0f for plain */
     int32_t out_fp32;       /* 0: bf16 output, 1: fp32 output */
+    /* ---- LayerNorm folding (r2-prep). The GEMM that WRITES the residual stream emits, per
+     * output row and per N tile of that launch, {sum, sum of squares} of its bf16-rounded outputs (producer); the GEMM
+     * that follows the LayerNorm reads the raw stream and applies  rstd * (alpha * acc - mean * colsum[c]) + bias[c]
+     * (consumer), with W' = W * diag(gamma) as its weight, colsum[c] = sum_k W'[c, k] and bias = b + W beta. */
+    float* row_stats_out;       /* producer: [M, stats_ld] float2 (slot = N-tile index); NULL = off. act NONE, bf16 out only */
+    int64_t stats_ld;           /* in float2 units, >= imagd_gemm_tile_count_n(...) of the producing launch */
+    const float* row_stats_in;  /* consumer: [M, stats_in_ld] float2 partials of the A operand's rows; NULL = off */
+    int64_t stats_in_ld;
+    int32_t stats_parts;        /* partials per row to add up (the producer's N-tile count) */
+    int32_t ln_dim;             /* C of the folded LayerNorm (= K of this GEMM) */
+    float ln_eps;
+    const float* colsum;        /* consumer: [N] fp32 */
 } imagd_epilogue;
 
 /* D[M,N] = A[M,K] * W[N,K]^T (+ epilogue).  tcgen05 tensor cores, TMA-fed, fp32 accumulation in TMEM.
@@ -71,6 +83,15 @@ int imagd_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void
  * the distinct problems issued ("taps NB H W Cin N geglu m_tiles kb_total out_fp32" per line), 0 stops, -1 leaves
  * the state; when `out` is given the recorded lines are copied there. Returns the number of lines. */
 int imagd_gemm_debug_force(int block_n, int stages, int splits);
+/* r2-prep: Upsample2D (nearest 2x) + its 3x3 conv in one implicit GEMM over the LOW-resolution input: four 2x2 "phase"
+ * convolutions (output pixel (2y+py, 2x+px) sees input rows {y+py-1, y+py} and columns {x+px-1, x+px}); Wt is the
+ * phase weight matrix [4*Cout, 4*Cin]: row = phase*Cout + co (phase = py*2+px), column = tap*Cin + ci (tap = ty*2+tx),
+ * value = sum of the 3x3 taps (ky, kx) that land on that input pixel. X: [NB,H,W,ldx] -> Y: [NB,2H,2W,ldy]. Bias only. */
+int imagd_upconv3x3_bf16(const void* X, int64_t ldx, int NB, int H, int W, int Cin, const void* Wt, void* Y, int64_t ldy,
+                         int Cout, const imagd_epilogue* ep, imagd_stream stream);
+/* Number of N tiles imagd_gemm_bf16 will use for an [M, K] x [N, K]^T problem with a plain (LINEAR) epilogue - the
+ * number of row-statistics partials a producer launch writes per row (depends on the table-driven tile choice). */
+int imagd_gemm_tile_count_n(int M, int N, int K);
 int imagd_gemm_debug_log(int enable, char* out, int out_bytes);
 /* Profiling hook: while `device_buf` is non-NULL every GEMM/conv CTA writes 8 x u64 at device_buf[cta_linear * 8]:
  * clock64 at {kernel entry, prologue done, first operand tile landed, last MMA issued, accumulator ready, epilogue done},

@@ -27,11 +27,23 @@ def _store(y, out):
     return y
 
 
+TILE = 160  # emulated N tile of a row-statistics producer
+
+
+def gemm_tile_count_n(M, N, K):
+    return (N + TILE - 1) // TILE
+
+
 def gemm(a, w, *, out=None, bias=None, rowvec=None, rows_per_group=0, residual=None, act=ACT_NONE, alpha=1.0,
-         out_fp32=False):
+         out_fp32=False, stats_out=None, ln=None):
     lead = a.shape[:-1]
     y = alpha * (a.reshape(-1, a.shape[-1]).float() @ w.float().T)
-    if bias is not None:
+    if ln is not None:  # LayerNorm folded into this GEMM: rstd * (acc - mean * colsum) + folded bias
+        s = ln.stats[:, :ln.parts].sum(1)
+        mean = s[:, 0] / ln.dim
+        rstd = torch.rsqrt((s[:, 1] / ln.dim - mean * mean).clamp_min(0) + ln.eps)
+        y = rstd[:, None] * (y - mean[:, None] * ln.colsum[None, :]) + bias.float()[None, :]
+    elif bias is not None:
         y = y + bias.float()[None, :]
     if rowvec is not None:
         y = y + rowvec.float()[torch.arange(y.shape[0]) // rows_per_group]
@@ -42,6 +54,12 @@ def gemm(a, w, *, out=None, bias=None, rowvec=None, rows_per_group=0, residual=N
         y = _act(y, act)
     if residual is not None:
         y = y + residual.reshape(-1, residual.shape[-1]).float()
+    if stats_out is not None:  # per-row {sum, sum of squares} of the ROUNDED outputs, one slot per N tile
+        yr = y.to(BF).float()
+        stats_out.zero_()
+        for i, c in enumerate(range(0, yr.shape[1], TILE)):
+            stats_out[:, i, 0] = yr[:, c:c + TILE].sum(1)
+            stats_out[:, i, 1] = (yr[:, c:c + TILE] ** 2).sum(1)
     y = y.reshape(*lead, y.shape[-1])
     return _store(y if out_fp32 else y.to(BF), out)
 
@@ -60,6 +78,23 @@ def conv3x3(x, w, *, out=None, bias=None, rowvec=None, residual=None, act=ACT_NO
     if residual is not None:
         y = y + residual.float()
     return _store(y.to(BF).contiguous(), out)
+
+
+def upconv3x3(x, w_phase, *, bias=None, out=None):
+    """Four 2x2 phase convs with the kernel's conventions: phase = py*2+px, tap = ty*2+tx reads (y+py-1+ty, x+px-1+tx)."""
+    NB, H, W, Cin = x.shape
+    Cout = w_phase.shape[0] // 4
+    xin = F.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1))  # zero frame: input row -1 / H, column -1 / W
+    wp = w_phase.float().view(4, Cout, 4, Cin)
+    y = torch.zeros(NB, Cout, 2 * H, 2 * W)
+    for py in (0, 1):
+        for px in (0, 1):
+            k = wp[py * 2 + px].view(Cout, 2, 2, Cin).permute(0, 3, 1, 2)  # [Cout, Cin, ty, tx]
+            win = xin[:, :, py:py + H + 1, px:px + W + 1]  # rows y+py-1 .. y+py (shifted by the pad of 1)
+            y[:, :, py::2, px::2] = F.conv2d(win, k)
+    if bias is not None:
+        y = y + bias.float()[None, :, None, None]
+    return _store(y.permute(0, 2, 3, 1).to(BF).contiguous(), out)
 
 
 def conv3x3_direct(x, w, bias, *, stride=1, act=ACT_NONE, out_nchw_f32=False, add=None, out=None):
@@ -176,5 +211,5 @@ def install(monkeypatch):
 
     for name in ("gemm", "conv3x3", "conv3x3_direct", "groupnorm", "layernorm", "kv_stream", "attention", "concat_add",
                  "upsample2x", "im2col3x3_s2", "nchw_f32_to_nhwc_bf16", "timestep_embedding", "linear_small_m",
-                 "cfg_ddim_step"):
+                 "cfg_ddim_step", "gemm_tile_count_n", "upconv3x3"):
         monkeypatch.setattr(ops, name, globals()[name])

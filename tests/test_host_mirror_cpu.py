@@ -19,11 +19,15 @@ def rel(a, b):
     return float((a.float() - b.float()).norm() / b.float().norm())
 
 
-@pytest.fixture
-def emu(monkeypatch):
+@pytest.fixture(params=[(False, False), (True, False), (True, True)], ids=["plain", "ln_fold", "ln_fold+upconv_phase"])
+def emu(monkeypatch, request):
+    """Every test runs with the round-1 path, with LayerNorm folded into the consuming GEMMs, and with the upsample convs
+    as phase convs on top."""
     emulated_ops.install(monkeypatch)
     from imagdressing_b200 import modeling
 
+    monkeypatch.setattr(modeling, "FOLD_LN", request.param[0])
+    monkeypatch.setattr(modeling, "UPCONV_PHASE", request.param[1])
     return modeling
 
 

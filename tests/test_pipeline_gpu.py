@@ -28,21 +28,21 @@ def build(dev, controlnet=False):
     from oracle import processors as op
     from oracle import unet as ou
 
-    o, p = ou.UNet2DConditionModel(), modeling.UNet2DConditionModel()
+    with modeling.skip_default_init():  # every parameter is overwritten by init_synthetic_ below
+        o, p = ou.UNet2DConditionModel(), modeling.UNet2DConditionModel()
+        ro, rp = ou.UNet2DConditionModel(), modeling.UNet2DConditionModel()
+        co, cp = (ou.ControlNetModel(), modeling.ControlNetModel()) if controlnet else (None, None)
     o.set_attn_processor({n: (op.RefSAttnProcessor(n, hidden_of(n), scale=1.0) if "attn1" in n else op.CAttnProcessor(n))
                           for n in o.attn_processors})
     p.set_attn_processor({n: (RefSAttnProcessor2_0(n, hidden_of(n)) if "attn1" in n else CAttnProcessor2_0(n, hidden_of(n), 768))
                           for n in p.attn_processors})
-    ro, rp = ou.UNet2DConditionModel(), modeling.UNet2DConditionModel()
     ro.set_attn_processor({n: op.CacheAttnProcessor() for n in ro.attn_processors})
     rp.set_attn_processor({n: CacheAttnProcessor2_0() for n in rp.attn_processors})
     for m, seed in ((o, 0), (ro, 1)):
         ou.init_synthetic_(m, seed)
     for m, seed in ((p, 0), (rp, 1)):
         modeling.init_synthetic_(m, seed)
-    co = cp = None
     if controlnet:
-        co, cp = ou.ControlNetModel(), modeling.ControlNetModel()
         ou.init_synthetic_(co, 2)
         modeling.init_synthetic_(cp, 2)
         co, cp = co.to(dev).eval(), cp.to(dev).eval()
@@ -125,17 +125,18 @@ def test_ipa_controlnet_pipeline_with_face_tokens(cuda_device):
     from oracle.pipeline import sample_one
 
     dev = cuda_device
-    o, p = ou.UNet2DConditionModel(), modeling.UNet2DConditionModel()
+    with modeling.skip_default_init():
+        o, p = ou.UNet2DConditionModel(), modeling.UNet2DConditionModel()
+        ro, rp = ou.UNet2DConditionModel(), modeling.UNet2DConditionModel()
+        co, cp = ou.ControlNetModel(), modeling.ControlNetModel()
     o.set_attn_processor({n: (op.LoraRefSAttnProcessor(n, hidden_of(n), rank=16, lora_scale=0.2, scale=0.9) if "attn1" in n
                               else op.LoRAIPAttnProcessor(hidden_of(n), 768, rank=16, lora_scale=0.3, scale=0.8, num_tokens=4))
                           for n in o.attn_processors})
     p.set_attn_processor({n: (LoraRefSAttnProcessor2_0(n, hidden_of(n), rank=16) if "attn1" in n
                               else LoRAIPAttnProcessor2_0(hidden_of(n), 768, rank=16, num_tokens=4))
                           for n in p.attn_processors})
-    ro, rp = ou.UNet2DConditionModel(), modeling.UNet2DConditionModel()
     ro.set_attn_processor({n: op.CacheAttnProcessor() for n in ro.attn_processors})
     rp.set_attn_processor({n: CacheAttnProcessor2_0() for n in rp.attn_processors})
-    co, cp = ou.ControlNetModel(), modeling.ControlNetModel()
     for m, seed in ((o, 0), (ro, 1), (co, 2)):
         ou.init_synthetic_(m, seed)
     for m, seed in ((p, 0), (rp, 1), (cp, 2)):

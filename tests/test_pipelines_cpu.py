@@ -21,11 +21,12 @@ def rel(a, b):
     return float((a.float() - b.float()).norm() / b.float().norm())
 
 
-@pytest.fixture
-def emu(monkeypatch):
+@pytest.fixture(params=[False, True], ids=["plain", "ln_fold"])
+def emu(monkeypatch, request):
     emulated_ops.install(monkeypatch)
     from imagdressing_b200 import modeling
 
+    monkeypatch.setattr(modeling, "FOLD_LN", request.param)
     return modeling
 
 

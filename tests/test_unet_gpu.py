@@ -18,7 +18,8 @@ def build_pair(dev, seed=0, with_ref=True):
     from oracle import processors as op
     from oracle import unet as ou
 
-    o, p = ou.UNet2DConditionModel(), modeling.UNet2DConditionModel()
+    with modeling.skip_default_init():  # every parameter is overwritten by init_synthetic_ below
+        o, p = ou.UNet2DConditionModel(), modeling.UNet2DConditionModel()
     if with_ref:
         po, pp = {}, {}
         for name in p.attn_processors.keys():
