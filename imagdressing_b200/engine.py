@@ -78,13 +78,30 @@ class DenoiseEngine:
         _lib.launch_count += g["launches"]
         return g["sa"]
 
+    # ------------------------------------------------------------------ what a captured step graph froze
+    def _frozen_signature(self) -> tuple:
+        """Everything a captured step graph bakes in besides shapes: the processors' mutable scales (`scale` is a host
+        float in the kernel's KV-stream struct, `lora_scale` selects the merged q/out weights) and the identity +
+        in-place version of every weight (packed / LoRA-merged copies are separate device buffers). A second call
+        with a different `image_scale` / `ipa_scale` / `s_lora_scale` / `c_lora_scale`, or after a
+        `load_state_dict`, must not replay the old graph."""
+        sig = []
+        for model in (self.unet, self.controlnet):
+            if model is None:
+                continue
+            for name, proc in model.attn_processors.items():
+                sig.append((getattr(proc, "scale", None), getattr(proc, "lora_scale", None)))
+            sig.append(sum(p._version for p in model.parameters()))
+            sig.append(next(model.parameters()).data_ptr())  # .to() / re-assignment
+        return tuple(sig)
+
     # ------------------------------------------------------------------ one step
-    def _step(self, st):
+    def _step(self, st, use_control: bool = True):
         n = st["n"]
         lat = st["latents"]
         table = (st["t_table"], st["step_ptr"])
         down = mid = None
-        if self.controlnet is not None and st.get("control_cond") is not None:
+        if use_control and self.controlnet is not None and st.get("control_cond") is not None:
             down, mid = self.controlnet(lat, None, st["control_text"], st["control_cond"],
                                         conditioning_scale=st["control_scale"], return_dict=False,
                                         timestep_table=table, sample_repeat=2)
@@ -128,9 +145,11 @@ class DenoiseEngine:
                control_prompt_embeds: Optional[torch.Tensor] = None, control_negative_embeds: Optional[torch.Tensor] = None,
                control_scale: float = 1.0, mask: Optional[torch.Tensor] = None,
                image_latents: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
-               callback=None) -> torch.Tensor:
+               callback=None, control_keep: Optional[List[float]] = None) -> torch.Tensor:
         """latents [n,4,h,w] (scaled by init_noise_sigma = 1); embeds [n,T,768] (or [1,T,768], broadcast).
-        Returns the final latents as a new fp32 tensor."""
+        control_keep: per-step 0/1 ControlNet guidance window (`controlnet_keep` of
+        IMAGDressing_v1_pipeline_ipa_controlnet.py:584-590,643-649); steps with 0 run the UNet without residuals (what
+        a zero conditioning scale computes) from a second captured graph. Returns the final latents as a new fp32 tensor."""
         dev = latents.device
         n = latents.shape[0]
         sch = self.scheduler
@@ -146,7 +165,10 @@ class DenoiseEngine:
         has_control = self.controlnet is not None and control_cond is not None
         key = (n, tuple(latents.shape[1:]), prompt_embeds.shape[1], has_control, mask is not None,
                float(guidance_scale), float(control_scale), bool(sa_hidden_states), id(t_table),
-               tuple(control_cond.shape) if has_control else None)
+               tuple(control_cond.shape) if has_control else None, self._frozen_signature())
+        keep = [1.0] * S if control_keep is None or not has_control else [float(k) for k in control_keep]
+        if len(keep) != S or any(k not in (0.0, 1.0) for k in keep):
+            raise ValueError("control_keep must hold one 0/1 entry per step")
         st = self._states.get(key)
         if st is None:
             f32 = dict(device=dev, dtype=torch.float32)
@@ -154,7 +176,7 @@ class DenoiseEngine:
                       text=torch.empty(2 * n, prompt_embeds.shape[1], prompt_embeds.shape[2], device=dev, dtype=torch.bfloat16),
                       guidance=float(guidance_scale), coef=coef, t_table=t_table,
                       step_ptr=torch.zeros(2, dtype=torch.int32, device=dev),
-                      eps=torch.empty(2 * n, *latents.shape[1:], **f32), kwargs={}, graph=None)
+                      eps=torch.empty(2 * n, *latents.shape[1:], **f32), kwargs={}, graph=None, graph_nc=None)
             if has_control:
                 cp = control_prompt_embeds if control_prompt_embeds is not None else prompt_embeds
                 st.update(control_cond=torch.empty(control_cond.shape, **f32), control_scale=float(control_scale),
@@ -192,7 +214,7 @@ class DenoiseEngine:
 
         if not self.use_cuda_graph or callback is not None:
             for i in range(S):
-                self._step(st)
+                self._step(st, use_control=keep[i] > 0)
                 if callback is not None:
                     callback(i, int(timesteps[i]), lat)
             return lat.clone()
@@ -214,7 +236,20 @@ class DenoiseEngine:
             st["graph_launches"] = _lib.launch_count - before
             _lib.launch_count = before  # capture launched nothing
             st["graph"] = graph
-        for _ in range(S):
-            st["graph"].replay()
-        _lib.launch_count += S * st["graph_launches"]
+        if min(keep) == 0.0 and st["graph_nc"] is None:  # steps outside the ControlNet window: no-residual graph
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            before = _lib.launch_count
+            with torch.cuda.graph(graph):
+                self._step(st, use_control=False)
+            st["graph_nc_launches"] = _lib.launch_count - before
+            _lib.launch_count = before
+            st["graph_nc"] = graph
+        for i in range(S):
+            if keep[i] > 0:
+                st["graph"].replay()
+                _lib.launch_count += st["graph_launches"]
+            else:
+                st["graph_nc"].replay()
+                _lib.launch_count += st["graph_nc_launches"]
         return lat.clone()

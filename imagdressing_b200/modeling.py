@@ -565,25 +565,45 @@ class _ModelBase(nn.Module):
         return cls(**{**(config or {}), **kw})
 
     @classmethod
-    def from_pretrained(cls, path, subfolder: Optional[str] = None, torch_dtype=None, **kw):
-        """Local directory with config.json (+ optional diffusion_pytorch_model.safetensors). Offline only."""
+    def from_pretrained(cls, path, subfolder: Optional[str] = None, torch_dtype=None, allow_random_init: bool = False,
+                        **kw):
+        """Local directory with config.json + diffusion_pytorch_model{,.fp16}.safetensors (or .bin). Offline only.
+        A directory without a weight file raises FileNotFoundError — a silently random-initialised UNet samples noise —
+        unless `allow_random_init=True` (synthetic-weight tests / benchmarks)."""
         import json
         import os
 
         d = os.path.join(path, subfolder) if subfolder else path
+        if not os.path.isdir(d):
+            raise FileNotFoundError(f"{cls.__name__}.from_pretrained: no such directory {d!r} (offline: local paths only)")
         cfg = {}
         cj = os.path.join(d, "config.json")
         if os.path.exists(cj):
             raw = json.load(open(cj))
             cfg = {k: (tuple(v) if isinstance(v, list) else v) for k, v in raw.items() if k in SD15_CONFIG}
-        model = cls(**cfg)
-        for fn in ("diffusion_pytorch_model.safetensors", "diffusion_pytorch_model.fp16.safetensors"):
+        with skip_default_init():
+            model = cls(**cfg)
+        loaded = False
+        for fn in ("diffusion_pytorch_model.safetensors", "diffusion_pytorch_model.fp16.safetensors",
+                   "diffusion_pytorch_model.bin", "diffusion_pytorch_model.fp16.bin"):
             fp = os.path.join(d, fn)
             if os.path.exists(fp):
-                from safetensors.torch import load_file
+                if fn.endswith(".safetensors"):
+                    from safetensors.torch import load_file
 
-                model.load_state_dict(load_file(fp))
+                    sd = load_file(fp)
+                else:
+                    sd = torch.load(fp, map_location="cpu", weights_only=True)
+                model.load_state_dict(sd)
+                loaded = True
                 break
+        if not loaded:
+            if not allow_random_init:
+                raise FileNotFoundError(f"{cls.__name__}.from_pretrained: no diffusion_pytorch_model(.fp16).safetensors / "
+                                        f".bin under {d!r}; pass allow_random_init=True for synthetic weights")
+            for mod in model.modules():  # skip_default_init left torch.empty parameters
+                if isinstance(mod, (nn.Linear, nn.Conv2d)):
+                    mod.reset_parameters()
         if torch_dtype is not None:
             model = model.to(dtype=torch_dtype)
         return model

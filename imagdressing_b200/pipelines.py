@@ -37,6 +37,46 @@ def randn_tensor(shape, generator=None, device=None, dtype=torch.float32):
     return torch.randn(shape, generator=generator, device=device, dtype=dtype)
 
 
+def _control_window(guess_mode, start, end):
+    """Scalar (start, end) of the ControlNet guidance window; a one-element list is what diffusers normalises a single
+    ControlNet's arguments to (ipa_controlnet.py:443-461)."""
+    if guess_mode:
+        raise NotImplementedError("guess_mode=True: every reference script runs guess_mode=False (the pose pipelines "
+                                  "cannot even evaluate it, SURVEY.md B14); the cond-only ControlNet pass is not built")
+    one = lambda v: float(v[0] if isinstance(v, (list, tuple)) else v)
+    start, end = one(start), one(end)
+    if not 0.0 <= start <= end <= 1.0:
+        raise ValueError(f"control guidance window [{start}, {end}] must satisfy 0 <= start <= end <= 1")
+    return start, end
+
+
+def _image_batch(image, width, height, *, gray: bool = False) -> torch.Tensor:
+    """PIL image(s) / HWC uint8-or-float arrays / CHW tensors -> float32 [n, 3|1, height, width] in [0, 1], resized
+    with lanczos as diffusers-0.24 `VaeImageProcessor(resample="lanczos")` does for PIL input (tensors are resized
+    bilinearly like its tensor path)."""
+    import numpy as np
+
+    if torch.is_tensor(image):
+        t = image.float()
+        t = t[None] if t.dim() == 3 else t
+        if gray and t.shape[1] == 3:
+            t = (0.299 * t[:, 0:1] + 0.587 * t[:, 1:2] + 0.114 * t[:, 2:3])
+        if tuple(t.shape[-2:]) != (height, width):
+            t = torch.nn.functional.interpolate(t, size=(height, width), mode="bilinear", align_corners=False)
+        return t
+    from PIL import Image
+
+    imgs = list(image) if isinstance(image, (list, tuple)) else [image]
+    out = []
+    for im in imgs:
+        if isinstance(im, np.ndarray):
+            im = Image.fromarray((im * 255).round().astype("uint8") if im.dtype.kind == "f" else im)
+        im = im.convert("L" if gray else "RGB").resize((width, height), resample=Image.LANCZOS)
+        a = np.asarray(im).astype("float32") / 255.0
+        out.append(a[None] if gray else a.transpose(2, 0, 1))
+    return torch.from_numpy(np.stack(out))
+
+
 class _DressingPipelineBase:
     """Shared implementation; subclasses fix the constructor signature and which side paths are active."""
 
@@ -153,14 +193,22 @@ class _DressingPipelineBase:
             latents = latents.to(device=device, dtype=torch.float32)
         return latents * self.scheduler.init_noise_sigma
 
-    def _garment_tokens(self, ref_clip_image, garment_tokens, device, dtype):
+    def _garment_tokens(self, ref_clip_image, garment_tokens, device, dtype, prompt_embeds=None):
         """CLIP-vision penultimate hidden states -> ImgProj (Resampler) -> [n,16,768]
         (IMAGDressing_v1_pipeline.py:407-415). The null-image branch is not needed: the reference discards index 0
-        of the garment pass (B2)."""
+        of the garment pass (B2).
+
+        `ref_clip_image is None` (reference :416-427): the reference calls
+        `encode_prompt(null_prompt, ..., prompt_embeds=prompt_embeds, ...)` with the ALREADY ENCODED prompt embeddings,
+        and diffusers' encode_prompt only tokenises when `prompt_embeds is None` — so `null_prompt` is never encoded and
+        the garment UNet's text slot (index 1 of `cat([negative, null_prompt_embeds])`, :432-435) is the positive
+        prompt's [n,77,768] embedding. Reproduced as is (quirk B19)."""
         if garment_tokens is not None:
             return garment_tokens
         if ref_clip_image is None:
-            raise ValueError("pass ref_clip_image (with an image_encoder) or garment_tokens")
+            if prompt_embeds is None:
+                raise ValueError("pass ref_clip_image (with an image_encoder), garment_tokens, or a prompt")
+            return prompt_embeds
         if self.image_encoder is None:
             raise ValueError("no image_encoder: pass garment_tokens")
         hs = self.image_encoder(ref_clip_image.to(device, dtype=dtype), output_hidden_states=True).hidden_states[-2]
@@ -195,7 +243,8 @@ class _DressingPipelineBase:
              return_dict=True, clip_skip=None, callback=None, prompt_embeds=None, negative_prompt_embeds=None,
              cross_attention_kwargs=None, latents=None, garment_tokens=None, ref_image_latents=None,
              # ControlNet
-             control_image=None, controlnet_conditioning_scale=1.0,
+             control_image=None, controlnet_conditioning_scale=1.0, control_guidance_start=0.0,
+             control_guidance_end=1.0,
              # IP-Adapter
              face_tokens=None, face_null_tokens=None,
              # inpainting
@@ -227,12 +276,19 @@ class _DressingPipelineBase:
 
         latents = self.prepare_latents(n, self.unet.config.in_channels, width, height, torch.float32, device, generator,
                                        latents)
-        gtok = self._garment_tokens(ref_clip_image, garment_tokens, device, prompt_embeds.dtype)
+        gtok = self._garment_tokens(ref_clip_image, garment_tokens, device, prompt_embeds.dtype, control_pe)
+        if gtok.shape[0] != n:
+            gtok = gtok.expand(n, -1, -1)
         ref_lat = self._ref_latents(ref_image, ref_image_latents, device)
         sa = self._engine.garment_features(ref_lat, gtok)
 
+        keep = None
+        if control_image is not None and (control_guidance_start != 0.0 or control_guidance_end != 1.0):
+            T = len(timesteps)  # controlnet_keep, ipa_controlnet.py:584-590 / inpainting.py:373-379
+            keep = [1.0 - float(i / T < control_guidance_start or (i + 1) / T > control_guidance_end) for i in range(T)]
         out = self._engine.sample(
             latents, prompt_embeds, negative_prompt_embeds, sa, guidance_scale, len(timesteps), timesteps=timesteps,
+            control_keep=keep,
             control_cond=control_image, control_prompt_embeds=control_pe, control_negative_embeds=control_ne,
             control_scale=controlnet_conditioning_scale, mask=mask, image_latents=image_latents, noise=noise,
             callback=callback)
@@ -287,11 +343,7 @@ class IMAGDressing_v1_ControlNet(_DressingPipelineBase):
         """Pose image -> [n,3,H,W] in [0,1] (StableDiffusionControlNetPipeline.prepare_image, do_normalize=False)."""
         if torch.is_tensor(image):
             return image.to(device=device, dtype=torch.float32)
-        import numpy as np
-
-        imgs = image if isinstance(image, (list, tuple)) else [image]
-        arr = np.stack([np.asarray(i.convert("RGB").resize((width, height))) for i in imgs]).astype("float32") / 255.0
-        return torch.from_numpy(arr).permute(0, 3, 1, 2).to(device)
+        return _image_batch(image, width, height).to(device)  # control_image_processor: lanczos, no normalisation
 
     def __call__(self, prompt, null_prompt, negative_prompt, ref_image, width, height, num_inference_steps,
                  guidance_scale, pose_image=None, ref_clip_image=None, num_images_per_prompt=1, image_scale=1.0,
@@ -301,8 +353,7 @@ class IMAGDressing_v1_ControlNet(_DressingPipelineBase):
                  controlnet_conditioning_scale: Union[float, List[float]] = 1.0, guess_mode: bool = False,
                  control_guidance_start=0.0, control_guidance_end=1.0, latents=None, garment_tokens=None,
                  ref_image_latents=None, **kwargs):
-        assert not guess_mode and control_guidance_start == 0.0 and control_guidance_end == 1.0, \
-            "the reference scripts use guess_mode=False and the full control window"
+        start, end = _control_window(guess_mode, control_guidance_start, control_guidance_end)
         self.set_scale(image_scale)
         ctrl = self.prepare_image(pose_image, width, height, self._execution_device) if pose_image is not None else None
         return self._run(prompt=prompt, negative_prompt=negative_prompt, ref_image=ref_image, width=width, height=height,
@@ -312,7 +363,8 @@ class IMAGDressing_v1_ControlNet(_DressingPipelineBase):
                          callback=callback, prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds,
                          cross_attention_kwargs=cross_attention_kwargs, latents=latents, garment_tokens=garment_tokens,
                          ref_image_latents=ref_image_latents, control_image=ctrl,
-                         controlnet_conditioning_scale=float(controlnet_conditioning_scale))
+                         controlnet_conditioning_scale=float(controlnet_conditioning_scale),
+                         control_guidance_start=start, control_guidance_end=end)
 
 
 # ====================================================================================================== IPA + ControlNet
@@ -386,7 +438,7 @@ class IMAGDressing_v1_IPAControlNet(IMAGDressing_v1_ControlNet):
                  controlnet_conditioning_scale: Union[float, List[float]] = 1.0, guess_mode: bool = False,
                  control_guidance_start=0.0, control_guidance_end=1.0, latents=None, garment_tokens=None,
                  ref_image_latents=None, face_clip_embeds=None, face_tokens=None, face_null_tokens=None, **kwargs):
-        assert not guess_mode
+        start, end = _control_window(guess_mode, control_guidance_start, control_guidance_end)
         has_face = faceid_embeds is not None or face_tokens is not None
         if has_face:  # :433-438
             self.set_scale(image_scale, lora_scale=s_lora_scale)
@@ -405,7 +457,7 @@ class IMAGDressing_v1_IPAControlNet(IMAGDressing_v1_ControlNet):
                          cross_attention_kwargs=cross_attention_kwargs, latents=latents, garment_tokens=garment_tokens,
                          ref_image_latents=ref_image_latents, control_image=ctrl,
                          controlnet_conditioning_scale=float(controlnet_conditioning_scale), face_tokens=face_tokens,
-                         face_null_tokens=face_null_tokens)
+                         face_null_tokens=face_null_tokens, control_guidance_start=start, control_guidance_end=end)
 
 
 # ====================================================================================================== inpainting
@@ -423,20 +475,33 @@ class IMAGDressing_v1_ControlNetInpaint(IMAGDressing_v1_ControlNet):
                  cross_attention_kwargs=None, controlnet_conditioning_scale: Union[float, List[float]] = 0.5,
                  guess_mode: bool = False, control_guidance_start=0.0, control_guidance_end=1.0, clip_skip=None,
                  garment_tokens=None, ref_image_latents=None, image_latents=None, mask_latents=None, **kwargs):
-        assert not guess_mode
+        cg_start, cg_end = _control_window(guess_mode, control_guidance_start, control_guidance_end)
         dev = self._execution_device
         self.set_scale(image_scale)
         ctrl = self.prepare_image(control_image, width, height, dev) if control_image is not None else None
         if image_latents is None:
             if self.vae is None:
                 raise ValueError("no vae: pass image_latents and mask_latents")
-            img = image.to(device=dev, dtype=self.vae.dtype)
-            image_latents = (self.vae.encode(img).latent_dist.mean * self.vae.config.scaling_factor).float()
+            if height is None or width is None:
+                raise ValueError("height and width are required to preprocess `image`")
+            # image_processor.preprocess (:301-304): resize to (height, width), [0,1] -> [-1,1]
+            img = (_image_batch(image, width, height) * 2.0 - 1.0).to(device=dev, dtype=self.vae.dtype)
+            dist = self.vae.encode(img).latent_dist  # _encode_vae_image: latent_dist.sample(generator) * scaling_factor
+            z = dist.sample(generator) if hasattr(dist, "sample") else dist.mean
+            image_latents = (z * self.vae.config.scaling_factor).float()
         n = image_latents.shape[0]
         h, w = image_latents.shape[-2:]
         if mask_latents is None:
-            m = mask_image.to(device=dev, dtype=torch.float32)
-            mask_latents = torch.nn.functional.interpolate(m, size=(h, w))  # prepare_mask_latents (:352-362)
+            # mask_processor.preprocess (:306-308): grayscale, resize, binarise at 0.5; prepare_mask_latents (:352-362)
+            # then resizes to the latent grid with F.interpolate's default nearest mode
+            m = _image_batch(mask_image, w * self.vae_scale_factor, h * self.vae_scale_factor, gray=True)
+            m = (m >= 0.5).to(device=dev, dtype=torch.float32)
+            mask_latents = torch.nn.functional.interpolate(m, size=(h, w))
+        if ctrl is not None and tuple(ctrl.shape[-2:]) != (h * self.vae_scale_factor, w * self.vae_scale_factor):
+            raise ValueError(f"control_image {tuple(ctrl.shape[-2:])} does not match the image "
+                             f"{(h * self.vae_scale_factor, w * self.vae_scale_factor)}")
+        if mask_latents.shape[0] != n:
+            mask_latents = mask_latents.expand(n, -1, -1, -1)
         noise = randn_tensor(image_latents.shape, generator=generator, device=dev) if latents is None else latents.to(dev)
         # is_strength_max: pure noise start; else add_noise(image_latents, noise, t_start) (inherited prepare_latents)
         self.scheduler.set_timesteps(num_inference_steps, device=dev)
@@ -455,4 +520,5 @@ class IMAGDressing_v1_ControlNetInpaint(IMAGDressing_v1_ControlNet):
                          cross_attention_kwargs=cross_attention_kwargs, latents=start, garment_tokens=garment_tokens,
                          ref_image_latents=ref_image_latents, control_image=ctrl,
                          controlnet_conditioning_scale=float(controlnet_conditioning_scale), mask=mask_latents,
-                         image_latents=image_latents, strength=strength, noise=noise)
+                         image_latents=image_latents, strength=strength, noise=noise, control_guidance_start=cg_start,
+                         control_guidance_end=cg_end)

@@ -87,6 +87,42 @@ def _merged(lin: nn.Linear, lora, lora_scale: float) -> torch.Tensor:
     return w
 
 
+def _ver(*mods) -> tuple:
+    """Identity + in-place version of every weight a derived (packed) tensor is built from: `load_state_dict`,
+    `copy_` and optimizer steps bump `_version`, `.to()` / re-assignment change `data_ptr` (a reference-style
+    `ModuleList(unet.attn_processors.values()).load_state_dict(...)` must not leave stale packed weights behind)."""
+    out = []
+    for m in mods:
+        if m is None:
+            continue
+        for w in ((m.weight,) if hasattr(m, "weight") else (m.down.weight, m.up.weight)):
+            out.append((w.data_ptr(), w._version))
+        b = getattr(m, "bias", None)
+        if b is not None:
+            out.append((b.data_ptr(), b._version))
+    return tuple(out)
+
+
+def _packer(proc, attn):
+    """packed(key, build, ver) -> derived tensor, cached per (attention module, key) and rebuilt when `ver` changes
+    (one entry per key: an old lora_scale / weight version is evicted, not accumulated). The cache lives on our own
+    `modeling.Attention` (cleared by its `_apply` / `invalidate_packed`); on a FOREIGN host module — e.g. a stock
+    diffusers `Attention`, which has no such cache — it lives on the processor, keyed by the host's id."""
+    store = getattr(attn, "_pk", None)
+    if not isinstance(store, dict) or not hasattr(attn, "packed"):
+        store = proc.__dict__.setdefault("_foreign_pk", {}).setdefault(id(attn), {})
+
+    def packed(key, build, ver=()):
+        hit = store.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        val = build()
+        store[key] = (ver, val)
+        return val
+
+    return packed
+
+
 def _flat(t: torch.Tensor) -> torch.Tensor:
     """[B, L, C] -> [B*L, C] view (keeps a column-slice's row stride)."""
     B, L, C = t.shape
@@ -109,6 +145,7 @@ class _ProcState:
     def invalidate_packed(self):
         for m in (self._ctx_memo, self._kv_memo, self._kv2_memo, self._g_memo):
             m.clear()
+        self.__dict__.pop("_foreign_pk", None)
 
 
 def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor], *,
@@ -129,53 +166,56 @@ def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_st
     heads = attn.heads
     hd = C // heads
     x = as_bf16(hidden_states)
-    lkey = f"{id(proc)}:{lora_scale}" if lora else "base"
+    packed = _packer(proc, attn)
+    lq, lk, lv, lo = ((lora["q"], lora["k"], lora["v"], lora["out"]) if lora else (None,) * 4)
+    ls = float(lora_scale) if lora else 0.0
+    lkey = f"{id(proc)}" if lora else "base"
+    v_q, v_k, v_v = _ver(attn.to_q, lq) + (ls,), _ver(attn.to_k, lk) + (ls,), _ver(attn.to_v, lv) + (ls,)
     fold = getattr(attn, "_ln_fold", None)  # (stats, parts, gamma, beta, eps, stats_out): hidden_states is the RAW stream
     stats_out = None
     if fold is not None:
         attn._ln_fold = None  # consumed
         f_stats, f_parts, f_gamma, f_beta, f_eps, stats_out = fold
+        v_ln = ((f_gamma.data_ptr(), f_gamma._version), (f_beta.data_ptr(), f_beta._version))
 
-        def folded(key, build_w):
+        def folded(key, build_w, ver):
             """(W' bf16, b' fp32, colsum fp32) of a projection that reads LN(hidden_states)."""
             from .modeling import fold_layernorm
 
-            pk = attn.packed("ln:" + key, lambda: fold_layernorm(build_w(), None, f_gamma, f_beta))
+            pk = packed("ln:" + key, lambda: fold_layernorm(build_w(), None, f_gamma, f_beta), ver + v_ln)
             return pk, ops.LnFold(f_stats, f_parts, C, f_eps, pk[2])
 
     if encoder_hidden_states is None and prepare_only:
         q2 = s0 = None
     elif encoder_hidden_states is None:
         build_qkv = lambda: torch.cat(
-            [_merged(attn.to_q, lora and lora["q"], lora_scale), _merged(attn.to_k, lora and lora["k"], lora_scale),
-             _merged(attn.to_v, lora and lora["v"], lora_scale)], 0)
+            [_merged(attn.to_q, lq, ls), _merged(attn.to_k, lk, ls), _merged(attn.to_v, lv, ls)], 0)
         if fold is not None:
-            (wf, bf_, _), ln = folded("qkv:" + lkey, build_qkv)
+            (wf, bf_, _), ln = folded("qkv:" + lkey, build_qkv, v_q + v_k + v_v)
             qkv = ops.gemm(x, wf, bias=bf_, ln=ln)
         else:
-            wqkv = attn.packed("qkv:" + lkey, lambda: build_qkv().to(BF16).contiguous())
+            wqkv = packed("qkv:" + lkey, lambda: build_qkv().to(BF16).contiguous(), v_q + v_k + v_v)
             qkv = ops.gemm(x, wqkv)  # [B, L, 3C]
         q2 = _flat(qkv[..., :C])
         s0 = ops.kv_stream(_flat(qkv[..., C:2 * C]), _flat(qkv[..., 2 * C:]), L)
     else:
-        build_q = lambda: _merged(attn.to_q, lora and lora["q"], lora_scale)
+        build_q = lambda: _merged(attn.to_q, lq, ls)
         if prepare_only:
             q2 = None
         elif fold is not None:
-            (wf, bf_, _), ln = folded("q:" + lkey, build_q)
+            (wf, bf_, _), ln = folded("q:" + lkey, build_q, v_q)
             q2 = _flat(ops.gemm(x, wf, bias=bf_, ln=ln))
         else:
-            q2 = _flat(ops.gemm(x, attn.packed("q:" + lkey, lambda: build_q().to(BF16).contiguous())))
+            q2 = _flat(ops.gemm(x, packed("q:" + lkey, lambda: build_q().to(BF16).contiguous(), v_q)))
         ctx_src = encoder_hidden_states
         Lc = ctx_src.shape[1] if text_len is None else text_len
-        kv = proc._kv_memo.get(ctx_src, (lkey, Lc))
+        kv = proc._kv_memo.get(ctx_src, (lkey, Lc, v_k, v_v))
         if kv is None:
-            wkv = attn.packed("kv:" + lkey, lambda: torch.cat(
-                [_merged(attn.to_k, lora and lora["k"], lora_scale), _merged(attn.to_v, lora and lora["v"], lora_scale)],
-                0).to(BF16).contiguous())
+            wkv = packed("kv:" + lkey, lambda: torch.cat([_merged(attn.to_k, lk, ls), _merged(attn.to_v, lv, ls)],
+                                                         0).to(BF16).contiguous(), v_k + v_v)
             ctx = as_bf16(ctx_src, proc._ctx_memo)
             buf = proc._kv_memo.reusable((*ctx.shape[:-1], 2 * C))
-            kv = proc._kv_memo.put(ctx_src, ops.gemm(ctx, wkv, out=buf), (lkey, Lc))  # [B, Lctx, 2C]
+            kv = proc._kv_memo.put(ctx_src, ops.gemm(ctx, wkv, out=buf), (lkey, Lc, v_k, v_v))  # [B, Lctx, 2C]
         # per-sample row stride stays the full context length; only the first Lc keys are visited
         s0 = _stream_from_kv(kv, C, Lc)
 
@@ -183,12 +223,13 @@ def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_st
     if second is not None:
         src, to_k, to_v, out_scale, n_q = second[:5]
         first = second[5] if len(second) > 5 else 0
-        kv2 = proc._kv2_memo.get(src, id(to_k))
+        v_2 = _ver(to_k, to_v)
+        kv2 = proc._kv2_memo.get(src, v_2)
         if kv2 is None:
-            w2 = attn.packed(f"kv2:{id(to_k)}", lambda: torch.cat([_w(to_k), _w(to_v)], 0).to(BF16).contiguous())
+            w2 = packed(f"kv2:{id(to_k)}", lambda: torch.cat([_w(to_k), _w(to_v)], 0).to(BF16).contiguous(), v_2)
             src_bf = as_bf16(src, proc._g_memo)
             buf = proc._kv2_memo.reusable((*src_bf.shape[:-1], 2 * C))
-            kv2 = proc._kv2_memo.put(src, ops.gemm(src_bf, w2, out=buf), id(to_k))
+            kv2 = proc._kv2_memo.put(src, ops.gemm(src_bf, w2, out=buf), v_2)
         bcast = kv2.shape[0] == 1 and n_q > 1
         if not bcast and kv2.shape[0] < n_q:
             raise ValueError(f"second KV stream has batch {kv2.shape[0]} but {n_q} query samples use it")
@@ -199,9 +240,12 @@ def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_st
 
     o = ops.attention(q2, B, L, heads, hd, s0, s1)  # [B*L, C]
 
-    wo = attn.packed("o:" + lkey, lambda: _merged(attn.to_out[0], lora and lora["out"], lora_scale).to(BF16).contiguous())
-    bo = attn.packed("bo", lambda: attn.to_out[0].bias.detach().float().contiguous())
-    residual = attn._fused_residual
+    out_lin = attn.to_out[0]
+    wo = packed("o:" + lkey, lambda: _merged(out_lin, lo, ls).to(BF16).contiguous(), _ver(out_lin, lo) + (ls,))
+    bo = packed("bo", lambda: out_lin.bias.detach().float().contiguous(), _ver(out_lin))
+    # our own Attention offers the transformer block's residual for the out-projection epilogue; a foreign host module
+    # (stock diffusers Attention) has no such attribute: the block adds the residual itself, as diffusers does
+    residual = getattr(attn, "_fused_residual", None)
     if residual is not None and residual.dtype == BF16 and residual.shape == hidden_states.shape:
         attn._fused_residual = None  # consumed: fused into the out-projection epilogue
         y = ops.gemm(o, wo, bias=bo, residual=residual.reshape(B * L, C), stats_out=stats_out)

@@ -12,8 +12,9 @@ from .ddim import DDIMOracle
 @torch.no_grad()
 def sample_one(unet, ref_unet, latents, prompt_embeds, negative_embeds, garment_tokens, ref_latents, guidance, steps,
                controlnet=None, control_cond=None, control_scale=1.0, control_text=None, mask=None,
-               image_latents=None, noise=None):
-    """One image. latents [1,4,h,w]; embeds [1,T,768]; garment_tokens [1,16,768]; returns final latents."""
+               image_latents=None, noise=None, control_guidance_start=0.0, control_guidance_end=1.0):
+    """One image. latents [1,4,h,w]; embeds [1,T,768]; garment_tokens [1,16,768]; returns final latents.
+    control_guidance_start / _end: the `controlnet_keep` window (ipa_controlnet.py:584-590, applied :643-649)."""
     sch = DDIMOracle()
     sch.set_timesteps(steps, device=latents.device)
     ts = sch.timesteps
@@ -25,8 +26,9 @@ def sample_one(unet, ref_unet, latents, prompt_embeds, negative_embeds, garment_
         down_c = mid_c = down_u = mid_u = None
         if controlnet is not None:  # ipa_controlnet.py:651-666 — batch-2 call, [uncond, cond] text
             ct_c, ct_u = control_text if control_text is not None else (prompt_embeds, negative_embeds)
+            keep = 1.0 - float(i / len(ts) < control_guidance_start or (i + 1) / len(ts) > control_guidance_end)
             down, mid = controlnet(torch.cat([latents] * 2), t, torch.cat([ct_u, ct_c]), control_cond,
-                                   conditioning_scale=control_scale)
+                                   conditioning_scale=control_scale * keep)
             down_c, mid_c = [d[1:2] for d in down], mid[1:2]
             down_u, mid_u = [d[0:1] for d in down], mid[0:1]
         eps_c = unet(latents, t, prompt_embeds, cross_attention_kwargs={"sa_hidden_states": sa},

@@ -3,6 +3,8 @@ state_dict keys and isinstance behaviour of the drop-in modules, plus the opt-in
 import inspect
 import json
 import os
+
+import pytest
 import subprocess
 import sys
 
@@ -101,5 +103,19 @@ def test_diffusers_stand_in_is_opt_in(tmp_path):
               open(cfg_dir / "config.json", "w"))
     from imagdressing_b200.modeling import UNet2DConditionModel
 
-    u = UNet2DConditionModel.from_pretrained(str(tmp_path), subfolder="unet", torch_dtype=torch.float16)
+    with pytest.raises(FileNotFoundError):  # a directory without weights must not silently yield a random UNet
+        UNet2DConditionModel.from_pretrained(str(tmp_path), subfolder="unet")
+    u = UNet2DConditionModel.from_pretrained(str(tmp_path), subfolder="unet", torch_dtype=torch.float16,
+                                             allow_random_init=True)
     assert u.dtype == torch.float16 and u.config.block_out_channels == (32, 64, 64, 64)
+    # weights round-trip through both supported file formats
+    from safetensors.torch import save_file
+
+    sd = {k: v.float().contiguous() for k, v in u.state_dict().items()}
+    save_file(sd, str(cfg_dir / "diffusion_pytorch_model.safetensors"))
+    u2 = UNet2DConditionModel.from_pretrained(str(tmp_path), subfolder="unet")
+    assert all(torch.equal(u2.state_dict()[k], v) for k, v in sd.items())
+    os.remove(cfg_dir / "diffusion_pytorch_model.safetensors")
+    torch.save(sd, str(cfg_dir / "diffusion_pytorch_model.bin"))
+    u3 = UNet2DConditionModel.from_pretrained(str(tmp_path), subfolder="unet")
+    assert all(torch.equal(u3.state_dict()[k], v) for k, v in sd.items())
