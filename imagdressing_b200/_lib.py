@@ -133,6 +133,58 @@ def check(rc: int, what: str) -> None:
         raise ImagdError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
 
 
+class _ProfiledLib:
+    """Proxy over the loaded library that brackets every launching C-ABI call with CUDA events on the current stream
+    (bench.py's live per-kernel step shares; never active on a production path). Keys = symbol + small integer
+    arguments (shapes), so launches group by kernel and problem size."""
+
+    def __init__(self, lib, records):
+        self._lib, self._records = lib, records
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if name not in LAUNCHES:
+            return fn
+        import torch
+
+        def wrapped(*args):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            key = name + "(" + ",".join(str(a) for a in args if isinstance(a, int) and 0 <= a < 1000000) + ")"
+            self._records.append((key, e0, e1))
+            return rc
+
+        return wrapped
+
+
+class profile_launches:
+    """with profile_launches() as rec: ...eager kernels...  -> rec.by_key() = {key: (launches, total_ms)}."""
+
+    def __enter__(self):
+        global _lib
+        self._saved = load()
+        self._records = []
+        _lib = _ProfiledLib(self._saved, self._records)
+        return self
+
+    def __exit__(self, *exc):
+        global _lib
+        _lib = self._saved
+        return False
+
+    def by_key(self):
+        import torch
+
+        torch.cuda.synchronize()
+        out = {}
+        for key, e0, e1 in self._records:
+            n, ms = out.get(key, (0, 0.0))
+            out[key] = (n + 1, ms + e0.elapsed_time(e1))
+        return out
+
+
 def require_b200() -> None:
     rc = load().imagd_device_check()
     if rc < 0:

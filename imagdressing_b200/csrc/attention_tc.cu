@@ -22,6 +22,18 @@
 //   warp 8     TMA producer (K/V ring)
 //   warp 9     TMEM allocator + tcgen05.mma issuer:  S = Q K^T  (128x128xhd),  O_s += P V (128xhdx128)
 // TMEM columns: S [0,128), O_0 [128, +O_STRIDE), O_1 after it. Two CTAs per SM at head_dim 40 / 64.
+//
+// PT = true (head_dim 40 / 64, the two-CTAs-per-SM configurations): the probabilities never touch shared memory. Each
+// softmax thread packs its 64 exponentials to bf16 pairs and writes them with tcgen05.st over the first 64 columns of
+// its own S row (P aliases S), and P.V is a tcgen05.mma with the A operand in tensor memory. The round-1 profile of the
+// smem-P kernel (profiles/r01_ncu_attention_l0_v25.txt + the raw report) showed why: 15.2 M shared-store wavefronts +
+// 13.4 M tensor-core shared reads per launch (~60 % of the L1 data pipe), half of them P, and the MUFU.EX2 instructions
+// stalling on the MIO queue behind the 16-byte P stores. With P in TMEM the hot loop has no shared-memory store and no
+// generic->async proxy fence. S(i+1) = Q K(i+1)^T then has to follow P.V(i) (it overwrites P); the tensor-pipe gap
+// that leaves is covered by the second CTA on the SM.
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -44,7 +56,7 @@ struct AttnParams {
 
 constexpr int kAtomBytes = 128 * 128;  // one [128 rows x 64 bf16] swizzled tile
 
-template <int HD_MMA, int NATOM, int KV_STAGES>
+template <int HD_MMA, int NATOM, int KV_STAGES, bool PT>
 struct AttnCfg {
     static constexpr int kOStride = (HD_MMA + 63) / 64 * 64;
     static constexpr int kTmemNeed = 128 + 2 * kOStride;
@@ -53,19 +65,21 @@ struct AttnCfg {
     static constexpr int kKOff = kQBytes;
     static constexpr int kVOff = kKOff + KV_STAGES * NATOM * kAtomBytes;
     static constexpr int kPOff = kVOff + KV_STAGES * NATOM * kAtomBytes;
-    static constexpr int kBarOff = kPOff + 2 * kAtomBytes;
+    static constexpr int kPBytes = PT ? 2048 : 2 * kAtomBytes;  // PT: only the epilogue's row-sum exchange lives here
+    static constexpr int kBarOff = kPOff + kPBytes;
     static constexpr int kNumBars = 1 + 3 * KV_STAGES + 5;  // q, k/v/empty per stage, s_full, p_full, o_full, s_free, pv_done
     static constexpr int kMxOff = kBarOff + kNumBars * 8 + 16;  // [2 halves][128 rows] bf16 partial row maxima
     static constexpr int kTotal = kMxOff + 512;
 };
 
-template <int HD_MMA, int NATOM, int KV_STAGES>
-__global__ void __launch_bounds__(320, (AttnCfg<HD_MMA, NATOM, KV_STAGES>::kTmemCols <= 256 &&
-                                        AttnCfg<HD_MMA, NATOM, KV_STAGES>::kTotal <= 113 * 1024) ? 2 : 1)
+template <int HD_MMA, int NATOM, int KV_STAGES, bool PT>
+__global__ void __launch_bounds__(320, (AttnCfg<HD_MMA, NATOM, KV_STAGES, PT>::kTmemCols <= 256 &&
+                                        AttnCfg<HD_MMA, NATOM, KV_STAGES, PT>::kTotal <= 113 * 1024) ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                     const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
                     const __grid_constant__ CUtensorMap tmV1, const AttnParams p) {
-    using C = AttnCfg<HD_MMA, NATOM, KV_STAGES>;
+    using C = AttnCfg<HD_MMA, NATOM, KV_STAGES, PT>;
+    static_assert(!PT || C::kTmemCols == 256, "P-in-TMEM is built for the two-CTAs-per-SM configurations");
     // HD_MMA == 48 only serves head_dim 40: columns 40..47 of every V tile are TMA zero fill. Column 40 is set to 1.0
     // in shared memory, so O[:, 40] accumulates sum(P) on the tensor core — with exactly the bf16 rounding and the
     // rescaling the output columns see — and the softmax warps neither add up nor exchange row sums.
@@ -163,7 +177,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // S(i+1) = Q K(i+1)^T is issued as soon as the softmax warps hold S(i) in registers (s_free), so the tensor
         // core computes it underneath softmax(i); P.V(i) follows when P(i) is written. With a one-stage K/V ring
         // (head_dim 160) the next K tile only lands after P.V(i) frees the slot, so QK(i+1) keeps the old order there.
-        constexpr bool kEarly = KV_STAGES > 1;
+        constexpr bool kEarly = KV_STAGES > 1 && !PT;  // PT: S(i+1) overwrites P(i), so it is issued behind P.V(i)
         auto issue_qk = [&](int i) {
             const int st = i % KV_STAGES;
             mbar_wait(&k_full[st], (i / KV_STAGES) & 1);
@@ -215,16 +229,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const uint32_t o_addr = tmem_O + s * C::kOStride;
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
-                    const uint32_t poff = (ks / 4) * kAtomBytes + (ks % 4) * 32;
-                    umma_bf16(o_addr, umma_smem_desc_sw128(p_addr + poff, 16, 1024),
-                              umma_smem_desc_sw128(v_addr + ks * 2048, kAtomBytes, 1024), idesc_o,
-                              (j > 0 || ks > 0) ? 1u : 0u);
+                    if constexpr (PT) {  // A = P[:, 16 ks .. 16 ks + 15] = 8 packed columns of the S region
+                        umma_bf16_ts(o_addr, tmem_S + ks * 8, umma_smem_desc_sw128(v_addr + ks * 2048, kAtomBytes, 1024),
+                                     idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+                    } else {
+                        const uint32_t poff = (ks / 4) * kAtomBytes + (ks % 4) * 32;
+                        umma_bf16(o_addr, umma_smem_desc_sw128(p_addr + poff, 16, 1024),
+                                  umma_smem_desc_sw128(v_addr + ks * 2048, kAtomBytes, 1024), idesc_o,
+                                  (j > 0 || ks > 0) ? 1u : 0u);
+                    }
                 }
                 umma_commit(&kv_empty[st]);
                 umma_commit(pv_done);
                 if (!kEarly && i + 1 < T) {
-                    mbar_wait(s_free, i & 1);  // (already complete: P(i) was written after S(i) was read)
-                    issue_qk(i + 1);
+                    if constexpr (!PT) mbar_wait(s_free, i & 1);  // (already complete: P(i) was written after S(i) was read)
+                    issue_qk(i + 1);  // PT: the tensor pipe runs it behind P.V(i), which is done with P by then
                 }
             }
             __syncwarp();
@@ -264,8 +283,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             tmem_ld32(tmem_S + lane_addr + half * 64, va);
             tmem_ld32(tmem_S + lane_addr + half * 64 + 32, vb);
             tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(s_free);  // my 64 scores live in registers from here on
+            if constexpr (!PT) {
+                tc_fence_before();
+                mbar_arrive(s_free);  // my 64 scores live in registers from here on
+            }
             if (valid >= 64) {
 #pragma unroll
                 for (int k = 0; k < 32; k += 4) {
@@ -286,7 +307,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             // one: each publishes its maximum rounded UP to bf16 and both take the larger.
             const __nv_bfloat16 mine = __float2bfloat16_ru(mx);
             mxbuf[half * 128 + r] = mine;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // only the two warps that share these 32 rows have to meet (named barrier 1 + quadrant, 64 threads)
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + lg) : "memory");
             const float m_blk = fmaxf(__bfloat162float(mine), __bfloat162float(mxbuf[(half ^ 1) * 128 + r]));
             // Lazy rescale: keep the old reference max unless the row max grew by more than 2^8. The probabilities are
             // then bounded by 256 instead of 1 (exact in bf16 / fp32 all the same) and O / the row sum are rescaled
@@ -314,44 +336,65 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             m_run = m_new;
 
-            // pass 2: P = exp2(S*scale - m) for my 64 columns (still in registers) -> one 64-wide swizzled atom of P
+            // pass 2: P = exp2(S*scale - m) for my 64 columns (still in registers) -> bf16 pairs; PT: written over the
+            // first 64 columns of my own S row in TMEM (32 packed columns per half), else one swizzled smem atom of P
             float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
             const float sc = p.scale_log2;
+            // one branch per key block (full / ragged tile), not one per 8 columns
+            auto pass2 = [&](auto full_tag) {
+                constexpr bool kFull = decltype(full_tag)::value;
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                uint32_t(&v)[32] = cc ? vb : va;
+                for (int cc = 0; cc < 2; ++cc) {
+                    uint32_t(&v)[32] = cc ? vb : va;
+                    uint32_t pk[16];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float e[8];
-                    if (valid >= 64) {
+                    for (int q = 0; q < 4; ++q) {
+                        float e[8];
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const float arg = __uint_as_float(v[q * 8 + k]) * sc - m_new;
-                            // IMAGD_ATTN_POLY of every 8 exponentials go to the FMA pipe instead of MUFU (default 0)
-                            e[k] = (k < IMAGD_ATTN_POLY) ? ex2_poly(arg) : ex2_approx(arg);
+                            if constexpr (kFull) {
+                                // IMAGD_ATTN_POLY of every 8 exponentials go to the FMA pipe instead of MUFU (default 0)
+                                e[k] = (k < IMAGD_ATTN_POLY) ? ex2_poly(arg) : ex2_approx(arg);
+                            } else {
+                                e[k] = (cc * 32 + q * 8 + k < valid) ? ex2_approx(arg) : 0.f;
+                            }
                         }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            e[k] = (cc * 32 + q * 8 + k < valid) ? ex2_approx(__uint_as_float(v[q * 8 + k]) * sc - m_new)
-                                                                : 0.f;
+                        if constexpr (!kOnes) {
+                            sum0 += e[0] + e[4];
+                            sum1 += e[1] + e[5];
+                            sum2 += e[2] + e[6];
+                            sum3 += e[3] + e[7];
+                        }
+                        if constexpr (PT) {
+                            pk[q * 4 + 0] = pack_bf16x2(e[0], e[1]);
+                            pk[q * 4 + 1] = pack_bf16x2(e[2], e[3]);
+                            pk[q * 4 + 2] = pack_bf16x2(e[4], e[5]);
+                            pk[q * 4 + 3] = pack_bf16x2(e[6], e[7]);
+                        } else {
+                            const uint32_t chunk = static_cast<uint32_t>(cc * 4 + q) ^ rx;
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16),
+                                         "r"(pack_bf16x2(e[0], e[1])), "r"(pack_bf16x2(e[2], e[3])),
+                                         "r"(pack_bf16x2(e[4], e[5])), "r"(pack_bf16x2(e[6], e[7]))
+                                         : "memory");
+                        }
                     }
-                    if constexpr (!kOnes) {
-                        sum0 += e[0] + e[4];
-                        sum1 += e[1] + e[5];
-                        sum2 += e[2] + e[6];
-                        sum3 += e[3] + e[7];
-                    }
-                    const uint32_t chunk = static_cast<uint32_t>(cc * 4 + q) ^ rx;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16),
-                                 "r"(pack_bf16x2(e[0], e[1])), "r"(pack_bf16x2(e[2], e[3])),
-                                 "r"(pack_bf16x2(e[4], e[5])), "r"(pack_bf16x2(e[6], e[7]))
-                                 : "memory");
+                    // 16 packed columns per 32 scores: the first store is in flight while the second half is computed
+                    if constexpr (PT) tmem_st16(tmem_S + lane_addr + half * 32 + cc * 16, pk);
                 }
+            };
+            if (valid >= 64) {
+                pass2(std::true_type{});
+            } else {
+                pass2(std::false_type{});
             }
             if constexpr (!kOnes) l_run = l_run * alpha + ((sum0 + sum1) + (sum2 + sum3));
 
-            fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor core (async proxy)
+            if constexpr (PT) {
+                tmem_st_wait();
+            } else {
+                fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor core (async proxy)
+            }
             tc_fence_before();
             mbar_arrive(p_full);
         }
@@ -371,7 +414,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             float* lbuf = reinterpret_cast<float*>(sP);  // [2 halves][2 values][128 rows]
             lbuf[(half * 2 + 0) * 128 + r] = l_first;
             lbuf[(half * 2 + 1) * 128 + r] = l_run;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + lg) : "memory");
             lf = l_first + lbuf[((half ^ 1) * 2 + 0) * 128 + r];
             lr = l_run + lbuf[((half ^ 1) * 2 + 1) * 128 + r];
         }
@@ -426,14 +469,23 @@ static int make_head_tmap(CUtensorMap* tm, const void* base, int64_t ld, int hd,
     return make_tmap_bf16(tm, base, 4, dims, strides, box);
 }
 
-template <int HD_MMA, int NATOM, int KV_STAGES>
+template <int HD_MMA, int NATOM, int KV_STAGES, bool PT>
 static int launch_attn(const CUtensorMap* tms, const AttnParams& p, cudaStream_t stream) {
-    using C = AttnCfg<HD_MMA, NATOM, KV_STAGES>;
-    IMAGD_SET_MAX_SMEM((attention_tc_kernel<HD_MMA, NATOM, KV_STAGES>), C::kTotal);
+    using C = AttnCfg<HD_MMA, NATOM, KV_STAGES, PT>;
+    IMAGD_SET_MAX_SMEM((attention_tc_kernel<HD_MMA, NATOM, KV_STAGES, PT>), C::kTotal);
     dim3 grid((p.Lq + 127) / 128, p.heads, p.B);
-    IMAGD_CUDA(launch_pdl(attention_tc_kernel<HD_MMA, NATOM, KV_STAGES>, grid, dim3(320), C::kTotal, stream, tms[0],
+    IMAGD_CUDA(launch_pdl(attention_tc_kernel<HD_MMA, NATOM, KV_STAGES, PT>, grid, dim3(320), C::kTotal, stream, tms[0],
                           tms[1], tms[2], tms[3], tms[4], p));
     return IMAGD_OK;
+}
+
+// IMAGD_ATTN_PTMEM=0 falls back to the shared-memory P path of round 1 (A/B switch; read once).
+static bool attn_ptmem() {
+    static const bool on = [] {
+        const char* e = getenv("IMAGD_ATTN_PTMEM");
+        return e == nullptr || e[0] != '0';
+    }();
+    return on;
 }
 
 }  // namespace imagd
@@ -486,9 +538,9 @@ extern "C" int imagd_attention_bf16(const void* q, int64_t q_ld, void* out, int6
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (head_dim) {
-        case 40: return launch_attn<48, 1, 2>(tms, p, st);
-        case 64: return launch_attn<64, 1, 2>(tms, p, st);
-        case 80: return launch_attn<80, 2, 2>(tms, p, st);
-        default: return launch_attn<160, 3, 1>(tms, p, st);
+        case 40: return attn_ptmem() ? launch_attn<48, 1, 2, true>(tms, p, st) : launch_attn<48, 1, 2, false>(tms, p, st);
+        case 64: return attn_ptmem() ? launch_attn<64, 1, 2, true>(tms, p, st) : launch_attn<64, 1, 2, false>(tms, p, st);
+        case 80: return launch_attn<80, 2, 2, false>(tms, p, st);
+        default: return launch_attn<160, 3, 1, false>(tms, p, st);
     }
 }

@@ -728,11 +728,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     const bool bulk = bulk_env >= 0 ? bulk_env == 1 : ctas > 2 * 148;
     if (!linear) return launch_gemm_impl<BLOCK_N, STAGES, 0>(tmA, tmB, p, m_tiles, stream);
     if (!bulk) return launch_gemm_impl<BLOCK_N, STAGES, 1>(tmA, tmB, p, m_tiles, stream);
-    // IMAGD_GEMM_BULK_RES=1 (r2-prep, never run): the residual also travels by bulk copy through the staging rows
+    // The residual also travels by bulk copy through the staging rows (validated on B200 in round 2: all GEMM tests
+    // green with it forced on, batch-8 step 24.49 -> 24.32 ms); IMAGD_GEMM_BULK_RES=0 switches it off.
     static int bulk_res = -1;
     if (bulk_res < 0) {
         const char* e = getenv("IMAGD_GEMM_BULK_RES");
-        bulk_res = (e && e[0] == '1') ? 1 : 0;
+        bulk_res = (e && e[0] == '0') ? 0 : 1;
     }
     const bool res_ok = p.ep.residual != nullptr && p.ep.ldr % 8 == 0;
     return (bulk_res && res_ok) ? launch_gemm_impl<BLOCK_N, STAGES, 3>(tmA, tmB, p, m_tiles, stream)

@@ -393,25 +393,10 @@ class IMAGDressing_v1_IPAControlNet(IMAGDressing_v1_ControlNet):
 
     def load_ip_adapter(self):
         """FaceID checkpoint: `image_proj.*` -> ProjPlusModel, `ip_adapter.{i}.*` -> processors by ModuleList index
-        (attn2 processors sit at odd indices), strict=False (:88-101)."""
-        import os
+        (attn2 processors sit at odd indices), strict=False (:88-101). Implemented in checkpoint.py."""
+        from .checkpoint import load_ip_adapter_checkpoint
 
-        if os.path.splitext(self.ip_ckpt)[-1] == ".safetensors":
-            from safetensors import safe_open
-
-            sd = {"image_proj": {}, "ip_adapter": {}}
-            with safe_open(self.ip_ckpt, framework="pt", device="cpu") as f:
-                for key in f.keys():
-                    if key.startswith("image_proj."):
-                        sd["image_proj"][key.replace("image_proj.", "")] = f.get_tensor(key)
-                    elif key.startswith("ip_adapter."):
-                        sd["ip_adapter"][key.replace("ip_adapter.", "")] = f.get_tensor(key)
-        else:
-            sd = torch.load(self.ip_ckpt, map_location="cpu")
-        self.image_proj_model.load_state_dict(sd["image_proj"])
-        layers = torch.nn.ModuleList([p for p in self.unet.attn_processors.values()])
-        layers.load_state_dict(sd["ip_adapter"], strict=False)
-        self.unet.invalidate_packed()
+        load_ip_adapter_checkpoint(self.ip_ckpt, image_proj_model=self.image_proj_model, unet=self.unet)
 
     @torch.no_grad()
     def get_image_embeds(self, face_clip_image=None, faceid_embeds=None, face_clip_embeds=None):

@@ -34,6 +34,34 @@ def test_groupnorm(cuda_device, NB, H, W, C, silu, eps):
     assert rel_l2(out, ref) < 5e-3
 
 
+@pytest.mark.parametrize("NB,H,W,C,mean,std", [(1, 64, 64, 320, 300.0, 1.0), (2, 32, 32, 640, -800.0, 4.0),
+                                                (1, 16, 16, 1280, 2000.0, 0.5), (2, 8, 8, 1280, 64.0, 0.05)])
+def test_groupnorm_large_mean(cuda_device, NB, H, W, C, mean, std):
+    """real SD1.5 activations carry per-group means of hundreds. The one-pass raw E[x^2] - mean^2
+    form loses every significant bit of the variance there (mean^2 ~ 1e5..4e6 against a variance of ~1); the kernel's
+    shifted statistics + Chan merge must not. Per-group offsets differ so the group means really are what is large; the
+    bf16 grid at |x| ~ 300 has a spacing of 2, so the reference is computed from the SAME rounded input in fp64."""
+    from imagdressing_b200 import ops
+
+    g = torch.Generator().manual_seed(11)
+    offs = mean * (1.0 + 0.1 * torch.randn(NB, 1, 1, 32, 1, generator=g))
+    x = (torch.randn(NB, H, W, 32, C // 32, generator=g) * std + offs).reshape(NB, H, W, C).to(cuda_device).bfloat16()
+    gamma = 1.0 + 0.1 * _rand((C,), cuda_device, 2)
+    beta = 0.1 * _rand((C,), cuda_device, 3)
+    out = ops.groupnorm(x, gamma, beta, 32, 1e-5, silu=False)
+    xd = x.double().reshape(NB, H * W, 32, C // 32)
+    mu = xd.mean(dim=(1, 3), keepdim=True)
+    var = xd.var(dim=(1, 3), keepdim=True, unbiased=False)
+    ref = ((xd - mu) / torch.sqrt(var + 1e-5)).reshape(NB, H, W, C) * gamma.double() + beta.double()
+    err = rel_l2(out, ref)
+    # what the round-1 formula would have produced (fp32 raw moments), for the record
+    xf = x.float().reshape(NB, H * W, 32, C // 32)
+    m1, m2 = xf.mean(dim=(1, 3), keepdim=True), (xf * xf).mean(dim=(1, 3), keepdim=True)
+    naive = ((xf - m1) * torch.rsqrt((m2 - m1 * m1).clamp_min(0) + 1e-5)).reshape(NB, H, W, C) * gamma + beta
+    print(f"mean {mean} std {std}: kernel rel-L2 {err:.2e}; raw one-pass fp32 moments would give {rel_l2(naive, ref):.2e}")
+    assert err < 5e-3
+
+
 @pytest.mark.parametrize("rows,C", [(4096, 320), (1024, 640), (77, 768), (257, 1280), (16, 768), (3, 2048)])
 def test_layernorm(cuda_device, rows, C):
     from imagdressing_b200 import ops
