@@ -457,6 +457,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (warp == 9) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
+#include "attention_pp.inc"
+
 // ------------------------------------------------------------------------------------------------ host side
 
 static int make_head_tmap(CUtensorMap* tm, const void* base, int64_t ld, int hd, int heads, int len, int nsamples,
@@ -477,6 +479,26 @@ static int launch_attn(const CUtensorMap* tms, const AttnParams& p, cudaStream_t
     IMAGD_CUDA(launch_pdl(attention_tc_kernel<HD_MMA, NATOM, KV_STAGES, PT>, grid, dim3(320), C::kTotal, stream, tms[0],
                           tms[1], tms[2], tms[3], tms[4], p));
     return IMAGD_OK;
+}
+
+template <int HD_MMA>
+static int launch_attn_pp(const CUtensorMap* tms, const AttnParams& p, cudaStream_t stream) {
+    constexpr int kStages = 3;
+    using C = AttnPPCfg<kStages>;
+    IMAGD_SET_MAX_SMEM((attention_pp_kernel<HD_MMA, kStages>), C::kTotal);
+    dim3 grid((p.Lq + 255) / 256, p.heads, p.B);
+    IMAGD_CUDA(launch_pdl(attention_pp_kernel<HD_MMA, kStages>, grid, dim3(576), C::kTotal, stream, tms[0], tms[1], tms[2],
+                          tms[3], tms[4], p));
+    return IMAGD_OK;
+}
+
+// IMAGD_ATTN_PP=0 switches the ping-pong kernel (two Q tiles per CTA, head_dim 40 / 64, Lq > 128) off (A/B switch).
+static bool attn_pp() {
+    static const bool on = [] {
+        const char* e = getenv("IMAGD_ATTN_PP");
+        return e == nullptr || e[0] != '0';
+    }();
+    return on;
 }
 
 // IMAGD_ATTN_PTMEM=0 falls back to the shared-memory P path of round 1 (A/B switch; read once).
@@ -537,6 +559,8 @@ extern "C" int imagd_attention_bf16(const void* q, int64_t q_ld, void* out, int6
         tms[4] = tms[2];
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (attn_pp() && Lq > 128 && (head_dim == 40 || head_dim == 64))
+        return head_dim == 40 ? launch_attn_pp<48>(tms, p, st) : launch_attn_pp<64>(tms, p, st);
     switch (head_dim) {
         case 40: return attn_ptmem() ? launch_attn<48, 1, 2, true>(tms, p, st) : launch_attn<48, 1, 2, false>(tms, p, st);
         case 64: return attn_ptmem() ? launch_attn<64, 1, 2, true>(tms, p, st) : launch_attn<64, 1, 2, false>(tms, p, st);

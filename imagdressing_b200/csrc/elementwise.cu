@@ -62,7 +62,7 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, __nv_bflo
 }
 
 __global__ void im2col3x3_s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, int NB, int H,
-                                    int W, int C) {
+                                    int W, int C, int pad_lo) {
     pdl_launch_dependents();
     pdl_wait();
     const int Ho = H / 2, Wo = W / 2, CV = C / 8;
@@ -77,11 +77,67 @@ __global__ void im2col3x3_s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
         t /= Wo;
         const int yo = static_cast<int>(t % Ho);
         const int n = static_cast<int>(t / Ho);
-        const int yi = 2 * yo + tap / 3 - 1, xi = 2 * xo + tap % 3 - 1;
+        const int yi = 2 * yo + tap / 3 - pad_lo, xi = 2 * xo + tap % 3 - pad_lo;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (yi >= 0 && yi < H && xi >= 0 && xi < W)
             v = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<int64_t>(n) * H + yi) * W + xi) * C + cv * 8));
         *reinterpret_cast<uint4*>(col + idx * 8) = v;
+    }
+}
+
+// Row softmax of an fp32 score matrix into bf16 probabilities: P[r, :] = softmax(scale * S[r, :]). One CTA per row, the
+// row lives in registers (<= 64 values per thread = 16384 columns), fp32 statistics, fixed-order block reductions. Serves
+// the single-head, head-dim-512 attention of the VAE mid block (AutoencoderKL, diffusers-0.24: 4096..6912 tokens at
+// 512x512..768x576), whose 512-wide head does not fit the TMEM budget of the flash kernel: S = Q K^T and O = P V run as
+// plain tcgen05 GEMMs around this HBM-bound pass (2 x rows x cols x 4 B read, 2 B written per element).
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, int64_t lds,
+                                                           __nv_bfloat16* __restrict__ p, int64_t ldp, int cols,
+                                                           float scale_log2) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ float red[8];
+    const float* row = s + static_cast<int64_t>(blockIdx.x) * lds;
+    __nv_bfloat16* out = p + static_cast<int64_t>(blockIdx.x) * ldp;
+    const int nvec = cols / 4;
+    float4 v[16];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int c = threadIdx.x + i * 256;
+        v[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (c < nvec) v[i] = __ldg(reinterpret_cast<const float4*>(row) + c);
+        mx = fmaxf(mx, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    const float m = mx * scale_log2;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        v[i].x = ex2_approx(v[i].x * scale_log2 - m);
+        v[i].y = ex2_approx(v[i].y * scale_log2 - m);
+        v[i].z = ex2_approx(v[i].z * scale_log2 - m);
+        v[i].w = ex2_approx(v[i].w * scale_log2 - m);
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);  // -inf padding contributes exp2(-inf) = 0
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    sum = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) sum += red[w];
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int c = threadIdx.x + i * 256;
+        if (c < nvec)
+            *reinterpret_cast<uint2*>(out + c * 4) =
+                make_uint2(pack_bf16x2(v[i].x * inv, v[i].y * inv), pack_bf16x2(v[i].z * inv, v[i].w * inv));
     }
 }
 
@@ -400,12 +456,34 @@ int imagd_upsample2x_bf16(const void* x, void* y, int NB, int H, int W, int C, i
     return IMAGD_OK;
 }
 
-int imagd_im2col3x3_s2_bf16(const void* x, void* col, int NB, int H, int W, int C, imagd_stream stream) {
+static int im2col_s2(const void* x, void* col, int NB, int H, int W, int C, int pad_lo, imagd_stream stream) {
     using namespace imagd;
     IMAGD_CHECK_ARG(x && col && NB > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "im2col_s2: bad args");
+    IMAGD_CHECK_ARG(pad_lo == 0 || pad_lo == 1, "im2col_s2: pad_lo %d", pad_lo);
     const int64_t total = static_cast<int64_t>(NB) * (H / 2) * (W / 2) * 9 * (C / 8);
     IMAGD_CUDA(launch_pdl(im2col3x3_s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(col), NB, H, W, C));
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(col), NB, H, W, C, pad_lo));
+    return IMAGD_OK;
+}
+
+int imagd_im2col3x3_s2_bf16(const void* x, void* col, int NB, int H, int W, int C, imagd_stream stream) {
+    return im2col_s2(x, col, NB, H, W, C, 1, stream);
+}
+
+int imagd_im2col3x3_s2_pad_bf16(const void* x, void* col, int NB, int H, int W, int C, int pad_lo, imagd_stream stream) {
+    return im2col_s2(x, col, NB, H, W, C, pad_lo, stream);
+}
+
+int imagd_softmax_rows(const float* s, int64_t lds, void* p, int64_t ldp, int64_t rows, int cols, float scale,
+                       imagd_stream stream) {
+    using namespace imagd;
+    IMAGD_CHECK_ARG(s && p && rows > 0 && cols > 0 && cols <= 256 * 64, "softmax_rows: rows=%lld cols=%d unsupported",
+                    (long long)rows, cols);
+    IMAGD_CHECK_ARG(cols % 4 == 0 && lds % 4 == 0 && ldp % 4 == 0 && aligned16(s) && (reinterpret_cast<uintptr_t>(p) & 7u) == 0,
+                    "softmax_rows: alignment");
+    IMAGD_CHECK_ARG(rows < (1ll << 31), "softmax_rows: too many rows");
+    IMAGD_CUDA(launch_pdl(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                          s, lds, reinterpret_cast<__nv_bfloat16*>(p), ldp, cols, scale * 1.4426950408889634f));
     return IMAGD_OK;
 }
 

@@ -49,7 +49,7 @@ class DenoiseEngine:
 
         if getattr(self, "_zero_t", None) is None or self._zero_t.device != dev:
             self._zero_t = torch.zeros(1, device=dev, dtype=torch.float32)
-        if not self.use_cuda_graph:
+        if not (self.use_cuda_graph and dev.type == "cuda"):  # (graphs need a CUDA device; the kernels raise without one)
             run(ref_latents.float().contiguous(), garment_tokens)
             return collect()
         key = (tuple(ref_latents.shape), tuple(garment_tokens.shape))
@@ -212,7 +212,7 @@ class DenoiseEngine:
                 if isinstance(m, Attention) and hasattr(m.processor, "_kv2_memo"):
                     m.processor._kv2_memo.clear()
 
-        if not self.use_cuda_graph or callback is not None:
+        if not (self.use_cuda_graph and dev.type == "cuda") or callback is not None:
             for i in range(S):
                 self._step(st, use_control=keep[i] > 0)
                 if callback is not None:

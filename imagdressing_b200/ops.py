@@ -238,13 +238,31 @@ def upsample2x(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def im2col3x3_s2(x: torch.Tensor) -> torch.Tensor:
+def im2col3x3_s2(x: torch.Tensor, pad_lo: int = 1) -> torch.Tensor:
+    """Stride-2 3x3 patches, tap-major. pad_lo = 1: symmetric padding 1 (UNet Downsample2D); pad_lo = 0: the VAE
+    encoder's (0,1,0,1) right/bottom-only padding."""
     lib = _lib.load()
     NB, H, W, C = x.shape
     assert x.is_contiguous() and x.dtype == BF16
     out = torch.empty(NB, H // 2, W // 2, 9 * C, device=x.device, dtype=BF16)
-    _lib.check(lib.imagd_im2col3x3_s2_bf16(x.data_ptr(), out.data_ptr(), NB, H, W, C, _stream()),
-               "imagd_im2col3x3_s2_bf16")
+    if pad_lo == 1:
+        _lib.check(lib.imagd_im2col3x3_s2_bf16(x.data_ptr(), out.data_ptr(), NB, H, W, C, _stream()),
+                   "imagd_im2col3x3_s2_bf16")
+    else:
+        _lib.check(lib.imagd_im2col3x3_s2_pad_bf16(x.data_ptr(), out.data_ptr(), NB, H, W, C, int(pad_lo), _stream()),
+                   "imagd_im2col3x3_s2_pad_bf16")
+    return out
+
+
+def softmax_rows(s: torch.Tensor, scale: float = 1.0, *, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(scale * s) over the last dim: fp32 [rows, cols] -> bf16 [rows, cols]."""
+    lib = _lib.load()
+    assert s.dtype == torch.float32 and s.dim() == 2 and s.stride(1) == 1
+    rows, cols = s.shape
+    if out is None:
+        out = torch.empty(rows, cols, device=s.device, dtype=BF16)
+    _lib.check(lib.imagd_softmax_rows(s.data_ptr(), s.stride(0), out.data_ptr(), out.stride(0), rows, cols, float(scale),
+                                      _stream()), "imagd_softmax_rows")
     return out
 
 

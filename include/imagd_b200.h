@@ -158,6 +158,15 @@ int imagd_concat_add_bf16(const void* a, int64_t lda, int Ca, const void* res_a,
 int imagd_upsample2x_bf16(const void* x, void* y, int NB, int H, int W, int C, imagd_stream stream);
 /* im2col for the stride-2 pad-1 3x3 Downsample2D conv: [NB,H,W,C] -> [NB*(H/2)*(W/2), 9*C] tap-major. */
 int imagd_im2col3x3_s2_bf16(const void* x, void* col, int NB, int H, int W, int C, imagd_stream stream);
+/* The same with a selectable leading pad: pad_lo = 1 is the UNet's Downsample2D (padding 1); pad_lo = 0 is the VAE
+ * encoder's Downsample2D, which pads (0,1,0,1) — right / bottom only — and convolves with padding 0 (diffusers-0.24
+ * Downsample2D with padding=0; AutoencoderKL encoder, reference call site IMAGDressing_v1_pipeline.py:457). */
+int imagd_im2col3x3_s2_pad_bf16(const void* x, void* col, int NB, int H, int W, int C, int pad_lo, imagd_stream stream);
+/* P[r, :] = softmax(scale * S[r, :]): fp32 scores [rows, lds] -> bf16 probabilities [rows, ldp]; cols % 4 == 0,
+ * cols <= 16384. The softmax of the VAE mid-block attention (one head of width 512: AutoencoderKL, diffusers-0.24
+ * Attention with upcast_softmax; reference call sites IMAGDressing_v1_pipeline.py:457,544), between two tcgen05 GEMMs. */
+int imagd_softmax_rows(const float* s, int64_t lds, void* p, int64_t ldp, int64_t rows, int cols, float scale,
+                       imagd_stream stream);
 /* Direct (SIMT) 3x3 conv, pad 1, stride 1 or 2, for the thin ends of the network where a tensor-core tile would
  * be empty: conv_in (4->320), conv_out (320->4), ControlNet conditioning embedding (3->16->...->320).
  * x: bf16 [NB,H,W,Cin]; w: bf16 [Cout, 9*Cin] tap-major; bias fp32; act in {NONE, SILU}.

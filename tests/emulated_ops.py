@@ -140,7 +140,8 @@ def attention(q, B, Lq, heads, head_dim, s0, s1=None, *, sm_scale=None, out=None
         rows = slice(src * s.sample_rows, src * s.sample_rows + s.length)
         k = s.k[rows, :C].float().reshape(s.length, heads, head_dim).transpose(0, 1)
         v = s.v[rows, :C].float().reshape(s.length, heads, head_dim).transpose(0, 1)
-        return torch.softmax(qf[b] @ k.transpose(1, 2) * scale, -1) @ v
+        # 4-D inputs select torch's fused CPU kernel (no Lq x L matrix; ~10x faster than the 3-D math path)
+        return F.scaled_dot_product_attention(qf[b][None], k[None], v[None], scale=scale)[0]
 
     rows = []
     for b in range(B):
@@ -161,9 +162,16 @@ def upsample2x(x):
     return x.repeat_interleave(2, 1).repeat_interleave(2, 2).contiguous()
 
 
-def im2col3x3_s2(x):
+def softmax_rows(s, scale=1.0, *, out=None):
+    return _store(torch.softmax(s.float() * scale, -1).to(BF), out)
+
+
+def im2col3x3_s2(x, pad_lo=1):
     NB, H, W, C = x.shape
-    cols = F.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)  # [NB, C*9, L], channel-major (c*9 + tap)
+    xin = x.float().permute(0, 3, 1, 2)
+    if pad_lo == 0:  # VAE encoder: right / bottom padding only
+        xin = F.pad(xin, (0, 1, 0, 1))
+    cols = F.unfold(xin, 3, padding=1 if pad_lo == 1 else 0, stride=2)  # [NB, C*9, L], channel-major (c*9 + tap)
     cols = cols.view(NB, C, 9, H // 2, W // 2).permute(0, 3, 4, 2, 1)          # -> tap-major (tap*C + c)
     return cols.reshape(NB, H // 2, W // 2, 9 * C).to(BF).contiguous()
 
@@ -211,5 +219,5 @@ def install(monkeypatch):
 
     for name in ("gemm", "conv3x3", "conv3x3_direct", "groupnorm", "layernorm", "kv_stream", "attention", "concat_add",
                  "upsample2x", "im2col3x3_s2", "nchw_f32_to_nhwc_bf16", "timestep_embedding", "linear_small_m",
-                 "cfg_ddim_step", "gemm_tile_count_n", "upconv3x3"):
+                 "cfg_ddim_step", "gemm_tile_count_n", "upconv3x3", "softmax_rows"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -34,9 +34,12 @@ def test_groupnorm(cuda_device, NB, H, W, C, silu, eps):
     assert rel_l2(out, ref) < 5e-3
 
 
-@pytest.mark.parametrize("NB,H,W,C,mean,std", [(1, 64, 64, 320, 300.0, 1.0), (2, 32, 32, 640, -800.0, 4.0),
-                                                (1, 16, 16, 1280, 2000.0, 0.5), (2, 8, 8, 1280, 64.0, 0.05)])
-def test_groupnorm_large_mean(cuda_device, NB, H, W, C, mean, std):
+@pytest.mark.parametrize("NB,H,W,C,mean,std,tol", [(1, 64, 64, 320, 300.0, 4.0, 5e-3), (2, 32, 32, 640, -800.0, 16.0, 5e-3),
+                                                    (1, 16, 16, 1280, 2000.0, 32.0, 5e-3), (2, 8, 8, 1280, 64.0, 1.0, 5e-3),
+                                                    # near-constant groups (std far below the bf16 spacing of 8 at 2000):
+                                                    # the variance is rounding noise, eps decides — raw moments return garbage
+                                                    (1, 16, 16, 1280, 2000.0, 0.5, 5e-2)])
+def test_groupnorm_large_mean(cuda_device, NB, H, W, C, mean, std, tol):
     """real SD1.5 activations carry per-group means of hundreds. The one-pass raw E[x^2] - mean^2
     form loses every significant bit of the variance there (mean^2 ~ 1e5..4e6 against a variance of ~1); the kernel's
     shifted statistics + Chan merge must not. Per-group offsets differ so the group means really are what is large; the
@@ -58,8 +61,11 @@ def test_groupnorm_large_mean(cuda_device, NB, H, W, C, mean, std):
     xf = x.float().reshape(NB, H * W, 32, C // 32)
     m1, m2 = xf.mean(dim=(1, 3), keepdim=True), (xf * xf).mean(dim=(1, 3), keepdim=True)
     naive = ((xf - m1) * torch.rsqrt((m2 - m1 * m1).clamp_min(0) + 1e-5)).reshape(NB, H, W, C) * gamma + beta
-    print(f"mean {mean} std {std}: kernel rel-L2 {err:.2e}; raw one-pass fp32 moments would give {rel_l2(naive, ref):.2e}")
-    assert err < 5e-3
+    e_naive = rel_l2(naive, ref)
+    print(f"mean {mean} std {std}: kernel rel-L2 {err:.2e}; raw one-pass fp32 moments would give {e_naive:.2e}")
+    assert err < tol
+    if std < 1.0:
+        assert e_naive > 10 * err  # the case the shifted statistics exist for
 
 
 @pytest.mark.parametrize("rows,C", [(4096, 320), (1024, 640), (77, 768), (257, 1280), (16, 768), (3, 2048)])
@@ -189,3 +195,39 @@ def test_cfg_ddim_step_and_counter(cuda_device):
     r = ops_ref.ddim_step_ref(ec, eu, 5.0, lat, *a[0])
     r = (1 - mask) * (0.8 * img + 0.6 * noise) + mask * r
     assert rel_l2(x, r) < 1e-5
+
+
+@pytest.mark.parametrize("rows,cols,scale", [(64, 4096, 512 ** -0.5), (7, 6912, 0.05), (3, 16384, 1.0), (5, 36, 2.0)])
+def test_softmax_rows(cuda_device, rows, cols, scale):
+    """Row softmax of the VAE mid-block attention (fp32 scores -> bf16 probabilities), incl. a large-logit row."""
+    from imagdressing_b200 import ops
+
+    s = _rand((rows, cols), cuda_device, 21, 6.0)
+    s[0, :4] += 200.0
+    out = ops.softmax_rows(s, scale)
+    ref = torch.softmax(s.double() * scale, dim=-1)
+    assert out.dtype == torch.bfloat16 and rel_l2(out, ref) < 4e-3
+    assert torch.allclose(out.float().sum(-1), torch.ones(rows, device=cuda_device), atol=2e-2)
+    # strided input / output (row stride > cols)
+    big = torch.zeros(rows, cols + 8, device=cuda_device)
+    big[:, :cols] = s
+    o2 = torch.empty(rows, cols + 8, device=cuda_device, dtype=torch.bfloat16)
+    ops.softmax_rows(big[:, :cols], scale, out=o2[:, :cols])
+    assert torch.equal(o2[:, :cols], out)
+
+
+def test_vae_downsample_via_im2col_pad0(cuda_device):
+    """AutoencoderKL encoder Downsample2D: F.pad(x, (0,1,0,1)) + conv3x3 stride 2 padding 0 == im2col(pad_lo=0) GEMM."""
+    from imagdressing_b200 import ops
+
+    x = _rand((2, 16, 12, 128), cuda_device, 22).bfloat16()
+    w = _rand((128, 128, 3, 3), cuda_device, 23, 0.03).bfloat16()
+    b = _rand((128,), cuda_device, 24, 0.1)
+    col = ops.im2col3x3_s2(x, pad_lo=0)
+    y = ops.gemm(col, ops_ref.conv3x3_pack(w), bias=b)
+    ref = F.conv2d(F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1)), w.float(), b, stride=2).permute(0, 2, 3, 1)
+    assert y.shape == (2, 8, 6, 128) and rel_l2(y, ref) < 1e-2
+    # pad_lo = 1 is still the UNet's symmetric downsample
+    col1 = ops.im2col3x3_s2(x, pad_lo=1)
+    ref1 = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, stride=2, padding=1).permute(0, 2, 3, 1)
+    assert rel_l2(ops.gemm(col1, ops_ref.conv3x3_pack(w), bias=b), ref1) < 1e-2
