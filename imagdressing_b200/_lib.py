@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libimagd_b200.so")
 
 IMAGD_OK = 0
-ACT_NONE, ACT_GEGLU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
+ACT_NONE, ACT_GEGLU, ACT_SILU, ACT_GELU, ACT_QUICK_GELU = 0, 1, 2, 3, 4
 
 
 class Epilogue(Structure):
@@ -72,6 +72,8 @@ SIGNATURES = {
                                      POINTER(Epilogue), c_void_p]),
     "imagd_attention_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int,
                                      POINTER(KVStream), POINTER(KVStream), c_float, c_void_p]),
+    "imagd_attention_causal_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int,
+                                            POINTER(KVStream), c_float, c_void_p]),
     "imagd_groupnorm_ws_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "imagd_groupnorm_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p,
                                      c_void_p, c_float, c_int, c_void_p, c_void_p]),
@@ -82,6 +84,9 @@ SIGNATURES = {
     "imagd_upsample2x_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "imagd_im2col3x3_s2_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "imagd_im2col3x3_s2_pad_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "imagd_embed_tokens_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "imagd_patchify_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "imagd_broadcast_row_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
     "imagd_softmax_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p]),
     "imagd_conv3x3_direct_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                           c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -120,9 +125,9 @@ def load() -> ctypes.CDLL:
 
 
 # kernels launched through the C ABI (bench.py reports it as gpu_launches); graph replays add their node count
-LAUNCHES = {"imagd_gemm_bf16": 1, "imagd_conv3x3_bf16": 1, "imagd_upconv3x3_bf16": 1, "imagd_attention_bf16": 1, "imagd_groupnorm_bf16": 1,
+LAUNCHES = {"imagd_gemm_bf16": 1, "imagd_conv3x3_bf16": 1, "imagd_upconv3x3_bf16": 1, "imagd_attention_bf16": 1, "imagd_attention_causal_bf16": 1, "imagd_groupnorm_bf16": 1,
             "imagd_layernorm_bf16": 1, "imagd_concat_add_bf16": 1, "imagd_upsample2x_bf16": 1,
-            "imagd_im2col3x3_s2_bf16": 1, "imagd_im2col3x3_s2_pad_bf16": 1, "imagd_softmax_rows": 1, "imagd_conv3x3_direct_bf16": 1, "imagd_nchw_f32_to_nhwc_bf16": 1,
+            "imagd_im2col3x3_s2_bf16": 1, "imagd_im2col3x3_s2_pad_bf16": 1, "imagd_softmax_rows": 1, "imagd_embed_tokens_bf16": 1, "imagd_patchify_bf16": 1, "imagd_broadcast_row_bf16": 1, "imagd_conv3x3_direct_bf16": 1, "imagd_nchw_f32_to_nhwc_bf16": 1,
             "imagd_timestep_embedding": 1, "imagd_linear_small_m": 1, "imagd_cfg_ddim_step": 1}
 launch_count = 0
 

@@ -50,6 +50,8 @@ struct AttnParams {
     int nq1;               // stream 1 applies to samples [0, nq1)
     int bcast0, bcast1;
     float oscale0, oscale1;
+    int causal;            // stream 0 only: query q sees keys 0..q
+    int pp_sync;           // ping-pong kernels: 1 = the two softmax groups alternate on the MUFU pipe through named barriers
     void* out;
     int64_t out_ld;
 };
@@ -272,7 +274,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 m_run = -INFINITY;
                 l_run = 0.f;
             }
-            const int valid = min(128, (s ? p.len1 : p.len0) - j * 128) - half * 64;  // valid columns in my half (may be <= 0)
+            int valid = min(128, (s ? p.len1 : p.len0) - j * 128) - half * 64;  // valid columns in my half (may be <= 0)
+            if (p.causal) valid = min(valid, q0 + r + 1 - j * 128 - half * 64);   // keys 0..q of my row
+            // the full-tile fast path holds warp-collective TMEM stores: take it only when EVERY row of the warp is full
+            const bool full = __all_sync(0xffffffffu, valid >= 64);
             mbar_wait(s_full, i & 1);
             tc_fence_after();
 
@@ -287,7 +292,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 tc_fence_before();
                 mbar_arrive(s_free);  // my 64 scores live in registers from here on
             }
-            if (valid >= 64) {
+            if (full) {
 #pragma unroll
                 for (int k = 0; k < 32; k += 4) {
                     mx0 = fmaxf(mx0, fmaxf(__uint_as_float(va[k]), __uint_as_float(vb[k])));
@@ -383,7 +388,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     if constexpr (PT) tmem_st16(tmem_S + lane_addr + half * 32 + cc * 16, pk);
                 }
             };
-            if (valid >= 64) {
+            if (full) {
                 pass2(std::true_type{});
             } else {
                 pass2(std::false_type{});
@@ -458,6 +463,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 #include "attention_pp.inc"
+#include "attention_pp1.inc"
 
 // ------------------------------------------------------------------------------------------------ host side
 
@@ -481,12 +487,29 @@ static int launch_attn(const CUtensorMap* tms, const AttnParams& p, cudaStream_t
     return IMAGD_OK;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 template <int HD_MMA>
-static int launch_attn_pp(const CUtensorMap* tms, const AttnParams& p, cudaStream_t stream) {
+static int launch_attn_pp(const CUtensorMap* tms, AttnParams p, cudaStream_t stream) {
     constexpr int kStages = 3;
+    // A/B switches (read once): IMAGD_ATTN_PP_VARIANT = 2 (separate P buffer, early S(i+1)) | 1 (P aliases S);
+    // IMAGD_ATTN_PP_SYNC = 1 (strict hand-over of the MUFU pipe between the groups) | 0 (free-running groups)
+    static const int variant = env_int("IMAGD_ATTN_PP_VARIANT", 2);
+    static const int sync = env_int("IMAGD_ATTN_PP_SYNC", 1);
+    p.pp_sync = sync;
+    dim3 grid((p.Lq + 255) / 256, p.heads, p.B);
+    if (variant == 1) {
+        using C = AttnPP1Cfg<kStages>;
+        IMAGD_SET_MAX_SMEM((attention_pp1_kernel<HD_MMA, kStages>), C::kTotal);
+        IMAGD_CUDA(launch_pdl(attention_pp1_kernel<HD_MMA, kStages>, grid, dim3(576), C::kTotal, stream, tms[0], tms[1],
+                              tms[2], tms[3], tms[4], p));
+        return IMAGD_OK;
+    }
     using C = AttnPPCfg<kStages>;
     IMAGD_SET_MAX_SMEM((attention_pp_kernel<HD_MMA, kStages>), C::kTotal);
-    dim3 grid((p.Lq + 255) / 256, p.heads, p.B);
     IMAGD_CUDA(launch_pdl(attention_pp_kernel<HD_MMA, kStages>, grid, dim3(576), C::kTotal, stream, tms[0], tms[1], tms[2],
                           tms[3], tms[4], p));
     return IMAGD_OK;
@@ -512,9 +535,24 @@ static bool attn_ptmem() {
 
 }  // namespace imagd
 
+static int attention_impl(const void* q, int64_t q_ld, void* out, int64_t out_ld, int B, int Lq, int heads, int head_dim,
+                          const imagd_kv_stream* s0, const imagd_kv_stream* s1, float sm_scale, int causal,
+                          imagd_stream stream);
+
 extern "C" int imagd_attention_bf16(const void* q, int64_t q_ld, void* out, int64_t out_ld, int B, int Lq, int heads,
                                     int head_dim, const imagd_kv_stream* s0, const imagd_kv_stream* s1, float sm_scale,
                                     imagd_stream stream) {
+    return attention_impl(q, q_ld, out, out_ld, B, Lq, heads, head_dim, s0, s1, sm_scale, 0, stream);
+}
+
+extern "C" int imagd_attention_causal_bf16(const void* q, int64_t q_ld, void* out, int64_t out_ld, int B, int Lq, int heads,
+                                           int head_dim, const imagd_kv_stream* s0, float sm_scale, imagd_stream stream) {
+    return attention_impl(q, q_ld, out, out_ld, B, Lq, heads, head_dim, s0, nullptr, sm_scale, 1, stream);
+}
+
+static int attention_impl(const void* q, int64_t q_ld, void* out, int64_t out_ld, int B, int Lq, int heads, int head_dim,
+                          const imagd_kv_stream* s0, const imagd_kv_stream* s1, float sm_scale, int causal,
+                          imagd_stream stream) {
     using namespace imagd;
     IMAGD_CHECK_ARG(q && out && s0 && s0->k && s0->v, "attention: null pointer");
     IMAGD_CHECK_ARG(B > 0 && Lq > 0 && heads > 0, "attention: bad shape");
@@ -538,6 +576,8 @@ extern "C" int imagd_attention_bf16(const void* q, int64_t q_ld, void* out, int6
     p.nq1 = has1 ? (s1->n_query_samples < B ? s1->n_query_samples : B) : 0;
     p.bcast1 = has1 ? s1->broadcast : 0;
     p.oscale1 = has1 ? s1->out_scale : 0.f;
+    p.causal = causal;
+    p.pp_sync = 1;
     p.out = out;
     p.out_ld = out_ld;
 
@@ -559,7 +599,7 @@ extern "C" int imagd_attention_bf16(const void* q, int64_t q_ld, void* out, int6
         tms[4] = tms[2];
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (attn_pp() && Lq > 128 && (head_dim == 40 || head_dim == 64))
+    if (attn_pp() && !causal && Lq > 128 && (head_dim == 40 || head_dim == 64))
         return head_dim == 40 ? launch_attn_pp<48>(tms, p, st) : launch_attn_pp<64>(tms, p, st);
     switch (head_dim) {
         case 40: return attn_ptmem() ? launch_attn<48, 1, 2, true>(tms, p, st) : launch_attn<48, 1, 2, false>(tms, p, st);

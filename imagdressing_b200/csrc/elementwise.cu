@@ -141,6 +141,64 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
     }
 }
 
+// ---- CLIP encoder front ends: gathers and layout only, the arithmetic is the GEMM / LN / attention
+// out[b*T + t, :] = tok[ids[b*T + t], :] + pos[t, :]   (CLIPTextEmbeddings: token + position embedding)
+__global__ void embed_tokens_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ tok,
+                                    const __nv_bfloat16* __restrict__ pos, __nv_bfloat16* __restrict__ out, int rows, int T,
+                                    int C, int vocab) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int CV = C / 8;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < static_cast<int64_t>(rows) * CV;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int row = static_cast<int>(idx / CV), cv = static_cast<int>(idx % CV);
+        int64_t id = ids[row];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(tok + id * C + cv * 8));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(pos + static_cast<int64_t>(row % T) * C + cv * 8));
+        const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = pack_bf16x2(bf16lo(ua[k]) + bf16lo(ub[k]), bf16hi(ua[k]) + bf16hi(ub[k]));
+        *reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * C + cv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// Non-overlapping patches of an fp32 NCHW image as GEMM rows (CLIPVisionEmbeddings.patch_embedding = conv with
+// kernel = stride = patch): out[(b*Py + py)*Px + px, (c*patch + iy)*patch + ix] = x[b, c, py*patch + iy, px*patch + ix];
+// columns [3*patch*patch, Kpad) are zero (K is padded to a multiple of 8 for the tensor-core GEMM).
+__global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W, int patch,
+                                int Kpad) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int Py = H / patch, Px = W / patch, K = 3 * patch * patch;
+    const int64_t total = static_cast<int64_t>(B) * Py * Px * Kpad;
+    for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(idx % Kpad);
+        int64_t t = idx / Kpad;
+        const int px = static_cast<int>(t % Px);
+        t /= Px;
+        const int py = static_cast<int>(t % Py);
+        const int b = static_cast<int>(t / Py);
+        float v = 0.f;
+        if (k < K) {
+            const int c = k / (patch * patch), iy = (k / patch) % patch, ix = k % patch;
+            v = __ldg(x + ((static_cast<int64_t>(b) * 3 + c) * H + py * patch + iy) * W + px * patch + ix);
+        }
+        out[idx] = __float2bfloat16_rn(v);
+    }
+}
+
+// out[b * rows_per_sample + row, :] = vec  for every sample b (the ViT class-token row: class_embedding + position[0])
+__global__ void broadcast_row_kernel(const __nv_bfloat16* __restrict__ vec, __nv_bfloat16* __restrict__ out, int B,
+                                     int64_t rows_per_sample, int row, int C) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < B * C; idx += gridDim.x * blockDim.x)
+        out[(static_cast<int64_t>(idx / C) * rows_per_sample + row) * C + idx % C] = vec[idx % C];
+}
+
 // thread per (output pixel, cout): thin convs where 9*Cin is small or the call happens once per image
 __global__ void conv3x3_direct_thread_kernel(const __nv_bfloat16* __restrict__ x, int NB, int H, int W, int Cin,
                                              const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
@@ -472,6 +530,35 @@ int imagd_im2col3x3_s2_bf16(const void* x, void* col, int NB, int H, int W, int 
 
 int imagd_im2col3x3_s2_pad_bf16(const void* x, void* col, int NB, int H, int W, int C, int pad_lo, imagd_stream stream) {
     return im2col_s2(x, col, NB, H, W, C, pad_lo, stream);
+}
+
+int imagd_embed_tokens_bf16(const int64_t* ids, const void* tok, const void* pos, void* out, int rows, int T, int C, int vocab,
+                            imagd_stream stream) {
+    using namespace imagd;
+    IMAGD_CHECK_ARG(ids && tok && pos && out && rows > 0 && T > 0 && C % 8 == 0 && vocab > 0, "embed_tokens: bad args");
+    IMAGD_CUDA(launch_pdl(embed_tokens_kernel, dim3(grid_for(static_cast<int64_t>(rows) * (C / 8), 256)), dim3(256), 0,
+                          static_cast<cudaStream_t>(stream), ids, reinterpret_cast<const __nv_bfloat16*>(tok),
+                          reinterpret_cast<const __nv_bfloat16*>(pos), reinterpret_cast<__nv_bfloat16*>(out), rows, T, C, vocab));
+    return IMAGD_OK;
+}
+
+int imagd_patchify_bf16(const float* x, void* out, int B, int H, int W, int patch, int Kpad, imagd_stream stream) {
+    using namespace imagd;
+    IMAGD_CHECK_ARG(x && out && B > 0 && patch > 0 && H % patch == 0 && W % patch == 0 && Kpad >= 3 * patch * patch &&
+                        Kpad % 8 == 0, "patchify: bad args");
+    const int64_t total = static_cast<int64_t>(B) * (H / patch) * (W / patch) * Kpad;
+    IMAGD_CUDA(launch_pdl(patchify_kernel, dim3(grid_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), x,
+                          reinterpret_cast<__nv_bfloat16*>(out), B, H, W, patch, Kpad));
+    return IMAGD_OK;
+}
+
+int imagd_broadcast_row_bf16(const void* vec, void* out, int B, int64_t rows_per_sample, int row, int C, imagd_stream stream) {
+    using namespace imagd;
+    IMAGD_CHECK_ARG(vec && out && B > 0 && C > 0 && row >= 0 && row < rows_per_sample, "broadcast_row: bad args");
+    IMAGD_CUDA(launch_pdl(broadcast_row_kernel, dim3(grid_for(static_cast<int64_t>(B) * C, 256)), dim3(256), 0,
+                          static_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(vec),
+                          reinterpret_cast<__nv_bfloat16*>(out), B, rows_per_sample, row, C));
+    return IMAGD_OK;
 }
 
 int imagd_softmax_rows(const float* s, int64_t lds, void* p, int64_t ldp, int64_t rows, int cols, float scale,

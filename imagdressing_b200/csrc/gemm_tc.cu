@@ -559,6 +559,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     } else if (ep.act == IMAGD_ACT_GELU) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
+                    } else if (ep.act == IMAGD_ACT_QUICK_GELU) {  // x * sigmoid(1.702 x): CLIP text MLP (quick_gelu)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-1.702f * f[j]));
                     }
                     if (res) {
                         const uint4 rv = rcur[g];

@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_SILU, Epilogue, KVStream
+from ._lib import ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, Epilogue, KVStream
 
 BF16 = torch.bfloat16
 
@@ -155,8 +155,9 @@ def kv_stream(k: torch.Tensor, v: torch.Tensor, length: int, *, sample_rows: int
 
 def attention(q: torch.Tensor, B: int, Lq: int, heads: int, head_dim: int, s0: KVStream,
               s1: Optional[KVStream] = None, *, sm_scale: Optional[float] = None,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q: [B*Lq, >= heads*head_dim] bf16 view (row stride arbitrary). Returns [B*Lq, heads*head_dim] bf16."""
+              out: Optional[torch.Tensor] = None, causal: bool = False) -> torch.Tensor:
+    """q: [B*Lq, >= heads*head_dim] bf16 view (row stride arbitrary). Returns [B*Lq, heads*head_dim] bf16.
+    causal: query i attends to keys 0..i of stream 0 (CLIP text encoder); no second stream then."""
     lib = _lib.load()
     assert q.dtype == BF16 and q.stride(-1) == 1
     q_ld = q.stride(-2)
@@ -164,6 +165,12 @@ def attention(q: torch.Tensor, B: int, Lq: int, heads: int, head_dim: int, s0: K
         out = torch.empty(B * Lq, heads * head_dim, device=q.device, dtype=BF16)
     if sm_scale is None:
         sm_scale = head_dim ** -0.5
+    if causal:
+        assert s1 is None
+        rc = lib.imagd_attention_causal_bf16(q.data_ptr(), q_ld, out.data_ptr(), out.stride(-2), B, Lq, heads, head_dim,
+                                             ctypes.byref(s0), float(sm_scale), _stream())
+        _lib.check(rc, "imagd_attention_causal_bf16")
+        return out
     rc = lib.imagd_attention_bf16(q.data_ptr(), q_ld, out.data_ptr(), out.stride(-2), B, Lq, heads, head_dim,
                                   ctypes.byref(s0), ctypes.byref(s1) if s1 is not None else None, float(sm_scale),
                                   _stream())
@@ -335,3 +342,35 @@ def cfg_ddim_step(eps_cond: torch.Tensor, eps_uncond: Optional[torch.Tensor], gu
                                  _ptr(blend_coef), NB, C, H * W, _stream())
     _lib.check(rc, "imagd_cfg_ddim_step")
     return latents
+
+
+def embed_tokens(ids: torch.Tensor, tok: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+    """ids int64 [B, T]; tok bf16 [V, C]; pos bf16 [>= T, C] -> bf16 [B, T, C] = tok[ids] + pos[:T]."""
+    lib = _lib.load()
+    B, T = ids.shape
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and tok.dtype == BF16 and pos.dtype == BF16
+    assert tok.is_contiguous() and pos.is_contiguous() and pos.shape[0] >= T and pos.shape[1] == tok.shape[1]
+    out = torch.empty(B, T, tok.shape[1], device=ids.device, dtype=BF16)
+    _lib.check(lib.imagd_embed_tokens_bf16(ids.data_ptr(), tok.data_ptr(), pos.data_ptr(), out.data_ptr(), B * T, T,
+                                           tok.shape[1], tok.shape[0], _stream()), "imagd_embed_tokens_bf16")
+    return out
+
+
+def patchify(x: torch.Tensor, patch: int, kpad: int) -> torch.Tensor:
+    """fp32 [B, 3, H, W] -> bf16 [B * (H/patch) * (W/patch), kpad] patch rows (column = (c*patch + iy)*patch + ix)."""
+    lib = _lib.load()
+    B, C, H, W = x.shape
+    assert C == 3 and x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty(B * (H // patch) * (W // patch), kpad, device=x.device, dtype=BF16)
+    _lib.check(lib.imagd_patchify_bf16(x.data_ptr(), out.data_ptr(), B, H, W, patch, kpad, _stream()), "imagd_patchify_bf16")
+    return out
+
+
+def broadcast_row(vec: torch.Tensor, out: torch.Tensor, row: int) -> torch.Tensor:
+    """out[b, row, :] = vec for every sample of out [B, rows, C] (bf16, contiguous)."""
+    lib = _lib.load()
+    B, R, C = out.shape
+    assert out.is_contiguous() and out.dtype == BF16 and vec.dtype == BF16 and vec.numel() == C
+    _lib.check(lib.imagd_broadcast_row_bf16(vec.data_ptr(), out.data_ptr(), B, R, row, C, _stream()),
+               "imagd_broadcast_row_bf16")
+    return out

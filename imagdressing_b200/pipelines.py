@@ -89,6 +89,15 @@ class _DressingPipelineBase:
         for k, v in modules.items():
             setattr(self, k, v)
 
+    def _encoder(self, name):
+        """The CLIP text / vision encoder under `name`, running on the kernels once it lives on a CUDA device (clip.py;
+        the wrapped transformers module stays the parameter container)."""
+        from .clip import auto_accelerate
+
+        enc = auto_accelerate(getattr(self, name, None))
+        setattr(self, name, enc)
+        return enc
+
     def _finish_init(self):
         vae = getattr(self, "vae", None)
         self.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1) if vae is not None else 8
@@ -162,13 +171,14 @@ class _DressingPipelineBase:
         def enc(texts):
             if self.tokenizer is None or self.text_encoder is None:
                 raise ValueError("no tokenizer/text_encoder: pass prompt_embeds and negative_prompt_embeds")
+            text_encoder = self._encoder("text_encoder")
             texts = [texts] if isinstance(texts, str) else list(texts)
             ids = self.tokenizer(texts, padding="max_length", max_length=self.tokenizer.model_max_length,
                                  truncation=True, return_tensors="pt").input_ids.to(device)
             if clip_skip is None:
-                return self.text_encoder(ids)[0]
-            hs = self.text_encoder(ids, output_hidden_states=True)[-1][-(clip_skip + 1)]
-            return self.text_encoder.text_model.final_layer_norm(hs)
+                return text_encoder(ids)[0]
+            hs = text_encoder(ids, output_hidden_states=True)[-1][-(clip_skip + 1)]
+            return text_encoder.text_model.final_layer_norm(hs)
 
         if prompt_embeds is None:
             prompt_embeds = enc(prompt)
@@ -211,7 +221,8 @@ class _DressingPipelineBase:
             return prompt_embeds
         if self.image_encoder is None:
             raise ValueError("no image_encoder: pass garment_tokens")
-        hs = self.image_encoder(ref_clip_image.to(device, dtype=dtype), output_hidden_states=True).hidden_states[-2]
+        enc = self._encoder("image_encoder")
+        hs = enc(ref_clip_image.to(device, dtype=dtype), output_hidden_states=True).hidden_states[-2]
         return self.ImgProj(hs)
 
     def _ref_latents(self, ref_image, ref_image_latents, device):
@@ -403,10 +414,10 @@ class IMAGDressing_v1_IPAControlNet(IMAGDressing_v1_ControlNet):
         """(:366-377) ProjPlusModel(faceid, CLIP hidden_states[-2], shortcut=False); uncond = zeros inputs (B12)."""
         dev = self.device
         if face_clip_embeds is None:
-            face_clip_embeds = self.image_encoder(face_clip_image.to(dev, dtype=self.image_encoder.dtype),
-                                                  output_hidden_states=True).hidden_states[-2]
-            zero_clip = self.image_encoder(torch.zeros_like(face_clip_image).to(dev, dtype=self.image_encoder.dtype),
-                                           output_hidden_states=True).hidden_states[-2]
+            enc = self._encoder("image_encoder")
+            face_clip_embeds = enc(face_clip_image.to(dev, dtype=enc.dtype), output_hidden_states=True).hidden_states[-2]
+            zero_clip = enc(torch.zeros_like(face_clip_image).to(dev, dtype=enc.dtype),
+                            output_hidden_states=True).hidden_states[-2]
         else:
             zero_clip = torch.zeros_like(face_clip_embeds)
         fid = faceid_embeds.to(dev)

@@ -29,7 +29,8 @@ enum imagd_status {
     IMAGD_ERR_ARCH = -3  /* device is not sm_100 */
 };
 
-enum imagd_act { IMAGD_ACT_NONE = 0, IMAGD_ACT_GEGLU = 1, IMAGD_ACT_SILU = 2, IMAGD_ACT_GELU = 3 };
+enum imagd_act { IMAGD_ACT_NONE = 0, IMAGD_ACT_GEGLU = 1, IMAGD_ACT_SILU = 2, IMAGD_ACT_GELU = 3,
+                 IMAGD_ACT_QUICK_GELU = 4 /* x * sigmoid(1.702 x): the CLIP text encoder's MLP */ };
 
 /* ---- library ---- */
 int imagd_version(void);
@@ -132,6 +133,11 @@ typedef struct imagd_kv_stream {
 int imagd_attention_bf16(const void* q, int64_t q_ld, void* out, int64_t out_ld, int B, int Lq, int heads,
                          int head_dim, const imagd_kv_stream* s0, const imagd_kv_stream* s1, float sm_scale,
                          imagd_stream stream);
+/* The same with a causal mask on stream 0 (query i sees keys 0..i; s1 must be NULL): the CLIP text encoder's
+ * self-attention (transformers CLIPTextModel, reference call sites inference_IMAGdressing.py:44-46,
+ * IMAGDressing_v1_pipeline.py:396-405 encode_prompt). */
+int imagd_attention_causal_bf16(const void* q, int64_t q_ld, void* out, int64_t out_ld, int B, int Lq, int heads,
+                                int head_dim, const imagd_kv_stream* s0, float sm_scale, imagd_stream stream);
 
 /* ---- normalisation ---- */
 /* GroupNorm over [NB, HW, C] (token-major) with optional fused SiLU; workspace ws (imagd_groupnorm_ws_bytes; its first
@@ -179,6 +185,17 @@ int imagd_conv3x3_direct_bf16(const void* x, int NB, int H, int W, int Cin, cons
  * dressing_sd/pipelines/IMAGDressing_v1_pipeline.py:483-485) in the same pass. */
 int imagd_nchw_f32_to_nhwc_bf16(const float* x, void* y, int NB, int C, int H, int W, int Cpad, int repeat,
                                 imagd_stream stream);
+
+/* ---- CLIP encoder front ends (transformers CLIPTextModel / CLIPVisionModelWithProjection, reference
+ * call sites inference_IMAGdressing.py:44-49, IMAGDressing_v1_pipeline.py:396-415) ---- */
+/* out[r, :] = tok[ids[r], :] + pos[r % T, :]  (token + position embedding; ids int64, clamped to the vocabulary). */
+int imagd_embed_tokens_bf16(const int64_t* ids, const void* tok, const void* pos, void* out, int rows, int T, int C, int vocab,
+                            imagd_stream stream);
+/* fp32 NCHW image -> bf16 patch rows [B*(H/patch)*(W/patch), Kpad], column = (c*patch + iy)*patch + ix, zero padded:
+ * the A operand of the patch-embedding GEMM (a conv with kernel = stride = patch). */
+int imagd_patchify_bf16(const float* x, void* out, int B, int H, int W, int patch, int Kpad, imagd_stream stream);
+/* out[b*rows_per_sample + row, :] = vec for every sample (the ViT class-token row). */
+int imagd_broadcast_row_bf16(const void* vec, void* out, int B, int64_t rows_per_sample, int row, int C, imagd_stream stream);
 
 /* ---- time conditioning ---- */
 /* Sinusoidal timestep embedding, flip_sin_to_cos=True, freq_shift=0: out[b] = [cos | sin] (dim/2 each), fp32.

@@ -9,7 +9,7 @@ import torch
 import torch.nn.functional as F
 
 BF = torch.bfloat16
-ACT_NONE, ACT_GEGLU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
+ACT_NONE, ACT_GEGLU, ACT_SILU, ACT_GELU, ACT_QUICK_GELU = 0, 1, 2, 3, 4
 
 
 def _act(y, act):
@@ -17,6 +17,8 @@ def _act(y, act):
         return F.silu(y)
     if act == ACT_GELU:
         return F.gelu(y)
+    if act == ACT_QUICK_GELU:
+        return y * torch.sigmoid(1.702 * y)
     return y
 
 
@@ -130,7 +132,7 @@ def kv_stream(k, v, length, **kw):
     return Stream(k, v, length, **kw)
 
 
-def attention(q, B, Lq, heads, head_dim, s0, s1=None, *, sm_scale=None, out=None):
+def attention(q, B, Lq, heads, head_dim, s0, s1=None, *, sm_scale=None, out=None, causal=False):
     C = heads * head_dim
     scale = sm_scale if sm_scale is not None else head_dim ** -0.5
     qf = q[:, :C].float().reshape(B, Lq, heads, head_dim).transpose(1, 2)
@@ -141,7 +143,7 @@ def attention(q, B, Lq, heads, head_dim, s0, s1=None, *, sm_scale=None, out=None
         k = s.k[rows, :C].float().reshape(s.length, heads, head_dim).transpose(0, 1)
         v = s.v[rows, :C].float().reshape(s.length, heads, head_dim).transpose(0, 1)
         # 4-D inputs select torch's fused CPU kernel (no Lq x L matrix; ~10x faster than the 3-D math path)
-        return F.scaled_dot_product_attention(qf[b][None], k[None], v[None], scale=scale)[0]
+        return F.scaled_dot_product_attention(qf[b][None], k[None], v[None], scale=scale, is_causal=causal)[0]
 
     rows = []
     for b in range(B):
@@ -160,6 +162,21 @@ def concat_add(a, b=None, *, res_a=None, res_b=None, out=None):
 
 def upsample2x(x):
     return x.repeat_interleave(2, 1).repeat_interleave(2, 2).contiguous()
+
+
+def embed_tokens(ids, tok, pos):
+    return (tok.float()[ids] + pos.float()[: ids.shape[1]][None]).to(BF)
+
+
+def patchify(x, patch, kpad):
+    B, C, H, W = x.shape
+    cols = F.unfold(x.float(), patch, stride=patch).transpose(1, 2).reshape(-1, C * patch * patch)  # (c, iy, ix) order
+    return F.pad(cols, (0, kpad - cols.shape[1])).to(BF).contiguous()
+
+
+def broadcast_row(vec, out, row):
+    out[:, row, :] = vec
+    return out
 
 
 def softmax_rows(s, scale=1.0, *, out=None):
@@ -219,5 +236,5 @@ def install(monkeypatch):
 
     for name in ("gemm", "conv3x3", "conv3x3_direct", "groupnorm", "layernorm", "kv_stream", "attention", "concat_add",
                  "upsample2x", "im2col3x3_s2", "nchw_f32_to_nhwc_bf16", "timestep_embedding", "linear_small_m",
-                 "cfg_ddim_step", "gemm_tile_count_n", "upconv3x3", "softmax_rows"):
+                 "cfg_ddim_step", "gemm_tile_count_n", "upconv3x3", "softmax_rows", "embed_tokens", "patchify", "broadcast_row"):
         monkeypatch.setattr(ops, name, globals()[name])
