@@ -519,6 +519,10 @@ def main():
             del p2
             torch.cuda.empty_cache()
 
+    edges = None
+    if rank == 0 and standard_run(a) and not a.no_extras:
+        edges = edge_models(dev)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -566,6 +570,8 @@ def main():
                         "top_launch_keys": top_keys, "ms_per_launch_of_roofline_kernels": {k: round(v, 4) for k, v in
                                                                                           by_launch.items()}},
     }
+    if edges:
+        line["edges"] = edges
     if batches:
         line["batches"] = batches
     if other_configs:
@@ -580,6 +586,55 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def edge_models(dev):
+    """The steps either side of the loop, on the same kernels (excluded from the headline's timed
+    region exactly as the metric defines): VAE decode of 32 512x512 images, VAE encode of 1, CLIP ViT-H/14 image encoder
+    (hidden_states[-2]) and the SD1.5 text encoder, random-init at the real widths. CUDA events, 1 warm-up + 2 timed calls."""
+    from transformers import CLIPTextConfig, CLIPTextModel, CLIPVisionConfig, CLIPVisionModelWithProjection
+
+    from imagdressing_b200 import clip, modeling, vae
+
+    def ev(fn, n=2):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    out = {}
+    with _no_default_init():
+        v = vae.AutoencoderKL().to(dev, torch.bfloat16)
+    modeling.init_synthetic_fast_(v, 5)
+    z = torch.randn(32, 4, HW, HW, device=dev)
+    img = torch.rand(1, 3, HW * 8, HW * 8, device=dev) * 2 - 1
+    ms = ev(lambda: v.decode(z, return_dict=False))
+    out["vae_decode_b32_512x512"] = {"ms": round(ms, 2), "images_per_s": round(32e3 / ms, 2)}
+    ms = ev(lambda: v.encode(img))
+    out["vae_encode_b1_512x512"] = {"ms": round(ms, 2)}
+    del v, z
+    torch.cuda.empty_cache()
+    torch.manual_seed(0)
+    vis = CLIPVisionModelWithProjection(CLIPVisionConfig(hidden_size=1280, intermediate_size=5120, num_hidden_layers=32,
+                                                         num_attention_heads=16, image_size=224, patch_size=14,
+                                                         projection_dim=1024, hidden_act="gelu")).to(dev, torch.bfloat16).eval()
+    enc = clip.accelerate(vis)
+    px = torch.randn(2, 3, 224, 224, device=dev)
+    out["clip_vit_h14_b2_hidden_states_m2"] = {"ms": round(ev(lambda: enc(px, output_hidden_states=True)), 2)}
+    del vis, enc
+    txt = CLIPTextModel(CLIPTextConfig(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
+                                       num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu")
+                        ).to(dev, torch.bfloat16).eval()
+    tenc = clip.accelerate(txt)
+    ids = torch.randint(0, 49000, (2, 77), device=dev)
+    out["clip_text_b2"] = {"ms": round(ev(lambda: tenc(ids)), 2)}
+    torch.cuda.empty_cache()
+    return out
 
 
 def standard_run(a):

@@ -16,14 +16,19 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-bool pdl_enabled() {
+// IMAGD_PDL: 0 (default) no programmatic dependent launch; 1 every kernel lets its dependent start at once (round 1:
+// neutral-to-negative on the B=1 step - the dependent's CTAs take shared memory / TMEM the running kernel still needs);
+// 2 "late trigger": the tensor-core kernels release their dependent only when their own mainloop is done, so the next
+// kernel's launch latency and prologue hide under this kernel's epilogue / tail instead of competing with its mainloop.
+int pdl_mode() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("IMAGD_PDL");  // opt-in: measured neutral-to-slightly-negative on the B=1 step
-        v = (e && e[0] == '1') ? 1 : 0;
+        const char* e = getenv("IMAGD_PDL");
+        v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
     }
-    return v == 1;
+    return v;
 }
+bool pdl_enabled() { return pdl_mode() != 0; }
 
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);

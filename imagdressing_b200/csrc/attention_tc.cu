@@ -51,6 +51,7 @@ struct AttnParams {
     int bcast0, bcast1;
     float oscale0, oscale1;
     int causal;            // stream 0 only: query q sees keys 0..q
+    int pdl_late;          // 1: release the dependent kernel when the last MMA is issued instead of at kernel entry
     int pp_sync;           // ping-pong kernels: 1 = the two softmax groups alternate on the MUFU pipe through named barriers
     void* out;
     int64_t out_ld;
@@ -106,7 +107,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* pv_done = s_free + 1;  // P.V(i) retired: P may be overwritten, O may be rescaled
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
 
-    pdl_launch_dependents();
+    if (!p.pdl_late) pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128;
@@ -250,7 +251,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             __syncwarp();
         }
-        if (leader) umma_commit(o_full);
+        if (leader) {
+            umma_commit(o_full);
+            if (p.pdl_late) pdl_launch_dependents();
+        }
     } else {
         // ------------------------------------------------ softmax / correction / epilogue (warps 0-7)
         const int lg = warp & 3;          // TMEM lane quadrant
@@ -495,9 +499,12 @@ static int env_int(const char* name, int dflt) {
 template <int HD_MMA>
 static int launch_attn_pp(const CUtensorMap* tms, AttnParams p, cudaStream_t stream) {
     constexpr int kStages = 3;
-    // A/B switches (read once): IMAGD_ATTN_PP_VARIANT = 2 (separate P buffer, early S(i+1)) | 1 (P aliases S);
-    // IMAGD_ATTN_PP_SYNC = 1 (strict hand-over of the MUFU pipe between the groups) | 0 (free-running groups)
-    static const int variant = env_int("IMAGD_ATTN_PP_VARIANT", 2);
+    // A/B switches (read once): IMAGD_ATTN_PP_VARIANT = 1 (P aliases S; default) | 2 (separate P buffer, early S(i+1));
+    // IMAGD_ATTN_PP_SYNC = 1 (strict hand-over of the MUFU pipe between the groups; default) | 0 (free-running groups).
+    // Measured on B200, level-0 hybrid attention, batch 1 / 8 (profiles/r02_call5_attention_matrix_clip.txt):
+    //   variant 1 sync 1: 197.9 / 1202.8 us   variant 1 sync 0: 216.0 / 1260.0 us
+    //   variant 2 sync 1: 221.7 / 1347.5 us   variant 2 sync 0: 212.0 / 1321.5 us   two-CTAs-per-SM kernel: 214 / 1298 us
+    static const int variant = env_int("IMAGD_ATTN_PP_VARIANT", 1);
     static const int sync = env_int("IMAGD_ATTN_PP_SYNC", 1);
     p.pp_sync = sync;
     dim3 grid((p.Lq + 255) / 256, p.heads, p.B);
@@ -578,6 +585,7 @@ static int attention_impl(const void* q, int64_t q_ld, void* out, int64_t out_ld
     p.oscale1 = has1 ? s1->out_scale : 0.f;
     p.causal = causal;
     p.pp_sync = 1;
+    p.pdl_late = pdl_mode() == 2 ? 1 : 0;
     p.out = out;
     p.out_ld = out_ld;
 

@@ -49,6 +49,7 @@ struct GemmParams {
     int persist_n_tiles;
     int persist_total;
     int ups_n_tiles;  // LNM == 3: N tiles per phase (gridDim.y = 4 * ups_n_tiles)
+    int pdl_late;     // 1: release the dependent kernel when the accumulator is complete instead of at kernel entry
 };
 
 __device__ __forceinline__ void dbg_mark(const GemmParams& p, int slot) {
@@ -115,7 +116,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* s_bias = reinterpret_cast<float*>(smem + L::kVecOffset);
     float* s_rowvec = s_bias + BLOCK_N;
 
-    pdl_launch_dependents();
+    if (!p.pdl_late) pdl_launch_dependents();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0 && p.dbg != nullptr) {
@@ -293,6 +294,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("bar.sync 1, 128;" ::: "memory");  // s_bias / s_rowvec visible to the four epilogue warps
 
         mbar_wait(tmem_full_bar, 0);
+        if (p.pdl_late) pdl_launch_dependents();  // mainloop done: the next kernel's prologue may overlap this epilogue
         tc_fence_after();
         if (threadIdx.x == 64) dbg_mark(p, 4);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_group * 32) << 16);
@@ -835,6 +837,7 @@ static int run_gemm_like(const void* A, int64_t lda, int NB, int H, int W, int C
     }
     p.persist_n_tiles = p.persist_total = 0;
     p.ups_n_tiles = ups_mode ? 1 : 0;  // the launcher fills in the real tile count
+    p.pdl_late = pdl_mode() == 2 ? 1 : 0;
     p.splits = cfg.splits;
     p.kb_per_split = (kb_total + cfg.splits - 1) / cfg.splits;
     p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
