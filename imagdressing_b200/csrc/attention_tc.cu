@@ -55,6 +55,13 @@ struct AttnParams {
     int pp_sync;           // ping-pong kernels: 1 = the two softmax groups alternate on the MUFU pipe through named barriers
     void* out;
     int64_t out_ld;
+    // training-mode extras (imagd_attention_train_fwd_bf16; all null / 0 on the inference path): per-row log-sum-exp of
+    // each stream in the log2 domain, [2][B][heads][lq_pad] fp32, and the un-weighted per-stream outputs O_s / l_s
+    float* lse;
+    void* out_s0;
+    void* out_s1;
+    int64_t ld_s;
+    int lq_pad;
 };
 
 constexpr int kAtomBytes = 128 * 128;  // one [128 rows x 64 bf16] swizzled tile
@@ -262,7 +269,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int r = lg * 32 + lane;     // query row in tile == TMEM lane
         const uint32_t lane_addr = static_cast<uint32_t>(lg * 32) << 16;
         __nv_bfloat16* mxbuf = reinterpret_cast<__nv_bfloat16*>(smem + C::kMxOff);
-        float m_run = -INFINITY, l_run = 0.f, l_first = 0.f;
+        float m_run = -INFINITY, l_run = 0.f, l_first = 0.f, m_first = 0.f;
         const uint32_t p_row = smem_u32(sP) + half * kAtomBytes + (r >> 3) * 1024 + (r & 7) * 128;
         const uint32_t rx = r & 7;
         // this thread's share of the O columns (16-column chunks) for the in-TMEM rescale and the epilogue
@@ -275,6 +282,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const int j = s ? i - nb0 : i;
             if (j == 0 && i > 0) {
                 l_first = l_run;
+                m_first = m_run;
                 m_run = -INFINITY;
                 l_run = 0.f;
             }
@@ -437,6 +445,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int q = q0 + r;
         __nv_bfloat16* orow =
             reinterpret_cast<__nv_bfloat16*>(p.out) + (static_cast<int64_t>(b) * p.Lq + q) * p.out_ld + h * p.hd;
+        if (p.lse != nullptr && half == 0 && q < p.Lq) {  // training: log2-domain log-sum-exp per stream (m + log2 l)
+            const int64_t per = static_cast<int64_t>(p.heads) * p.lq_pad;
+            float* l0p = p.lse + (static_cast<int64_t>(b) * p.heads + h) * p.lq_pad + q;
+            if (nb1 > 0) {
+                l0p[0] = m_first + __log2f(lf);
+                l0p[static_cast<int64_t>(p.B) * per] = m_run + __log2f(lr);
+            } else {
+                l0p[0] = m_run + __log2f(lr);
+            }
+        }
+        const bool per_stream = p.out_s0 != nullptr && nb1 > 0;  // training, two streams: O_s / l_s on their own
+        const float u0 = nb1 > 0 ? 1.f / lf : 0.f, u1 = nb1 > 0 ? 1.f / lr : 0.f;
+        const int64_t srow = (static_cast<int64_t>(b) * p.Lq + q) * p.ld_s + h * p.hd;
 #pragma unroll 1
         for (int cc = ch_begin; cc < ch_end; ++cc) {
             const int c = cc * 16;
@@ -457,6 +478,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 if (c + 8 < p.hd)
                     dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
                                         pack_bf16x2(f[14], f[15]));
+                if (per_stream) {
+#pragma unroll
+                    for (int st = 0; st < 2; ++st) {
+                        const uint32_t(&o)[16] = st ? o1 : o0;
+                        const float u = st ? u1 : u0;
+                        uint4* d2 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(st ? p.out_s1 : p.out_s0) + srow + c);
+                        d2[0] = make_uint4(pack_bf16x2(u * __uint_as_float(o[0]), u * __uint_as_float(o[1])),
+                                           pack_bf16x2(u * __uint_as_float(o[2]), u * __uint_as_float(o[3])),
+                                           pack_bf16x2(u * __uint_as_float(o[4]), u * __uint_as_float(o[5])),
+                                           pack_bf16x2(u * __uint_as_float(o[6]), u * __uint_as_float(o[7])));
+                        if (c + 8 < p.hd)
+                            d2[1] = make_uint4(pack_bf16x2(u * __uint_as_float(o[8]), u * __uint_as_float(o[9])),
+                                               pack_bf16x2(u * __uint_as_float(o[10]), u * __uint_as_float(o[11])),
+                                               pack_bf16x2(u * __uint_as_float(o[12]), u * __uint_as_float(o[13])),
+                                               pack_bf16x2(u * __uint_as_float(o[14]), u * __uint_as_float(o[15])));
+                    }
+                }
             }
         }
     }
@@ -544,7 +582,14 @@ static bool attn_ptmem() {
 
 static int attention_impl(const void* q, int64_t q_ld, void* out, int64_t out_ld, int B, int Lq, int heads, int head_dim,
                           const imagd_kv_stream* s0, const imagd_kv_stream* s1, float sm_scale, int causal,
-                          imagd_stream stream);
+                          imagd_stream stream, const imagd_attn_train* aux = nullptr);
+
+extern "C" int imagd_attention_train_fwd_bf16(const void* q, int64_t q_ld, void* out, int64_t out_ld, int B, int Lq, int heads,
+                                              int head_dim, const imagd_kv_stream* s0, const imagd_kv_stream* s1,
+                                              float sm_scale, const imagd_attn_train* aux, imagd_stream stream) {
+    IMAGD_CHECK_ARG(aux != nullptr, "attention(train): aux is null");
+    return attention_impl(q, q_ld, out, out_ld, B, Lq, heads, head_dim, s0, s1, sm_scale, 0, stream, aux);
+}
 
 extern "C" int imagd_attention_bf16(const void* q, int64_t q_ld, void* out, int64_t out_ld, int B, int Lq, int heads,
                                     int head_dim, const imagd_kv_stream* s0, const imagd_kv_stream* s1, float sm_scale,
@@ -559,7 +604,7 @@ extern "C" int imagd_attention_causal_bf16(const void* q, int64_t q_ld, void* ou
 
 static int attention_impl(const void* q, int64_t q_ld, void* out, int64_t out_ld, int B, int Lq, int heads, int head_dim,
                           const imagd_kv_stream* s0, const imagd_kv_stream* s1, float sm_scale, int causal,
-                          imagd_stream stream) {
+                          imagd_stream stream, const imagd_attn_train* aux) {
     using namespace imagd;
     IMAGD_CHECK_ARG(q && out && s0 && s0->k && s0->v, "attention: null pointer");
     IMAGD_CHECK_ARG(B > 0 && Lq > 0 && heads > 0, "attention: bad shape");
@@ -588,6 +633,18 @@ static int attention_impl(const void* q, int64_t q_ld, void* out, int64_t out_ld
     p.pdl_late = pdl_mode() == 2 ? 1 : 0;
     p.out = out;
     p.out_ld = out_ld;
+    p.lse = aux ? aux->lse : nullptr;
+    p.out_s0 = aux ? aux->out_s0 : nullptr;
+    p.out_s1 = aux ? aux->out_s1 : nullptr;
+    p.ld_s = aux ? aux->ld_s : 0;
+    p.lq_pad = aux ? aux->lq_pad : 0;
+    if (aux) {
+        IMAGD_CHECK_ARG(aux->lse && aux->lq_pad >= Lq && aux->lq_pad % 128 == 0, "attention(train): lse / lq_pad");
+        IMAGD_CHECK_ARG(!has1 || (aux->out_s0 && aux->out_s1 && aux->ld_s % 8 == 0 && aligned16(aux->out_s0) &&
+                                  aligned16(aux->out_s1)),
+                        "attention(train): two streams need out_s0 / out_s1");
+        IMAGD_CHECK_ARG(!causal, "attention(train): causal not supported");
+    }
 
     CUtensorMap tms[5];
     int rc = make_head_tmap(&tms[0], q, q_ld, head_dim, heads, Lq, B);
@@ -607,7 +664,7 @@ static int attention_impl(const void* q, int64_t q_ld, void* out, int64_t out_ld
         tms[4] = tms[2];
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (attn_pp() && !causal && Lq > 128 && (head_dim == 40 || head_dim == 64))
+    if (attn_pp() && !aux && !causal && Lq > 128 && (head_dim == 40 || head_dim == 64))
         return head_dim == 40 ? launch_attn_pp<48>(tms, p, st) : launch_attn_pp<64>(tms, p, st);
     switch (head_dim) {
         case 40: return attn_ptmem() ? launch_attn<48, 1, 2, true>(tms, p, st) : launch_attn<48, 1, 2, false>(tms, p, st);

@@ -1,0 +1,680 @@
+// Backward / training-step kernels that are NOT tensor-core work (reference train.py:573-609 gets
+// all of this from torch autograd + DeepSpeed's fused Adam): layout transposes that feed the tcgen05 GEMM its dgrad / wgrad
+// operands, GroupNorm / LayerNorm / activation backward, column reductions (bias and time-embedding gradients), the
+// stride-2 col2im and 2x-upsample adjoints, the MSE loss + its gradient, AdamW. All HBM / L2-bound: 128-bit accesses where
+// the layout allows, fp32 accumulation, fixed-order (bit-reproducible) reductions — no atomics on data.
+#include <cstdlib>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace imagd {
+
+// ------------------------------------------------------------------------------------------------ transposes
+// y[c, r] = x[r, c] for r < rows, 0 for rows <= r < rows_pad  (y: [cols, ldy], ldy >= rows_pad). 64 x 64 tiles through
+// shared memory: 4-byte global accesses on both sides (bf16 pairs along the contiguous dimension).
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                                                             __nv_bfloat16* __restrict__ y, int64_t ldy, int rows, int cols,
+                                                             int rows_pad) {
+    __shared__ __nv_bfloat16 tile[64][66];
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int rr = ty; rr < 64; rr += 8) {
+        const int r = r0 + rr, c = c0 + tx * 2;
+        __nv_bfloat16 a = __float2bfloat16(0.f), b = a;
+        if (r < rows) {
+            if (c + 1 < cols && ((ldx & 1) == 0)) {
+                const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + static_cast<int64_t>(r) * ldx + c);
+                a = v.x;
+                b = v.y;
+            } else {
+                if (c < cols) a = x[static_cast<int64_t>(r) * ldx + c];
+                if (c + 1 < cols) b = x[static_cast<int64_t>(r) * ldx + c + 1];
+            }
+        }
+        tile[rr][tx * 2] = a;
+        tile[rr][tx * 2 + 1] = b;
+    }
+    __syncthreads();
+    for (int cc = ty; cc < 64; cc += 8) {
+        const int c = c0 + cc, r = r0 + tx * 2;
+        if (c < cols) {
+            __nv_bfloat16* dst = y + static_cast<int64_t>(c) * ldy + r;
+            if (r + 1 < rows_pad && ((ldy & 1) == 0)) {
+                __nv_bfloat162 v;
+                v.x = tile[tx * 2][cc];
+                v.y = tile[tx * 2 + 1][cc];
+                *reinterpret_cast<__nv_bfloat162*>(dst) = v;
+            } else {
+                if (r < rows_pad) dst[0] = tile[tx * 2][cc];
+                if (r + 1 < rows_pad) dst[1] = tile[tx * 2 + 1][cc];
+            }
+        }
+    }
+}
+
+// Transposed im2col of a stride-1 pad-1 3x3 conv input: out[(tap * C + c), p] = x[n, y + ky - 1, x + kx - 1, c] (0 outside),
+// p = (n * H + y) * W + x, zero for P <= p < ldo. The B operand [9 Cin, P] of the conv weight-gradient GEMM
+// dW[Cout, 9 Cin] = dY^T[Cout, P] . col^T (K = P contiguous). grid (P tiles, C tiles, 9 taps).
+__global__ void __launch_bounds__(256) im2col3x3_t_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                          int64_t ldo, int NB, int H, int W, int C) {
+    __shared__ __nv_bfloat16 tile[64][66];
+    const int tap = blockIdx.z, ky = tap / 3, kx = tap % 3;
+    const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int P = NB * H * W;
+    for (int rr = ty; rr < 64; rr += 8) {
+        const int p = p0 + rr, c = c0 + tx * 2;
+        __nv_bfloat16 a = __float2bfloat16(0.f), b = a;
+        if (p < P) {
+            const int xx = p % W, yy = (p / W) % H, n = p / (W * H);
+            const int sy = yy + ky - 1, sx = xx + kx - 1;
+            if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+                const __nv_bfloat16* src = x + ((static_cast<int64_t>(n) * H + sy) * W + sx) * C + c;
+                if (c < C) a = src[0];
+                if (c + 1 < C) b = src[1];
+            }
+        }
+        tile[rr][tx * 2] = a;
+        tile[rr][tx * 2 + 1] = b;
+    }
+    __syncthreads();
+    for (int cc = ty; cc < 64; cc += 8) {
+        const int c = c0 + cc, p = p0 + tx * 2;
+        if (c < C) {
+            __nv_bfloat16* dst = out + (static_cast<int64_t>(tap) * C + c) * ldo + p;
+            if (p < ldo) dst[0] = tile[tx * 2][cc];
+            if (p + 1 < ldo) dst[1] = tile[tx * 2 + 1][cc];
+        }
+    }
+}
+
+// Adjoint of im2col3x3_s2 (pad 1, stride 2): dx[n, y, x, c] = sum over taps with 2 oy + ky - 1 == y, 2 ox + kx - 1 == x of
+// dcol[n, oy, ox, (ky * 3 + kx) * C + c].  One thread per 8 channels of an input pixel.
+__global__ void col2im3x3_s2_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dx, int NB, int H,
+                                    int W, int C) {
+    const int CV = C / 8;
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = static_cast<int64_t>(NB) * H * W * CV;
+    if (idx >= total) return;
+    const int cv = static_cast<int>(idx % CV);
+    const int64_t pix = idx / CV;
+    const int xx = static_cast<int>(pix % W), yy = static_cast<int>((pix / W) % H), n = static_cast<int>(pix / (static_cast<int64_t>(W) * H));
+    const int Ho = H / 2, Wo = W / 2;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int ky = 0; ky < 3; ++ky) {
+        const int ty = yy + 1 - ky;
+        if (ty < 0 || (ty & 1)) continue;
+        const int oy = ty >> 1;
+        if (oy >= Ho) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+            const int tx = xx + 1 - kx;
+            if (tx < 0 || (tx & 1)) continue;
+            const int ox = tx >> 1;
+            if (ox >= Wo) continue;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+                dcol + ((static_cast<int64_t>(n) * Ho + oy) * Wo + ox) * (9 * C) + (ky * 3 + kx) * C + cv * 8));
+            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                acc[2 * k] += bf16lo(u[k]);
+                acc[2 * k + 1] += bf16hi(u[k]);
+            }
+        }
+    }
+    *reinterpret_cast<uint4*>(dx + pix * C + cv * 8) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                                  pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+}
+
+// Adjoint of the nearest-neighbour 2x upsample: dx[n, y, x, :] = sum of the 2x2 block of dy.
+__global__ void downsum2x_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int NB, int H, int W,
+                                 int C) {
+    const int CV = C / 8;
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = static_cast<int64_t>(NB) * H * W * CV;
+    if (idx >= total) return;
+    const int cv = static_cast<int>(idx % CV);
+    const int64_t pix = idx / CV;
+    const int xx = static_cast<int>(pix % W), yy = static_cast<int>((pix / W) % H), n = static_cast<int>(pix / (static_cast<int64_t>(W) * H));
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int sy = 2 * yy + (t >> 1), sx = 2 * xx + (t & 1);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(dy + ((static_cast<int64_t>(n) * 2 * H + sy) * 2 * W + sx) * C + cv * 8));
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            acc[2 * k] += bf16lo(u[k]);
+            acc[2 * k + 1] += bf16hi(u[k]);
+        }
+    }
+    *reinterpret_cast<uint4*>(dx + pix * C + cv * 8) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                                  pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+}
+
+// ------------------------------------------------------------------------------------------------ column reductions
+// Stage 1: block (column slab of 64, group g, row split s) adds rows [s * span, (s+1) * span) of its group in a fixed order
+// -> part[s][g][c]; stage 2 folds the splits. MODE 0: sum of x.  MODE 1 (LayerNorm backward): a = dy * xhat, b = dy with
+// xhat = (x - mean[r]) * rstd[r]; two outputs.
+template <int MODE>
+__global__ void __launch_bounds__(256) colreduce_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                                                        const __nv_bfloat16* __restrict__ dy, int64_t lddy,
+                                                        const float* __restrict__ rowstat, float* __restrict__ part, int C,
+                                                        int rows_per_group, int groups, int splits) {
+    __shared__ float sa[8][64], sb[8][64];
+    const int c = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
+    const int g = blockIdx.y, s = blockIdx.z;
+    const int lane_r = threadIdx.x >> 5;
+    const int span = (rows_per_group + splits - 1) / splits;
+    const int r_begin = s * span, r_end = min(rows_per_group, r_begin + span);
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+    if (c < C) {
+        for (int r = r_begin + lane_r; r < r_end; r += 8) {
+            const int64_t row = static_cast<int64_t>(g) * rows_per_group + r;
+            float x0 = __bfloat162float(x[row * ldx + c]);
+            float x1 = c + 1 < C ? __bfloat162float(x[row * ldx + c + 1]) : 0.f;
+            if (MODE == 0) {
+                a0 += x0;
+                a1 += x1;
+            } else {
+                const float mean = rowstat[2 * row], rstd = rowstat[2 * row + 1];
+                const float d0 = __bfloat162float(dy[row * lddy + c]);
+                const float d1 = c + 1 < C ? __bfloat162float(dy[row * lddy + c + 1]) : 0.f;
+                a0 += d0 * (x0 - mean) * rstd;
+                a1 += d1 * (x1 - mean) * rstd;
+                b0 += d0;
+                b1 += d1;
+            }
+        }
+    }
+    sa[lane_r][(threadIdx.x & 31) * 2] = a0;
+    sa[lane_r][(threadIdx.x & 31) * 2 + 1] = a1;
+    sb[lane_r][(threadIdx.x & 31) * 2] = b0;
+    sb[lane_r][(threadIdx.x & 31) * 2 + 1] = b1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int cc = blockIdx.x * 64 + threadIdx.x;
+        if (cc < C) {
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                a += sa[k][threadIdx.x];
+                b += sb[k][threadIdx.x];
+            }
+            const int64_t o = (static_cast<int64_t>(s) * groups + g) * C + cc;
+            part[o] = a;
+            if (MODE == 1) part[static_cast<int64_t>(splits) * groups * C + o] = b;
+        }
+    }
+}
+
+// out[k][g][c] = sum_s part[k][s][g][c]   (k < nout)
+__global__ void colreduce_fold_kernel(const float* __restrict__ part, float* __restrict__ out0, float* __restrict__ out1, int C,
+                                      int groups, int splits) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t n = static_cast<int64_t>(groups) * C;
+    if (idx >= n) return;
+    float a = 0.f, b = 0.f;
+    for (int s = 0; s < splits; ++s) {
+        a += part[static_cast<int64_t>(s) * n + idx];
+        if (out1) b += part[(static_cast<int64_t>(splits) + s) * n + idx];
+    }
+    out0[idx] = a;
+    if (out1) out1[idx] = b;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm backward
+// One warp per row (C <= 2048): recompute mean / rstd (two-pass on the registers), dx = rstd * (g - mean(g) - xhat * mean(g xhat))
+// with g = dy * gamma; writes {mean, rstd} per row for the column reduction that produces dgamma / dbeta.
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                                                            const __nv_bfloat16* __restrict__ dy, int64_t lddy,
+                                                            __nv_bfloat16* __restrict__ dx, int64_t lddx,
+                                                            const float* __restrict__ gamma, float* __restrict__ rowstat,
+                                                            int rows, int C, float eps) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    constexpr int kMax = 2048 / 64;  // bf16 pairs per lane; fixed-trip loops keep xv / dv in registers
+    float xv[2 * kMax], dv[2 * kMax];
+    const int pairs = C / 2;
+    float sum = 0.f;
+#pragma unroll
+    for (int n = 0; n < kMax; ++n) {
+        const int i = lane + 32 * n;
+        xv[2 * n] = xv[2 * n + 1] = dv[2 * n] = dv[2 * n + 1] = 0.f;
+        if (i < pairs) {
+            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + static_cast<int64_t>(row) * ldx + 2 * i);
+            const __nv_bfloat162 d = *reinterpret_cast<const __nv_bfloat162*>(dy + static_cast<int64_t>(row) * lddy + 2 * i);
+            xv[2 * n] = __bfloat162float(v.x);
+            xv[2 * n + 1] = __bfloat162float(v.y);
+            dv[2 * n] = __bfloat162float(d.x) * (gamma ? gamma[2 * i] : 1.f);
+            dv[2 * n + 1] = __bfloat162float(d.y) * (gamma ? gamma[2 * i + 1] : 1.f);
+            sum += xv[2 * n] + xv[2 * n + 1];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / C;
+    float var = 0.f;
+#pragma unroll
+    for (int n = 0; n < kMax; ++n) {
+        if (lane + 32 * n < pairs) var += (xv[2 * n] - mean) * (xv[2 * n] - mean) + (xv[2 * n + 1] - mean) * (xv[2 * n + 1] - mean);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var / C + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int n = 0; n < kMax; ++n) {
+        if (lane + 32 * n < pairs) {
+            xv[2 * n] = (xv[2 * n] - mean) * rstd;  // xhat from here on
+            xv[2 * n + 1] = (xv[2 * n + 1] - mean) * rstd;
+            s1 += dv[2 * n] + dv[2 * n + 1];
+            s2 += dv[2 * n] * xv[2 * n] + dv[2 * n + 1] * xv[2 * n + 1];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    s1 /= C;
+    s2 /= C;
+#pragma unroll
+    for (int n = 0; n < kMax; ++n) {
+        const int i = lane + 32 * n;
+        if (i < pairs) {
+            __nv_bfloat162 o;
+            o.x = __float2bfloat16(rstd * (dv[2 * n] - s1 - xv[2 * n] * s2));
+            o.y = __float2bfloat16(rstd * (dv[2 * n + 1] - s1 - xv[2 * n + 1] * s2));
+            *reinterpret_cast<__nv_bfloat162*>(dx + static_cast<int64_t>(row) * lddx + 2 * i) = o;
+        }
+    }
+    if (lane == 0) {
+        rowstat[2 * row] = mean;
+        rowstat[2 * row + 1] = rstd;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm backward
+__device__ __forceinline__ float silu_grad(float z) {
+    const float s = 1.f / (1.f + __expf(-z));
+    return s * (1.f + z * (1.f - s));
+}
+
+// One CTA per (group, sample): thread = (pixel lane, channel of the group). Pass A mean, pass B variance (two-pass: no
+// cancellation), pass C the four sums of the backward formula. Writes stat[n][g] = {mean, rstd, S1/m, S2/m} with
+// S1 = sum dz gamma, S2 = sum dz gamma xhat (dz = dy * act'(z), z = xhat gamma + beta), and the per-(sample, channel) partials
+// pc[0][n][c] = sum_p dz xhat, pc[1][n][c] = sum_p dz that fold into dgamma / dbeta.
+__global__ void __launch_bounds__(256) groupnorm_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                   const __nv_bfloat16* __restrict__ dy, int HW, int C,
+                                                                   int groups, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, float eps, int fuse_silu,
+                                                                   float* __restrict__ stat, float* __restrict__ pc, int NB) {
+    __shared__ float red[4][256];
+    __shared__ float bc[4];
+    const int g = blockIdx.x, n = blockIdx.y;
+    const int cpg = C / groups;
+    const int lanes = 256 / cpg;  // pixel lanes (cpg <= 256)
+    const int ch = threadIdx.x % cpg, pl = threadIdx.x / cpg;
+    const bool active = pl < lanes;
+    const int c = g * cpg + ch;
+    const __nv_bfloat16* xb = x + static_cast<int64_t>(n) * HW * C + c;
+    const __nv_bfloat16* db = dy + static_cast<int64_t>(n) * HW * C + c;
+    const float m = static_cast<float>(HW) * cpg;
+
+    auto block_sum = [&](float v, int slot) {  // fixed-order tree over the 256 threads
+        red[slot][threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) red[slot][threadIdx.x] += red[slot][threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) bc[slot] = red[slot][0];
+        __syncthreads();
+        return bc[slot];
+    };
+
+    float s = 0.f;
+    if (active)
+        for (int p = pl; p < HW; p += lanes) s += __bfloat162float(xb[static_cast<int64_t>(p) * C]);
+    const float mean = block_sum(s, 0) / m;
+    s = 0.f;
+    if (active)
+        for (int p = pl; p < HW; p += lanes) {
+            const float d = __bfloat162float(xb[static_cast<int64_t>(p) * C]) - mean;
+            s += d * d;
+        }
+    const float rstd = rsqrtf(block_sum(s, 1) / m + eps);
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    float a = 0.f, b = 0.f;  // per channel: sum dz xhat, sum dz
+    if (active)
+        for (int p = pl; p < HW; p += lanes) {
+            const float xh = (__bfloat162float(xb[static_cast<int64_t>(p) * C]) - mean) * rstd;
+            float dz = __bfloat162float(db[static_cast<int64_t>(p) * C]);
+            if (fuse_silu) dz *= silu_grad(fmaf(xh, ga, be));
+            a += dz * xh;
+            b += dz;
+        }
+    const float S2 = block_sum(active ? a * ga : 0.f, 2);
+    const float S1 = block_sum(active ? b * ga : 0.f, 3);
+    // per-channel fold over the pixel lanes (fixed order): reuse red[0] / red[1]
+    red[0][threadIdx.x] = active ? a : 0.f;
+    red[1][threadIdx.x] = active ? b : 0.f;
+    __syncthreads();
+    if (threadIdx.x < cpg) {
+        float fa = 0.f, fb = 0.f;
+        for (int l = 0; l < lanes; ++l) {
+            fa += red[0][l * cpg + threadIdx.x];
+            fb += red[1][l * cpg + threadIdx.x];
+        }
+        pc[static_cast<int64_t>(n) * C + g * cpg + threadIdx.x] = fa;
+        pc[static_cast<int64_t>(NB) * C + static_cast<int64_t>(n) * C + g * cpg + threadIdx.x] = fb;
+    }
+    if (threadIdx.x == 0) {
+        float* o = stat + (static_cast<int64_t>(n) * groups + g) * 4;
+        o[0] = mean;
+        o[1] = rstd;
+        o[2] = S1 / m;
+        o[3] = S2 / m;
+    }
+}
+
+// dx = rstd * (dz gamma - S1/m - xhat S2/m), elementwise over [NB, HW, C] (8 channels per thread).
+__global__ void groupnorm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                           __nv_bfloat16* __restrict__ dx, int HW, int C, int groups,
+                                           const float* __restrict__ gamma, const float* __restrict__ beta, int fuse_silu,
+                                           const float* __restrict__ stat, int64_t total_vec) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total_vec) return;
+    const int CV = C / 8;
+    const int cv = static_cast<int>(idx % CV);
+    const int64_t pix = idx / CV;
+    const int n = static_cast<int>(pix / HW);
+    const int cpg = C / groups;
+    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + pix * C + cv * 8));
+    const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dy + pix * C + cv * 8));
+    const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w}, du[4] = {dv.x, dv.y, dv.z, dv.w};
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = cv * 8 + k;
+        const float* st = stat + (static_cast<int64_t>(n) * groups + c / cpg) * 4;
+        const float xe = (k & 1) ? bf16hi(xu[k >> 1]) : bf16lo(xu[k >> 1]);
+        const float de = (k & 1) ? bf16hi(du[k >> 1]) : bf16lo(du[k >> 1]);
+        const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+        const float xh = (xe - st[0]) * st[1];
+        float dz = de;
+        if (fuse_silu) dz *= silu_grad(fmaf(xh, ga, be));
+        o[k] = st[1] * (dz * ga - st[2] - xh * st[3]);
+    }
+    *reinterpret_cast<uint4*>(dx + pix * C + cv * 8) =
+        make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+}
+
+// ------------------------------------------------------------------------------------------------ activations
+__device__ __forceinline__ float gelu_grad(float x) {
+    const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752f));
+    return cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
+// mode 2 SiLU, 3 GELU(erf). dy == nullptr: y = act(x); else y = dy * act'(x). Element pairs.
+__global__ void act_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                           __nv_bfloat16* __restrict__ y, int64_t n, int mode) {
+    const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
+    if (i >= n) return;
+    auto f = [&](float v, float g, bool bwd) {
+        if (!bwd) return mode == 2 ? silu(v) : gelu_erf(v);
+        return g * (mode == 2 ? silu_grad(v) : gelu_grad(v));
+    };
+    if (i + 1 < n) {
+        const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162*>(x + i);
+        __nv_bfloat162 gv = xv;
+        if (dy) gv = *reinterpret_cast<const __nv_bfloat162*>(dy + i);
+        __nv_bfloat162 o;
+        o.x = __float2bfloat16(f(__bfloat162float(xv.x), __bfloat162float(gv.x), dy != nullptr));
+        o.y = __float2bfloat16(f(__bfloat162float(xv.y), __bfloat162float(gv.y), dy != nullptr));
+        *reinterpret_cast<__nv_bfloat162*>(y + i) = o;
+    } else {
+        y[i] = __float2bfloat16(f(__bfloat162float(x[i]), dy ? __bfloat162float(dy[i]) : 0.f, dy != nullptr));
+    }
+}
+
+// GEGLU on an un-fused projection h = [value | gate] ([M, 2F], diffusers-0.24 GEGLU: hidden, gate = proj(x).chunk(2)):
+// forward out = value * gelu(gate); backward dh = [dout * gelu(gate) | dout * value * gelu'(gate)].
+__global__ void geglu_kernel(const __nv_bfloat16* __restrict__ h, int64_t ldh, const __nv_bfloat16* __restrict__ dout,
+                             __nv_bfloat16* __restrict__ out, int64_t ldo, int64_t M, int F) {
+    const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int FV = F / 2;
+    if (idx >= M * FV) return;
+    const int64_t r = idx / FV;
+    const int c = static_cast<int>(idx % FV) * 2;
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(h + r * ldh + c);
+    const __nv_bfloat162 g = *reinterpret_cast<const __nv_bfloat162*>(h + r * ldh + F + c);
+    const float v0 = __bfloat162float(v.x), v1 = __bfloat162float(v.y), g0 = __bfloat162float(g.x), g1 = __bfloat162float(g.y);
+    if (dout == nullptr) {
+        __nv_bfloat162 o;
+        o.x = __float2bfloat16(v0 * gelu_erf(g0));
+        o.y = __float2bfloat16(v1 * gelu_erf(g1));
+        *reinterpret_cast<__nv_bfloat162*>(out + r * ldo + c) = o;
+    } else {  // out = dh [M, 2F] (ldo), dout [M, F] contiguous
+        const __nv_bfloat162 d = *reinterpret_cast<const __nv_bfloat162*>(dout + r * F + c);
+        const float d0 = __bfloat162float(d.x), d1 = __bfloat162float(d.y);
+        __nv_bfloat162 dv, dg;
+        dv.x = __float2bfloat16(d0 * gelu_erf(g0));
+        dv.y = __float2bfloat16(d1 * gelu_erf(g1));
+        dg.x = __float2bfloat16(d0 * v0 * gelu_grad(g0));
+        dg.y = __float2bfloat16(d1 * v1 * gelu_grad(g1));
+        *reinterpret_cast<__nv_bfloat162*>(out + r * ldo + c) = dv;
+        *reinterpret_cast<__nv_bfloat162*>(out + r * ldo + F + c) = dg;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ loss
+// MSE(pred, target) (reference train.py:577, F.mse_loss(..., reduction="mean")) + its gradient 2 (pred - target) / n, one pass.
+// part[blockIdx.x] = block partial; mse_fold_kernel adds the partials in order.
+__global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                  float* __restrict__ grad, float* __restrict__ part, int64_t n, float gscale) {
+    __shared__ float red[256];
+    float s = 0.f;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float d = pred[i] - target[i];
+        s += d * d;
+        grad[i] = gscale * d;
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+__global__ void mse_fold_kernel(const float* __restrict__ part, int nparts, float inv_n, float* __restrict__ loss) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < nparts; ++i) s += part[i];
+        loss[0] = s * inv_n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ optimizer
+// AdamW (decoupled weight decay; reference train.py:386-398 torch.optim.AdamW, run by DeepSpeed in bf16 mode with fp32 master
+// weights): fp32 master / moments, bf16 gradient in, bf16 working copy out. bc1 = 1 - beta1^t, bc2 = 1 - beta2^t.
+__global__ void adamw_kernel(float* __restrict__ master, __nv_bfloat16* __restrict__ param, const __nv_bfloat16* __restrict__ grad,
+                             float* __restrict__ m, float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                             float wd, float bc1, float bc2, float gscale) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float g = __bfloat162float(grad[i]) * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * g;
+    const float vi = b2 * v[i] + (1.f - b2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    float w = master[i];
+    w -= lr * wd * w;
+    w -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    master[i] = w;
+    param[i] = __float2bfloat16(w);
+}
+
+static inline unsigned blocks_for(int64_t n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
+
+}  // namespace imagd
+
+using namespace imagd;
+#define BF(p) static_cast<const __nv_bfloat16*>(p)
+#define BFW(p) static_cast<__nv_bfloat16*>(p)
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" int imagd_transpose_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int cols, int rows_pad,
+                                    imagd_stream stream) {
+    IMAGD_CHECK_ARG(x && y && rows > 0 && cols > 0 && rows_pad >= rows && ldy >= rows_pad && ldx >= cols, "transpose: bad argument");
+    dim3 grid((cols + 63) / 64, (rows_pad + 63) / 64);
+    transpose_bf16_kernel<<<grid, 256, 0, ST(stream)>>>(BF(x), ldx, BFW(y), ldy, rows, cols, rows_pad);
+    IMAGD_LAUNCH_CHECK("transpose_bf16_kernel");
+    return IMAGD_OK;
+}
+
+extern "C" int imagd_im2col3x3_t_bf16(const void* x, void* out, int64_t ldo, int NB, int H, int W, int C, imagd_stream stream) {
+    IMAGD_CHECK_ARG(x && out && NB > 0 && H > 0 && W > 0 && C > 0 && ldo >= static_cast<int64_t>(NB) * H * W, "im2col3x3_t: bad argument");
+    dim3 grid(static_cast<unsigned>((ldo + 63) / 64), (C + 63) / 64, 9);
+    im2col3x3_t_kernel<<<grid, 256, 0, ST(stream)>>>(BF(x), BFW(out), ldo, NB, H, W, C);
+    IMAGD_LAUNCH_CHECK("im2col3x3_t_kernel");
+    return IMAGD_OK;
+}
+
+extern "C" int imagd_col2im3x3_s2_bf16(const void* dcol, void* dx, int NB, int H, int W, int C, imagd_stream stream) {
+    IMAGD_CHECK_ARG(dcol && dx && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "col2im3x3_s2: bad argument");
+    const int64_t total = static_cast<int64_t>(NB) * H * W * (C / 8);
+    col2im3x3_s2_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(BF(dcol), BFW(dx), NB, H, W, C);
+    IMAGD_LAUNCH_CHECK("col2im3x3_s2_kernel");
+    return IMAGD_OK;
+}
+
+extern "C" int imagd_downsum2x_bf16(const void* dy, void* dx, int NB, int H, int W, int C, imagd_stream stream) {
+    IMAGD_CHECK_ARG(dy && dx && C % 8 == 0, "downsum2x: bad argument");
+    const int64_t total = static_cast<int64_t>(NB) * H * W * (C / 8);
+    downsum2x_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(BF(dy), BFW(dx), NB, H, W, C);
+    IMAGD_LAUNCH_CHECK("downsum2x_kernel");
+    return IMAGD_OK;
+}
+
+static int colreduce_splits(int rows_per_group, int groups, int C) {
+    const int slabs = (C + 63) / 64;
+    int s = (148 * 2) / (slabs * groups > 0 ? slabs * groups : 1);
+    const int by_rows = (rows_per_group + 63) / 64;  // at least 64 rows per split
+    if (s > by_rows) s = by_rows;
+    if (s > 64) s = 64;
+    return s < 1 ? 1 : s;
+}
+
+extern "C" int64_t imagd_colreduce_ws_bytes(int rows_per_group, int groups, int C) {
+    return static_cast<int64_t>(2) * colreduce_splits(rows_per_group, groups, C) * groups * C * 4;
+}
+
+extern "C" int imagd_colsum_bf16(const void* x, int64_t ldx, int rows_per_group, int groups, int C, float* out, void* ws,
+                                 imagd_stream stream) {
+    IMAGD_CHECK_ARG(x && out && ws && rows_per_group > 0 && groups > 0 && C > 0, "colsum: bad argument");
+    const int splits = colreduce_splits(rows_per_group, groups, C);
+    dim3 grid((C + 63) / 64, groups, splits);
+    colreduce_kernel<0><<<grid, 256, 0, ST(stream)>>>(BF(x), ldx, nullptr, 0, nullptr, static_cast<float*>(ws), C,
+                                                      rows_per_group, groups, splits);
+    IMAGD_LAUNCH_CHECK("colreduce_kernel<0>");
+    colreduce_fold_kernel<<<blocks_for(static_cast<int64_t>(groups) * C, 256), 256, 0, ST(stream)>>>(
+        static_cast<const float*>(ws), out, nullptr, C, groups, splits);
+    IMAGD_LAUNCH_CHECK("colreduce_fold_kernel");
+    return IMAGD_OK;
+}
+
+extern "C" int imagd_layernorm_bwd_bf16(const void* x, int64_t ldx, const void* dy, int64_t lddy, void* dx, int64_t lddx,
+                                        int rows, int C, const float* gamma, float eps, float* dgamma, float* dbeta,
+                                        float* rowstat, void* ws, imagd_stream stream) {
+    IMAGD_CHECK_ARG(x && dy && dx && rowstat && rows > 0 && C > 0 && C % 2 == 0 && C <= 2048, "layernorm_bwd: bad argument");
+    IMAGD_CHECK_ARG(ldx % 2 == 0 && lddy % 2 == 0 && lddx % 2 == 0, "layernorm_bwd: odd row stride");
+    layernorm_bwd_kernel<<<(rows + 7) / 8, 256, 0, ST(stream)>>>(BF(x), ldx, BF(dy), lddy, BFW(dx), lddx, gamma, rowstat, rows,
+                                                                C, eps);
+    IMAGD_LAUNCH_CHECK("layernorm_bwd_kernel");
+    if (dgamma != nullptr) {
+        IMAGD_CHECK_ARG(dbeta && ws, "layernorm_bwd: dbeta / ws");
+        const int splits = colreduce_splits(rows, 1, C);
+        dim3 grid((C + 63) / 64, 1, splits);
+        colreduce_kernel<1><<<grid, 256, 0, ST(stream)>>>(BF(x), ldx, BF(dy), lddy, rowstat, static_cast<float*>(ws), C, rows, 1,
+                                                          splits);
+        IMAGD_LAUNCH_CHECK("colreduce_kernel<1>");
+        colreduce_fold_kernel<<<blocks_for(C, 256), 256, 0, ST(stream)>>>(static_cast<const float*>(ws), dgamma, dbeta, C, 1,
+                                                                         splits);
+        IMAGD_LAUNCH_CHECK("colreduce_fold_kernel");
+    }
+    return IMAGD_OK;
+}
+
+extern "C" int imagd_groupnorm_bwd_bf16(const void* x, const void* dy, void* dx, int NB, int HW, int C, int groups,
+                                        const float* gamma, const float* beta, float eps, int fuse_silu, float* dgamma,
+                                        float* dbeta, void* ws, imagd_stream stream) {
+    IMAGD_CHECK_ARG(x && dy && dx && ws && NB > 0 && HW > 0 && C % 8 == 0 && groups > 0 && C % groups == 0 && C / groups <= 256,
+                    "groupnorm_bwd: bad argument");
+    // ws: stat [NB * groups * 4] | pc [2 * NB * C]
+    float* stat = static_cast<float*>(ws);
+    float* pc = stat + static_cast<int64_t>(NB) * groups * 4;
+    groupnorm_bwd_reduce_kernel<<<dim3(groups, NB), 256, 0, ST(stream)>>>(BF(x), BF(dy), HW, C, groups, gamma, beta, eps,
+                                                                         fuse_silu, stat, pc, NB);
+    IMAGD_LAUNCH_CHECK("groupnorm_bwd_reduce_kernel");
+    const int64_t total = static_cast<int64_t>(NB) * HW * (C / 8);
+    groupnorm_bwd_apply_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(BF(x), BF(dy), BFW(dx), HW, C, groups, gamma, beta,
+                                                                              fuse_silu, stat, total);
+    IMAGD_LAUNCH_CHECK("groupnorm_bwd_apply_kernel");
+    if (dgamma != nullptr) {
+        IMAGD_CHECK_ARG(dbeta, "groupnorm_bwd: dbeta");
+        // fold the per-sample partials: pc is [2][NB][C] = the colreduce part layout with splits = NB, groups = 1
+        colreduce_fold_kernel<<<blocks_for(C, 256), 256, 0, ST(stream)>>>(pc, dgamma, dbeta, C, 1, NB);
+        IMAGD_LAUNCH_CHECK("colreduce_fold_kernel");
+    }
+    return IMAGD_OK;
+}
+
+extern "C" int64_t imagd_groupnorm_bwd_ws_bytes(int NB, int C, int groups) {
+    return (static_cast<int64_t>(NB) * groups * 4 + static_cast<int64_t>(2) * NB * C) * 4;
+}
+
+extern "C" int imagd_act_bf16(const void* x, const void* dy, void* y, int64_t n, int mode, imagd_stream stream) {
+    IMAGD_CHECK_ARG(x && y && n > 0 && (mode == IMAGD_ACT_SILU || mode == IMAGD_ACT_GELU), "act: bad argument");
+    IMAGD_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 3) == 0, "act: alignment");
+    act_kernel<<<blocks_for((n + 1) / 2, 256), 256, 0, ST(stream)>>>(BF(x), BF(dy), BFW(y), n, mode);
+    IMAGD_LAUNCH_CHECK("act_kernel");
+    return IMAGD_OK;
+}
+
+extern "C" int imagd_geglu_bf16(const void* h, int64_t ldh, const void* dout, void* out, int64_t ldo, int64_t M, int F,
+                                imagd_stream stream) {
+    IMAGD_CHECK_ARG(h && out && M > 0 && F > 0 && F % 2 == 0 && ldh % 2 == 0 && ldo % 2 == 0, "geglu: bad argument");
+    geglu_kernel<<<blocks_for(M * (F / 2), 256), 256, 0, ST(stream)>>>(BF(h), ldh, BF(dout), BFW(out), ldo, M, F);
+    IMAGD_LAUNCH_CHECK("geglu_kernel");
+    return IMAGD_OK;
+}
+
+extern "C" int imagd_mse_loss_grad(const float* pred, const float* target, float* grad, float* loss, int64_t n, float grad_scale,
+                                   void* ws, imagd_stream stream) {
+    IMAGD_CHECK_ARG(pred && target && grad && loss && ws && n > 0, "mse: bad argument");
+    const int blocks = static_cast<int>(n / 1024 < 1 ? 1 : (n / 1024 > 296 ? 296 : n / 1024));
+    mse_kernel<<<blocks, 256, 0, ST(stream)>>>(pred, target, grad, static_cast<float*>(ws), n, grad_scale * 2.f / static_cast<float>(n));
+    IMAGD_LAUNCH_CHECK("mse_kernel");
+    mse_fold_kernel<<<1, 32, 0, ST(stream)>>>(static_cast<const float*>(ws), blocks, 1.f / static_cast<float>(n), loss);
+    IMAGD_LAUNCH_CHECK("mse_fold_kernel");
+    return IMAGD_OK;
+}
+
+extern "C" int imagd_adamw_step(float* master, void* param, const void* grad, float* m, float* v, int64_t n, float lr, float beta1,
+                                float beta2, float eps, float weight_decay, int step, float grad_scale, imagd_stream stream) {
+    IMAGD_CHECK_ARG(master && param && grad && m && v && n > 0 && step >= 1, "adamw: bad argument");
+    const float bc1 = 1.f - powf(beta1, static_cast<float>(step)), bc2 = 1.f - powf(beta2, static_cast<float>(step));
+    adamw_kernel<<<blocks_for(n, 256), 256, 0, ST(stream)>>>(master, BFW(param), BF(grad), m, v, n, lr, beta1, beta2, eps,
+                                                            weight_decay, bc1, bc2, grad_scale);
+    IMAGD_LAUNCH_CHECK("adamw_kernel");
+    return IMAGD_OK;
+}

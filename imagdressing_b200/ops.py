@@ -374,3 +374,226 @@ def broadcast_row(vec: torch.Tensor, out: torch.Tensor, row: int) -> torch.Tenso
     _lib.check(lib.imagd_broadcast_row_bf16(vec.data_ptr(), out.data_ptr(), B, R, row, C, _stream()),
                "imagd_broadcast_row_bf16")
     return out
+
+
+# ====================================================================================================== training step
+# Wrappers of the backward / training kernels (include/imagd_b200.h "Training step"). They are
+# called by the torch.autograd.Function classes of imagdressing_b200/autograd.py.
+_ws_cache = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    ws = _ws_cache.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 20), device=device, dtype=torch.uint8)
+        _ws_cache[device] = ws
+    return ws
+
+
+class AttnSaved:
+    """What a training-mode attention forward keeps for its backward."""
+
+    __slots__ = ("lse", "o0", "o1", "lq_pad", "out")
+
+    def __init__(self, lse, o0, o1, lq_pad, out):
+        self.lse, self.o0, self.o1, self.lq_pad, self.out = lse, o0, o1, lq_pad, out
+
+
+def attention_train(q: torch.Tensor, B: int, Lq: int, heads: int, head_dim: int, s0: KVStream, s1: Optional[KVStream] = None,
+                    *, sm_scale: Optional[float] = None):
+    """attention() that also returns AttnSaved (per-stream log-sum-exp rows and un-weighted per-stream outputs)."""
+    lib = _lib.load()
+    assert q.dtype == BF16 and q.stride(-1) == 1
+    C = heads * head_dim
+    out = torch.empty(B * Lq, C, device=q.device, dtype=BF16)
+    lq_pad = (Lq + 127) // 128 * 128
+    lse = torch.full((2, B, heads, lq_pad), float("inf"), device=q.device, dtype=torch.float32)
+    two = s1 is not None
+    o0 = torch.empty_like(out) if two else None
+    o1 = torch.empty_like(out) if two else None
+    aux = _lib.AttnTrain()
+    aux.lse, aux.out_s0, aux.out_s1, aux.ld_s, aux.lq_pad = lse.data_ptr(), _ptr(o0), _ptr(o1), C, lq_pad
+    if sm_scale is None:
+        sm_scale = head_dim ** -0.5
+    rc = lib.imagd_attention_train_fwd_bf16(q.data_ptr(), q.stride(-2), out.data_ptr(), C, B, Lq, heads, head_dim,
+                                            ctypes.byref(s0), ctypes.byref(s1) if two else None, float(sm_scale),
+                                            ctypes.byref(aux), _stream())
+    _lib.check(rc, "imagd_attention_train_fwd_bf16")
+    return out, AttnSaved(lse, o0, o1, lq_pad, out)
+
+
+def attention_bwd(q: torch.Tensor, d_out: torch.Tensor, B: int, Lq: int, heads: int, head_dim: int, s0: KVStream,
+                  s1: Optional[KVStream], saved: AttnSaved, *, sm_scale: Optional[float] = None, dq=None, dkv0=None, dkv1=None):
+    """dq: [B*Lq, >= C] view to receive dQ (or None); dkv0 / dkv1: (dk_view, dv_view) laid out like the stream's k / v (same
+    row stride and sample stride) or None. d_out: [B*Lq, C] bf16 (row stride arbitrary)."""
+    lib = _lib.load()
+    assert d_out.dtype == BF16 and d_out.stride(-1) == 1 and q.dtype == BF16
+    two = s1 is not None
+    dsum = torch.zeros_like(saved.lse)
+    if two:
+        rc = lib.imagd_attention_bwd_prep(d_out.data_ptr(), d_out.stride(-2), saved.o0.data_ptr(), saved.o1.data_ptr(),
+                                          saved.o0.stride(-2), float(s0.out_scale), float(s1.out_scale), dsum.data_ptr(), B, Lq,
+                                          heads, head_dim, saved.lq_pad, _stream())
+    else:  # out = w0 * O_0, so D_0 = rowsum(dO o out)
+        rc = lib.imagd_attention_bwd_prep(d_out.data_ptr(), d_out.stride(-2), saved.out.data_ptr(), None,
+                                          saved.out.stride(-2), 1.0, 0.0, dsum.data_ptr(), B, Lq, heads, head_dim,
+                                          saved.lq_pad, _stream())
+    _lib.check(rc, "imagd_attention_bwd_prep")
+    if sm_scale is None:
+        sm_scale = head_dim ** -0.5
+
+    def kvp(pair):
+        if pair is None:
+            return None, None, 0
+        dk, dv = pair
+        assert dk.dtype == BF16 and dk.stride(-1) == 1 and dv.stride(-2) == dk.stride(-2)
+        return dk.data_ptr(), dv.data_ptr(), dk.stride(-2)
+
+    k0p, v0p, ld0 = kvp(dkv0)
+    k1p, v1p, ld1 = kvp(dkv1)
+    rc = lib.imagd_attention_bwd_bf16(q.data_ptr(), q.stride(-2), d_out.data_ptr(), d_out.stride(-2), B, Lq, heads, head_dim,
+                                      ctypes.byref(s0), ctypes.byref(s1) if two else None, float(sm_scale),
+                                      saved.lse.data_ptr(), dsum.data_ptr(), saved.lq_pad, _ptr(dq),
+                                      dq.stride(-2) if dq is not None else 0, k0p, v0p, ld0, k1p, v1p, ld1, _stream())
+    _lib.check(rc, "imagd_attention_bwd_bf16")
+
+
+def transpose(x: torch.Tensor, pad_to: int = 8) -> torch.Tensor:
+    """x: [rows, cols] bf16 (row stride arbitrary) -> [cols, rows_pad] with zero columns up to a multiple of `pad_to`."""
+    lib = _lib.load()
+    assert x.dim() == 2 and x.dtype == BF16 and x.stride(1) == 1
+    rows, cols = x.shape
+    rows_pad = (rows + pad_to - 1) // pad_to * pad_to
+    out = torch.empty(cols, rows_pad, device=x.device, dtype=BF16)
+    _lib.check(lib.imagd_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), rows_pad, rows, cols, rows_pad, _stream()),
+               "imagd_transpose_bf16")
+    return out
+
+
+def im2col3x3_t(x: torch.Tensor) -> torch.Tensor:
+    """x: [NB, H, W, C] bf16 -> [roundup(9*C, 8), roundup(NB*H*W, 8)] transposed stride-1 pad-1 patches (tap-major rows)."""
+    lib = _lib.load()
+    NB, H, W, C = x.shape
+    assert x.is_contiguous() and x.dtype == BF16
+    P = NB * H * W
+    ldo = (P + 7) // 8 * 8
+    rows = (9 * C + 7) // 8 * 8
+    out = (torch.zeros if rows != 9 * C else torch.empty)(rows, ldo, device=x.device, dtype=BF16)
+    _lib.check(lib.imagd_im2col3x3_t_bf16(x.data_ptr(), out.data_ptr(), ldo, NB, H, W, C, _stream()), "imagd_im2col3x3_t_bf16")
+    return out
+
+
+def col2im3x3_s2(dcol: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """Adjoint of im2col3x3_s2: dcol [NB, H/2, W/2, 9*C] -> [NB, H, W, C]."""
+    lib = _lib.load()
+    NB, C = dcol.shape[0], dcol.shape[-1] // 9
+    assert dcol.is_contiguous() and dcol.dtype == BF16
+    out = torch.empty(NB, H, W, C, device=dcol.device, dtype=BF16)
+    _lib.check(lib.imagd_col2im3x3_s2_bf16(dcol.data_ptr(), out.data_ptr(), NB, H, W, C, _stream()), "imagd_col2im3x3_s2_bf16")
+    return out
+
+
+def downsum2x(dy: torch.Tensor) -> torch.Tensor:
+    """Adjoint of upsample2x: [NB, 2H, 2W, C] -> [NB, H, W, C]."""
+    lib = _lib.load()
+    NB, H2, W2, C = dy.shape
+    assert dy.is_contiguous() and dy.dtype == BF16
+    out = torch.empty(NB, H2 // 2, W2 // 2, C, device=dy.device, dtype=BF16)
+    _lib.check(lib.imagd_downsum2x_bf16(dy.data_ptr(), out.data_ptr(), NB, H2 // 2, W2 // 2, C, _stream()), "imagd_downsum2x_bf16")
+    return out
+
+
+def colsum(x: torch.Tensor, rows_per_group: Optional[int] = None) -> torch.Tensor:
+    """x: [rows, C] bf16 -> fp32 [groups, C] column sums over consecutive groups of rows_per_group rows."""
+    lib = _lib.load()
+    rows, C, ldx = _rows2d(x)
+    rpg = rows if rows_per_group is None else int(rows_per_group)
+    groups = rows // rpg
+    assert groups * rpg == rows and x.dtype == BF16
+    out = torch.empty(groups, C, device=x.device, dtype=torch.float32)
+    ws = _workspace(x.device, lib.imagd_colreduce_ws_bytes(rpg, groups, C))
+    _lib.check(lib.imagd_colsum_bf16(x.data_ptr(), ldx, rpg, groups, C, out.data_ptr(), ws.data_ptr(), _stream()),
+               "imagd_colsum_bf16")
+    return out
+
+
+def layernorm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma, eps: float, need_affine: bool):
+    """-> (dx bf16 like x, dgamma fp32 [C] | None, dbeta fp32 [C] | None)."""
+    lib = _lib.load()
+    rows, C, ldx = _rows2d(x)
+    _, _, lddy = _rows2d(dy)
+    dx = torch.empty(*x.shape, device=x.device, dtype=BF16)
+    rowstat = torch.empty(rows, 2, device=x.device, dtype=torch.float32)
+    dg = torch.empty(C, device=x.device, dtype=torch.float32) if need_affine else None
+    db = torch.empty(C, device=x.device, dtype=torch.float32) if need_affine else None
+    ws = _workspace(x.device, lib.imagd_colreduce_ws_bytes(rows, 1, C))
+    rc = lib.imagd_layernorm_bwd_bf16(x.data_ptr(), ldx, dy.data_ptr(), lddy, dx.data_ptr(), _rows2d(dx)[2], rows, C, _ptr(gamma),
+                                      float(eps), _ptr(dg), _ptr(db), rowstat.data_ptr(), ws.data_ptr(), _stream())
+    _lib.check(rc, "imagd_layernorm_bwd_bf16")
+    return dx, dg, db
+
+
+def groupnorm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma, beta, groups: int, eps: float, silu: bool, need_affine: bool):
+    """x, dy: contiguous [NB, HW..., C] bf16 -> (dx, dgamma | None, dbeta | None)."""
+    lib = _lib.load()
+    assert x.is_contiguous() and dy.is_contiguous() and x.dtype == BF16 and dy.dtype == BF16
+    NB, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (NB * C)
+    dx = torch.empty_like(x)
+    dg = torch.empty(C, device=x.device, dtype=torch.float32) if need_affine else None
+    db = torch.empty(C, device=x.device, dtype=torch.float32) if need_affine else None
+    ws = _workspace(x.device, lib.imagd_groupnorm_bwd_ws_bytes(NB, C, groups))
+    rc = lib.imagd_groupnorm_bwd_bf16(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), NB, HW, C, groups, _ptr(gamma), _ptr(beta),
+                                      float(eps), 1 if silu else 0, _ptr(dg), _ptr(db), ws.data_ptr(), _stream())
+    _lib.check(rc, "imagd_groupnorm_bwd_bf16")
+    return dx, dg, db
+
+
+def act(x: torch.Tensor, mode: int, dy: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """mode ACT_SILU / ACT_GELU. dy None: act(x); else dy * act'(x). Contiguous bf16."""
+    lib = _lib.load()
+    assert x.is_contiguous() and x.dtype == BF16 and (dy is None or (dy.is_contiguous() and dy.dtype == BF16))
+    y = torch.empty_like(x)
+    _lib.check(lib.imagd_act_bf16(x.data_ptr(), _ptr(dy), y.data_ptr(), x.numel(), int(mode), _stream()), "imagd_act_bf16")
+    return y
+
+
+def geglu(h: torch.Tensor, dout: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """h: [..., 2F] = [value | gate]. dout None: value * gelu(gate) [..., F]; else dh [..., 2F]."""
+    lib = _lib.load()
+    assert h.is_contiguous() and h.dtype == BF16
+    F2 = h.shape[-1]
+    M = h.numel() // F2
+    if dout is None:
+        out = torch.empty(*h.shape[:-1], F2 // 2, device=h.device, dtype=BF16)
+        ldo = F2 // 2
+    else:
+        assert dout.is_contiguous() and dout.dtype == BF16
+        out = torch.empty_like(h)
+        ldo = F2
+    _lib.check(lib.imagd_geglu_bf16(h.data_ptr(), F2, _ptr(dout), out.data_ptr(), ldo, M, F2 // 2, _stream()), "imagd_geglu_bf16")
+    return out
+
+
+def mse_loss_grad(pred: torch.Tensor, target: torch.Tensor, grad_scale: float = 1.0):
+    """-> (loss fp32 [1], grad fp32 like pred) of mean((pred - target)^2)."""
+    lib = _lib.load()
+    assert pred.dtype == torch.float32 and target.dtype == torch.float32 and pred.is_contiguous() and target.is_contiguous()
+    grad = torch.empty_like(pred)
+    loss = torch.empty(1, device=pred.device, dtype=torch.float32)
+    ws = _workspace(pred.device, 4096)
+    _lib.check(lib.imagd_mse_loss_grad(pred.data_ptr(), target.data_ptr(), grad.data_ptr(), loss.data_ptr(), pred.numel(),
+                                       float(grad_scale), ws.data_ptr(), _stream()), "imagd_mse_loss_grad")
+    return loss, grad
+
+
+def adamw_step(master: torch.Tensor, param: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: torch.Tensor, *, lr: float,
+               beta1: float, beta2: float, eps: float, weight_decay: float, step: int, grad_scale: float = 1.0) -> None:
+    """In place: fp32 master / moments, bf16 gradient, bf16 working copy (flat, contiguous, equal length)."""
+    lib = _lib.load()
+    n = master.numel()
+    assert master.dtype == torch.float32 and m.dtype == torch.float32 and v.dtype == torch.float32
+    assert param.dtype == BF16 and grad.dtype == BF16 and param.numel() == n and grad.numel() == n
+    _lib.check(lib.imagd_adamw_step(master.data_ptr(), param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), n, float(lr),
+                                    float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale),
+                                    _stream()), "imagd_adamw_step")

@@ -226,6 +226,81 @@ int imagd_cfg_ddim_step(const float* eps_cond, const float* eps_uncond, float gu
                         const float* noise, const float* blend_coef, int NB, int C, int HW,
                         imagd_stream stream);
 
+/* ================================================================================================================
+ * Training step (reference train.py:255-281 SDModel.forward, :573-605 loss + backward, :386-398 AdamW).
+ * The reference obtains every gradient from torch autograd over the diffusers modules; these entry points are the backward
+ * kernels a torch.autograd.Function per operator calls (imagdressing_b200/autograd.py).
+ * ================================================================================================================ */
+
+/* Extra outputs of a training-mode attention forward. lse: [2, B, heads, lq_pad] fp32, the per-row log-sum-exp of each
+ * stream in the log2 domain (m + log2 l); the caller pre-fills it with +inf (padding rows then give P = 0 in the backward);
+ * lq_pad = a multiple of 128 >= Lq. out_s0 / out_s1: the un-weighted per-stream outputs softmax(q k_s^T) v_s, bf16
+ * [B*Lq, ld_s] (needed for D_s = w_s rowsum(dO o O_s)); may be NULL when there is one stream (then D = rowsum(dO o out)). */
+typedef struct imagd_attn_train {
+    float* lse;
+    void* out_s0;
+    void* out_s1;
+    int64_t ld_s;
+    int32_t lq_pad;
+} imagd_attn_train;
+
+/* imagd_attention_bf16 + the imagd_attn_train outputs (adapter/attention_processor.py:589-612 under autograd). */
+int imagd_attention_train_fwd_bf16(const void* q, int64_t q_ld, void* out, int64_t out_ld, int B, int Lq, int heads,
+                                   int head_dim, const imagd_kv_stream* s0, const imagd_kv_stream* s1, float sm_scale,
+                                   const imagd_attn_train* aux, imagd_stream stream);
+/* dsum[s, b, h, q] = w_s * sum_d d_out[b, q, h, d] * o_s[b, q, h, d]  (o1 NULL: one stream); padding rows are left as the
+ * caller initialised them (0). */
+int imagd_attention_bwd_prep(const void* d_out, int64_t do_ld, const void* o0, const void* o1, int64_t ld_s, float w0, float w1,
+                             float* dsum, int B, int Lq, int heads, int head_dim, int lq_pad, imagd_stream stream);
+/* Backward of the two-stream attention (recompute-S flash style on tcgen05, deterministic, no atomics):
+ *   dq [B*Lq, dq_ld]           += over both streams   (NULL: skipped)
+ *   dk_s / dv_s                 same layout as the stream's k / v (row stride dkv_s_ld, sample stride = the stream's
+ *                               sample_rows or len)      (NULL pair: that stream's key / value gradients are skipped)
+ * Every query sample must own its keys in both streams (no broadcast, n_query_samples >= B): the training layout
+ * (train.py:266-268 keeps every cache row). */
+int imagd_attention_bwd_bf16(const void* q, int64_t q_ld, const void* d_out, int64_t do_ld, int B, int Lq, int heads,
+                             int head_dim, const imagd_kv_stream* s0, const imagd_kv_stream* s1, float sm_scale,
+                             const float* lse, const float* dsum, int lq_pad, void* dq, int64_t dq_ld, void* dk0, void* dv0,
+                             int64_t dkv0_ld, void* dk1, void* dv1, int64_t dkv1_ld, imagd_stream stream);
+
+/* y[c, r] = x[r, c] (r < rows), 0 for rows <= r < rows_pad; y: [cols, ldy]. Builds the K-contiguous operands of the
+ * dgrad / wgrad GEMMs (dX = dY W, dW = dY^T X) for imagd_gemm_bf16. */
+int imagd_transpose_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int cols, int rows_pad,
+                         imagd_stream stream);
+/* Transposed im2col of a stride-1 pad-1 3x3 conv input: out[tap*C + c, p] = x[n, y+ky-1, x+kx-1, c], p = (n*H + y)*W + x,
+ * zero for p >= NB*H*W; out: [9*C, ldo]. The B operand of the conv weight-gradient GEMM dW[Cout, 9 Cin] = dY^T col^T. */
+int imagd_im2col3x3_t_bf16(const void* x, void* out, int64_t ldo, int NB, int H, int W, int C, imagd_stream stream);
+/* Adjoint of imagd_im2col3x3_s2_bf16: dcol [NB, H/2, W/2, 9*C] -> dx [NB, H, W, C]. */
+int imagd_col2im3x3_s2_bf16(const void* dcol, void* dx, int NB, int H, int W, int C, imagd_stream stream);
+/* Adjoint of imagd_upsample2x_bf16: dy [NB, 2H, 2W, C] -> dx [NB, H, W, C] (sum of each 2x2 block). */
+int imagd_downsum2x_bf16(const void* dy, void* dx, int NB, int H, int W, int C, imagd_stream stream);
+/* out[g, c] = sum over the rows of group g of x[r, c] (fp32; bias gradients: groups = 1; ResnetBlock2D time-embedding
+ * gradients: one group per sample). Fixed-order two-stage reduction; ws >= imagd_colreduce_ws_bytes. */
+int64_t imagd_colreduce_ws_bytes(int rows_per_group, int groups, int C);
+int imagd_colsum_bf16(const void* x, int64_t ldx, int rows_per_group, int groups, int C, float* out, void* ws,
+                      imagd_stream stream);
+/* LayerNorm backward: dx, and (dgamma non-NULL) dgamma / dbeta [C] fp32. rowstat: [rows, 2] fp32 scratch (mean, rstd). */
+int imagd_layernorm_bwd_bf16(const void* x, int64_t ldx, const void* dy, int64_t lddy, void* dx, int64_t lddx, int rows, int C,
+                             const float* gamma, float eps, float* dgamma, float* dbeta, float* rowstat, void* ws,
+                             imagd_stream stream);
+/* GroupNorm (+SiLU) backward over contiguous [NB, HW, C]: dx, and (dgamma non-NULL) dgamma / dbeta [C] fp32. */
+int64_t imagd_groupnorm_bwd_ws_bytes(int NB, int C, int groups);
+int imagd_groupnorm_bwd_bf16(const void* x, const void* dy, void* dx, int NB, int HW, int C, int groups, const float* gamma,
+                             const float* beta, float eps, int fuse_silu, float* dgamma, float* dbeta, void* ws,
+                             imagd_stream stream);
+/* Elementwise activation (mode IMAGD_ACT_SILU / IMAGD_ACT_GELU): dy NULL: y = act(x); else y = dy * act'(x). */
+int imagd_act_bf16(const void* x, const void* dy, void* y, int64_t n, int mode, imagd_stream stream);
+/* GEGLU on an un-fused projection h = [value | gate], [M, 2F]: dout NULL: out [M, F] = value * gelu(gate);
+ * else out [M, 2F] = [dout * gelu(gate) | dout * value * gelu'(gate)] (dout contiguous [M, F]). */
+int imagd_geglu_bf16(const void* h, int64_t ldh, const void* dout, void* out, int64_t ldo, int64_t M, int F,
+                     imagd_stream stream);
+/* loss[0] = mean((pred - target)^2) (train.py:577) and grad = grad_scale * 2 (pred - target) / n, fp32; ws >= 2 KB. */
+int imagd_mse_loss_grad(const float* pred, const float* target, float* grad, float* loss, int64_t n, float grad_scale, void* ws,
+                        imagd_stream stream);
+/* AdamW, decoupled weight decay (train.py:386-398), fp32 master weights + moments, bf16 gradient in, bf16 working copy out. */
+int imagd_adamw_step(float* master, void* param, const void* grad, float* m, float* v, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int step, float grad_scale, imagd_stream stream);
+
 #ifdef __cplusplus
 }
 #endif
