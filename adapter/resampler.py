@@ -123,6 +123,12 @@ class Resampler(_PerceiverStack):
 
     def forward(self, x):
         in_dtype = x.dtype
+        if getattr(self, "_train_path", False) and torch.is_grad_enabled():
+            # training step (reference train.py:257): grad-enabled operators
+            from imagdressing_b200.train import resampler_forward_train
+
+            out = resampler_forward_train(self, x)
+            return out if in_dtype == BF16 else out.to(in_dtype)
         lat = self.latents.detach().to(BF16).repeat(x.size(0), 1, 1).contiguous()
         out = self._run_stack(x.to(BF16), lat)
         return out if in_dtype == BF16 else out.to(in_dtype)

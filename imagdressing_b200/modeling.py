@@ -713,6 +713,15 @@ class UNet2DConditionModel(_ModelBase):
                 encoder_attention_mask=None, return_dict: bool = True, timestep_table=None, out=None):
         """eps = UNet(sample [N,4,h,w], t, text [N,77|81,768]); returns (eps [N,4,h,w] in sample.dtype,).
         ControlNet residuals may be token-major bf16 tensors (from our ControlNetModel) or NCHW tensors."""
+        if getattr(self, "_train_path", False) and torch.is_grad_enabled():
+            # training step (SURVEY.md 8 row a13; reference train.py:259-264,272-279): autograd operators, no CUDA graph
+            if down_block_additional_residuals is not None or mid_block_additional_residual is not None:
+                raise NotImplementedError("the reference's training step has no ControlNet (train.py:255-281)")
+            from .train import unet_forward_train
+
+            eps32 = unet_forward_train(self, sample, timestep, encoder_hidden_states, cross_attention_kwargs)
+            res = eps32 if sample.dtype == torch.float32 else eps32.to(sample.dtype)
+            return (res,) if not return_dict else UNet2DConditionOutput(sample=res)
         eps32 = self.forward_tokens(sample, timestep, encoder_hidden_states, cross_attention_kwargs,
                                     down_block_additional_residuals, mid_block_additional_residual,
                                     timestep_table=timestep_table, out=out)

@@ -161,6 +161,13 @@ def attention_forward(proc, attn, hidden_states: torch.Tensor, encoder_hidden_st
     replays a captured CUDA graph for the steps).
     text_len: use only the first text_len context tokens for stream 0 (LoRAIP strips the IP tokens, :811-815).
     """
+    if getattr(attn, "_train_path", False) and torch.is_grad_enabled() and not prepare_only:
+        # training step (SURVEY.md 8 row a13): autograd operators instead of the fused, cached inference sequence
+        if lora is not None or text_len is not None:
+            raise NotImplementedError("training path: the reference trains RefS / C processors only (train.py:338-366)")
+        from .train import train_attention_forward
+
+        return train_attention_forward(proc, attn, hidden_states, encoder_hidden_states, second)
     in_dtype = hidden_states.dtype
     B, L, C = hidden_states.shape
     heads = attn.heads

@@ -1,0 +1,389 @@
+"""Training step of IMAGDressing-v1 on the sm_100a kernels (BASELINE.json configs[4]).
+
+Mirrors /root/reference/train.py:
+  * SDModel                      train.py:244-281  (Resampler -> garment UNet at t = 0 with the cache processors, EVERY batch row
+                                                    kept and grad-enabled -> denoising UNet with the hybrid processors)
+  * trainable set                train.py:368-379  (image projection + garment UNet + adapter modules; denoising UNet frozen)
+  * loss / backward              train.py:573-605  (MSE on the epsilon target, backward through both UNets)
+  * optimizer                    train.py:386-398  (AdamW; DeepSpeed bf16: fp32 master weights, bf16 working copy)
+  * data parallelism             train.py:601-609  (DeepSpeed ZeRO-2 gradient reduction) -> bucketed NCCL all-reduce of one flat
+                                                    bf16 gradient buffer, launched per bucket from gradient-ready hooks so that
+                                                    the reduction overlaps the rest of the backward pass
+
+The same nn.Module trees as inference (imagdressing_b200.modeling, adapter.*) hold the parameters; with the training path
+enabled and grad mode on, their forward walks the operators through imagdressing_b200.autograd (un-fused where a fused
+inference epilogue would lose what the backward needs: GEGLU pre-activations, LayerNorm outputs). torch autograd orders the
+backward; all arithmetic is in libimagd_b200.so.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import autograd as ag
+from . import modeling, ops
+from .processors import _packer, _ver
+
+BF16 = torch.bfloat16
+
+
+def enable_training_path(model: nn.Module, on: bool = True) -> nn.Module:
+    """Route `model.forward` (UNet2DConditionModel / Resampler) and its attention processors through the autograd operators
+    whenever grad mode is enabled. Inference calls (torch.no_grad) keep the fused / CUDA-graph path."""
+    model._train_path = bool(on)
+    for m in model.modules():
+        if isinstance(m, modeling.Attention):
+            m._train_path = bool(on)
+    return model
+
+
+def _frozen(*params) -> bool:
+    return not any(p is not None and p.requires_grad for p in params)
+
+
+def _bfc(t: torch.Tensor) -> torch.Tensor:
+    t = t if t.dtype == BF16 else t.to(BF16)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ attention processors
+def train_attention_forward(proc, attn, hidden_states, encoder_hidden_states, second=None) -> torch.Tensor:
+    """The grad-enabled counterpart of processors.attention_forward (adapter/attention_processor.py:531-627 under autograd):
+    projection GEMMs, two-stream attention, output projection (+ the block's residual when offered)."""
+    in_dtype = hidden_states.dtype
+    B, L, C = hidden_states.shape
+    x = _bfc(hidden_states)
+    packed = _packer(proc, attn)
+
+    def cat_w(key, *lins):
+        if _frozen(*[l.weight for l in lins]):
+            return packed("train:" + key, lambda: torch.cat([l.weight.detach() for l in lins], 0).to(BF16).contiguous(),
+                          _ver(*lins))
+        return torch.cat([ag._bf(l.weight) for l in lins], 0)
+
+    if encoder_hidden_states is None:
+        q_src, kv0 = ag.linear(x, cat_w("qkv", attn.to_q, attn.to_k, attn.to_v)), None
+    else:
+        q_src = ag.linear(x, attn.to_q.weight)
+        kv0 = ag.linear(_bfc(encoder_hidden_states), cat_w("kv", attn.to_k, attn.to_v))
+    kv1, w1 = None, 1.0
+    if second is not None:
+        src, to_k, to_v, w1, n_q = second[:5]
+        if len(second) > 5 or src.shape[0] != B or n_q < B:
+            raise NotImplementedError("training: the second stream must cover every sample with its own keys "
+                                      "(train.py:266-268 keeps every cache row)")
+        kv1 = ag.linear(_bfc(src), cat_w(f"kv2:{id(to_k)}", to_k, to_v))
+    o = ag.attention(q_src, kv0, kv1, attn.heads, float(w1))
+    residual = getattr(attn, "_fused_residual", None)
+    if residual is not None and residual.dtype == BF16 and residual.shape == hidden_states.shape:
+        attn._fused_residual = None
+    else:
+        residual = None
+    y = ag.linear(o, attn.to_out[0].weight, attn.to_out[0].bias, residual)
+    return y if in_dtype == BF16 else y.to(in_dtype)
+
+
+# ------------------------------------------------------------------------------------------------ UNet
+def _conv_w(conv: nn.Conv2d, owner=None, key: Optional[str] = None) -> torch.Tensor:
+    """Tap-major bf16 weight of a 3x3 conv: the module's inference pack when frozen, a differentiable repack otherwise."""
+    if owner is not None and _frozen(conv.weight):
+        return owner._packed()[key]
+    return ag.pack_conv3x3(conv.weight)
+
+
+def _w1x1(conv: nn.Conv2d) -> torch.Tensor:
+    return conv.weight.reshape(conv.weight.shape[0], -1)
+
+
+def _resnet(res: modeling.ResnetBlock2D, x, temb_all):
+    """h = conv1(silu(gn(x))) + time_emb_proj(silu(temb)); out = shortcut(x) + conv2(silu(gn(h)))  (SURVEY.md A.2)."""
+    h = ag.groupnorm(x, res.norm1, True)
+    h = ag.conv3x3(h, _conv_w(res.conv1, res, "w1"), res.conv1.bias,
+                   rowvec=temb_all[:, res.temb_offset:res.temb_offset + res.cout])
+    h = ag.groupnorm(h, res.norm2, True)
+    sc = x if res.conv_shortcut is None else ag.linear(x, _w1x1(res.conv_shortcut), res.conv_shortcut.bias)
+    return ag.conv3x3(h, _conv_w(res.conv2, res, "w2"), res.conv2.bias, residual=sc)
+
+
+def _attend(attn: modeling.Attention, normed, residual, ctx, kw):
+    attn._fused_residual = residual
+    out = attn(normed, encoder_hidden_states=ctx, **kw)
+    if attn._fused_residual is None:
+        return out
+    attn._fused_residual = None
+    return out.to(BF16) + residual  # foreign processor: plain residual add
+
+
+def _block(blk: modeling.BasicTransformerBlock, x, ctx, kw):
+    x = _attend(blk.attn1, ag.layernorm(x, blk.norm1), x, None, kw)
+    x = _attend(blk.attn2, ag.layernorm(x, blk.norm2), x, ctx, kw)
+    proj = blk.ff.net[0].proj
+    h = ag.Geglu.apply(ag.linear(ag.layernorm(x, blk.norm3), proj.weight, proj.bias))
+    return ag.linear(h, blk.ff.net[2].weight, blk.ff.net[2].bias, x)
+
+
+def _transformer(t2d: modeling.Transformer2DModel, x, ctx, kw):
+    NB, H, W, C = x.shape
+    h = ag.groupnorm(x, t2d.norm, False)
+    h = ag.linear(h, _w1x1(t2d.proj_in), t2d.proj_in.bias).view(NB, H * W, C)
+    for blk in t2d.transformer_blocks:
+        h = _block(blk, h, ctx, kw)
+    return ag.linear(h.view(NB, H, W, C), _w1x1(t2d.proj_out), t2d.proj_out.bias, x)
+
+
+def _downsample(ds: modeling.Downsample2D, x):
+    return ag.linear(ag.Im2colS2.apply(x), ag.pack_conv3x3(ds.conv.weight), ds.conv.bias)
+
+
+def _upsample(us: modeling.Upsample2D, x):
+    return ag.conv3x3(ag.Upsample2x.apply(x), ag.pack_conv3x3(us.conv.weight), us.conv.bias)
+
+
+def _time_conditioning(unet, NB: int, timestep, device) -> torch.Tensor:
+    """[NB, sum(Cout)] fp32: every ResnetBlock2D.time_emb_proj(silu(temb)) in one GEMM (M = batch rows on the tensor core).
+    Frozen model: the inference routine; trainable (garment UNet): autograd operators."""
+    te = unet.time_embedding
+    res = unet._resnets()
+    off = 0
+    for r in res:
+        r.temb_offset = off
+        off += r.cout
+    if _frozen(te.linear_1.weight, te.linear_2.weight, *[r.time_emb_proj.weight for r in res]):
+        with torch.no_grad():
+            return unet.time_conditioning(NB, timestep, device)
+    dim = unet.config.block_out_channels[0]
+    if not torch.is_tensor(timestep):
+        timestep = torch.tensor([float(timestep)], device=device)
+    t = timestep.reshape(-1).to(device=device, dtype=torch.float32)
+    if t.numel() == 1:
+        emb = ops.timestep_embedding(t, None, NB, dim)
+    else:
+        assert t.numel() == NB, "per-sample timesteps must match the batch"
+        emb = torch.cat([ops.timestep_embedding(t[i:i + 1], None, 1, dim) for i in range(NB)], 0)
+    h = ag.silu(ag.linear(emb.to(BF16), te.linear_1.weight, te.linear_1.bias))
+    h = ag.silu(ag.linear(h, te.linear_2.weight, te.linear_2.bias))
+    w = torch.cat([ag._bf(r.time_emb_proj.weight) for r in res], 0)
+    b = torch.cat([r.time_emb_proj.bias for r in res], 0)
+    return ag.linear(h, w, b, None, True)
+
+
+def unet_forward_train(unet: modeling.UNet2DConditionModel, sample, timestep, encoder_hidden_states,
+                       cross_attention_kwargs=None) -> torch.Tensor:
+    """Grad-enabled UNet2DConditionModel.forward (diffusers-0.24, called at train.py:259-264 and :272-279): eps fp32 NCHW."""
+    kw = cross_attention_kwargs or {}
+    NB = sample.shape[0]
+    ctx = _bfc(encoder_hidden_states)
+    temb_all = _time_conditioning(unet, NB, timestep, sample.device)
+    x = ag.ConvIn.apply(modeling._to_tokens(sample.detach()), ag.pack_conv3x3(unet.conv_in.weight), unet.conv_in.bias)
+    skips = [x]
+    for blk in unet.down_blocks:
+        for i, res in enumerate(blk.resnets):
+            x = _resnet(res, x, temb_all)
+            if blk.has_attn:
+                x = _transformer(blk.attentions[i], x, ctx, kw)
+            skips.append(x)
+        if blk.has_down:
+            x = _downsample(blk.downsamplers[0], x)
+            skips.append(x)
+    mid = unet.mid_block
+    x = _resnet(mid.resnets[0], x, temb_all)
+    x = _transformer(mid.attentions[0], x, ctx, kw)
+    x = _resnet(mid.resnets[1], x, temb_all)
+    for blk in unet.up_blocks:
+        for i, res in enumerate(blk.resnets):
+            x = _resnet(res, ag.Concat.apply(x, skips.pop()), temb_all)
+            if blk.has_attn:
+                x = _transformer(blk.attentions[i], x, ctx, kw)
+        if blk.has_up:
+            x = _upsample(blk.upsamplers[0], x)
+    x = ag.groupnorm(x, unet.conv_norm_out, True)
+    return ag.ConvOut.apply(x, ag.pack_conv3x3(unet.conv_out.weight), unet.conv_out.bias)
+
+
+# ------------------------------------------------------------------------------------------------ Resampler
+def resampler_forward_train(rs, x: torch.Tensor) -> torch.Tensor:
+    """Grad-enabled Resampler.forward (adapter/resampler.py:216-236, PerceiverAttention :49-78, FeedForward :13-20)."""
+    B = x.shape[0]
+    lat = ag._bf(rs.latents).repeat(B, 1, 1).contiguous()
+    x = ag.linear(_bfc(x), rs.proj_in.weight, rs.proj_in.bias)
+    for attn, ff in rs.layers:
+        xn, ln = ag.layernorm(x, attn.norm1), ag.layernorm(lat, attn.norm2)
+        q = ag.linear(ln, attn.to_q.weight)
+        kv = ag.linear(torch.cat([xn, ln], 1).contiguous(), attn.to_kv.weight)  # to_kv(cat(x, latents)): [B, n1+n2, k | v]
+        o = ag.attention(q, kv, None, attn.heads)  # (q d^-1/4)(k d^-1/4)^T == q k^T / sqrt(d)
+        lat = ag.linear(o, attn.to_out.weight, None, lat)
+        h = ag.gelu(ag.linear(ag.layernorm(lat, ff[0]), ff[1].weight))
+        lat = ag.linear(h, ff[3].weight, None, lat)
+    return ag.layernorm(ag.linear(lat, rs.proj_out.weight, rs.proj_out.bias), rs.norm_out)
+
+
+# ------------------------------------------------------------------------------------------------ SDModel
+class SDModel(nn.Module):
+    """train.py:244-281, same constructor and forward signature."""
+
+    def __init__(self, unet, ref_unet, proj, adapter_modules) -> None:
+        super().__init__()
+        self.unet = unet
+        self.ref_unet = ref_unet
+        self.proj = proj
+        self.adapter_modules = adapter_modules
+        for m in (unet, ref_unet, proj):
+            enable_training_path(m)
+
+    def forward(self, encoder_hidden_states, latents, ref_latents, clip_image_embeddings, timesteps):
+        ref_timesteps = torch.zeros_like(timesteps)
+        cloth_proj_embed = self.proj(clip_image_embeddings)                                      # :257
+        _ = self.ref_unet(ref_latents, ref_timesteps, cloth_proj_embed, return_dict=False)      # :259-264
+        sa_hidden_states = {name: proc.cache["hidden_states"]                                    # :266-268
+                            for name, proc in self.ref_unet.attn_processors.items()}
+        return self.unet(latents, timesteps, encoder_hidden_states=encoder_hidden_states,        # :272-279
+                         cross_attention_kwargs={"sa_hidden_states": sa_hidden_states}).sample
+
+
+def hidden_size_of(name: str, block_out_channels) -> int:
+    """train.py:341-348."""
+    if name.startswith("mid_block"):
+        return block_out_channels[-1]
+    if name.startswith("up_blocks"):
+        return list(reversed(block_out_channels))[int(name[len("up_blocks.")])]
+    return block_out_channels[int(name[len("down_blocks.")])]
+
+
+def install_training_processors(unet, ref_unet) -> nn.ModuleList:
+    """train.py:338-366: RefS processors on attn1 (to_k_ref / to_v_ref start as copies of the layer's to_k / to_v), C
+    processors on attn2, cache processors on the garment UNet. Returns `adapter_modules`."""
+    from adapter.attention_processor import CacheAttnProcessor2_0, CAttnProcessor2_0, RefSAttnProcessor2_0
+
+    st = unet.state_dict()
+    procs = {}
+    for name in unet.attn_processors.keys():
+        hidden = hidden_size_of(name, unet.config.block_out_channels)
+        if name.endswith("attn1.processor"):
+            p = RefSAttnProcessor2_0(name, hidden)
+            layer = name.split(".processor")[0]
+            p.load_state_dict({"to_k_ref.weight": st[layer + ".to_k.weight"], "to_v_ref.weight": st[layer + ".to_v.weight"]})
+            procs[name] = p
+        else:
+            procs[name] = CAttnProcessor2_0(name, hidden, unet.config.cross_attention_dim)
+    unet.set_attn_processor(procs)
+    ref_unet.set_attn_processor({n: CacheAttnProcessor2_0() for n in ref_unet.attn_processors.keys()})
+    return nn.ModuleList(unet.attn_processors.values())
+
+
+def set_trainable(unet, ref_unet, proj, adapter_modules) -> List[nn.Parameter]:
+    """train.py:368-379 (order matters: freezing the UNet also freezes the adapter modules registered inside it)."""
+    unet.requires_grad_(False)
+    proj.requires_grad_(True)
+    ref_unet.requires_grad_(True)
+    adapter_modules.requires_grad_(True)
+    return [*proj.parameters(), *ref_unet.parameters(), *adapter_modules.parameters()]
+
+
+# ------------------------------------------------------------------------------------------------ optimizer + data parallelism
+class FlatAdamW:
+    """AdamW over ONE flat buffer: the parameters become bf16 views of `self.param`, their .grad views of `self.grad`;
+    fp32 master weights and moments live beside them. With torch.distributed initialised, the gradient buffer is reduced in
+    buckets: each parameter's post-accumulate hook counts its bucket down and the completed bucket's all-reduce is launched
+    at once (NCCL over NVLink on its own stream), overlapping the remaining backward pass; step() waits for the handles and
+    applies the update with the 1/world scale folded into the kernel."""
+
+    def __init__(self, params: Iterable[nn.Parameter], lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
+                 bucket_bytes: int = 256 << 20, step_fn=None):
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params, "no trainable parameters"
+        dev = self.params[0].device
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.t = 0
+        self._step_fn = step_fn or ops.adamw_step
+        # backward produces gradients roughly in reverse registration order: lay the buffer out reversed so that buckets
+        # complete front to back
+        order = list(reversed(self.params))
+        sizes = [(p.numel() + 7) // 8 * 8 for p in order]  # 16-byte aligned views
+        total = sum(sizes)
+        self.master = torch.empty(total, device=dev, dtype=torch.float32)
+        self.param = torch.zeros(total, device=dev, dtype=BF16)
+        self.grad = torch.zeros(total, device=dev, dtype=BF16)
+        self.m = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.master.zero_()
+        off = 0
+        self._spans = []
+        with torch.no_grad():
+            for p, n in zip(order, sizes):
+                self.master[off:off + p.numel()].copy_(p.detach().reshape(-1).float())
+                view = self.param[off:off + p.numel()].view(p.shape)
+                view.copy_(p.detach())
+                p.data = view
+                p.grad = self.grad[off:off + p.numel()].view(p.shape)
+                self._spans.append((off, off + n))
+                off += n
+        # buckets: contiguous spans of ~bucket_bytes
+        per = max(1, bucket_bytes // 2)
+        self._buckets, self._bucket_of = [], []
+        lo, cnt = 0, 0
+        for i, (a, b) in enumerate(self._spans):
+            self._bucket_of.append(len(self._buckets))
+            cnt += 1
+            if b - lo >= per or i == len(self._spans) - 1:
+                self._buckets.append([lo, b, cnt])
+                lo, cnt = b, 0
+        self._pending = [b[2] for b in self._buckets]
+        self._handles = []
+        self._dist = torch.distributed.is_available() and torch.distributed.is_initialized() and \
+            torch.distributed.get_world_size() > 1
+        if self._dist:
+            for i, p in enumerate(order):
+                p.register_post_accumulate_grad_hook(self._make_hook(self._bucket_of[i]))
+
+    def _make_hook(self, bucket: int):
+        def hook(_p):
+            self._pending[bucket] -= 1
+            if self._pending[bucket] == 0:
+                lo, hi, _ = self._buckets[bucket]
+                self._handles.append(torch.distributed.all_reduce(self.grad[lo:hi], async_op=True))
+        return hook
+
+    def zero_grad(self):
+        self.grad.zero_()
+        self._pending = [b[2] for b in self._buckets]
+        self._handles = []
+
+    def reduce_remaining(self):
+        """Buckets whose parameters did not all receive a gradient this step (unused parameters) are reduced here."""
+        if not self._dist:
+            return
+        for i, n in enumerate(self._pending):
+            if n > 0:
+                lo, hi, _ = self._buckets[i]
+                self._handles.append(torch.distributed.all_reduce(self.grad[lo:hi], async_op=True))
+                self._pending[i] = 0
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+
+    def step(self):
+        self.reduce_remaining()
+        self.t += 1
+        world = torch.distributed.get_world_size() if self._dist else 1
+        self._step_fn(self.master, self.param, self.grad, self.m, self.v, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
+                      eps=self.eps, weight_decay=self.wd, step=self.t, grad_scale=1.0 / world)
+        # the kernel wrote through raw pointers: bump the version counters so that weight-derived caches keyed on
+        # (data_ptr, _version) — processors._ver, autograd._cached — see the update
+        torch.autograd.graph.increment_version([self.param, *self.params])
+
+
+def train_step(sd_model: SDModel, scheduler, latents, ref_latents, clip_image_embeddings, encoder_hidden_states, noise,
+               timesteps, optimizer: Optional[FlatAdamW] = None) -> torch.Tensor:
+    """One micro-batch of train.py:527-609 after the frozen VAE / CLIP encoders: add noise, predict, MSE against the noise,
+    backward, (optimizer step). Returns the detached loss."""
+    if optimizer is not None:
+        optimizer.zero_grad()
+    noisy = scheduler.add_noise(latents, noise, timesteps)                                                        # :545
+    pred = sd_model(encoder_hidden_states, noisy, ref_latents, clip_image_embeddings, timesteps)                  # :565-571
+    loss = ag.mse_loss(pred.float(), noise.float())                                                                # :577
+    loss.backward()                                                                                                # :603
+    if optimizer is not None:
+        optimizer.step()                                                                                           # :604
+    return loss.detach()

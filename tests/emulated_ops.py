@@ -231,10 +231,189 @@ def cfg_ddim_step(eps_cond, eps_uncond, guidance, latents, coef, step_ptr, *, ma
     return latents
 
 
+# ====================================================================================================== training step
+# Emulations of the backward / training kernels with EXPLICIT formulas (the ones the CUDA kernels implement), not torch
+# autograd: the CPU training tests then check both the autograd wiring and the backward algebra against the oracle's autograd.
+class AttnSaved:
+    def __init__(self, lse, o0, o1, lq_pad, out):
+        self.lse, self.o0, self.o1, self.lq_pad, self.out = lse, o0, o1, lq_pad, out
+
+
+def _heads(t, rows, heads, hd):
+    return t.float().reshape(rows, heads, hd).transpose(0, 1)  # [heads, rows, hd]
+
+
+def _stream_kv(s, b, C, heads, hd):
+    rows = slice(b * s.sample_rows, b * s.sample_rows + s.length)
+    return _heads(s.k[rows, :C], s.length, heads, hd), _heads(s.v[rows, :C], s.length, heads, hd)
+
+
+def attention_train(q, B, Lq, heads, head_dim, s0, s1=None, *, sm_scale=None):
+    C = heads * head_dim
+    scale = sm_scale if sm_scale is not None else head_dim ** -0.5
+    lq_pad = (Lq + 127) // 128 * 128
+    lse = torch.full((2, B, heads, lq_pad), float("inf"))
+    outs = [torch.zeros(B * Lq, C), torch.zeros(B * Lq, C)]
+    for b in range(B):
+        qh = _heads(q[b * Lq:(b + 1) * Lq, :C], Lq, heads, head_dim)
+        for si, s in enumerate((s0, s1)):
+            if s is None:
+                continue
+            assert not s.broadcast and s.n_query_samples >= B
+            k, v = _stream_kv(s, b, C, heads, head_dim)
+            sc = qh @ k.transpose(1, 2) * scale
+            lse[si, b, :, :Lq] = torch.logsumexp(sc, -1) / math.log(2.0)
+            o = torch.softmax(sc, -1) @ v
+            outs[si][b * Lq:(b + 1) * Lq] = o.transpose(0, 1).reshape(Lq, C)
+    out = s0.out_scale * outs[0] + (s1.out_scale * outs[1] if s1 is not None else 0)
+    two = s1 is not None
+    return out.to(BF), AttnSaved(lse, outs[0].to(BF) if two else None, outs[1].to(BF) if two else None, lq_pad, out.to(BF))
+
+
+def attention_bwd(q, d_out, B, Lq, heads, head_dim, s0, s1, saved, *, sm_scale=None, dq=None, dkv0=None, dkv1=None):
+    """P = exp2(S s log2e - lse2); dP = w dO V^T; D = w rowsum(dO o O_s); dS = P (dP - D); dQ += s dS K; dK = s dS^T Q; dV = w P^T dO
+    with P and dS rounded to bf16 before the second products, as in the kernels."""
+    C = heads * head_dim
+    scale = sm_scale if sm_scale is not None else head_dim ** -0.5
+    r = lambda t: t.to(BF).float()
+    for b in range(B):
+        rows = slice(b * Lq, (b + 1) * Lq)
+        qh = _heads(q[rows, :C], Lq, heads, head_dim)
+        doh = _heads(d_out[rows, :C], Lq, heads, head_dim)
+        dq_acc = torch.zeros(heads, Lq, head_dim)
+        for si, (s, pair) in enumerate(((s0, dkv0), (s1, dkv1))):
+            if s is None:
+                continue
+            w = s.out_scale
+            k, v = _stream_kv(s, b, C, heads, head_dim)
+            if s1 is not None:
+                os_ = (saved.o0 if si == 0 else saved.o1)[rows].float()
+                D = w * (doh * _heads(os_, Lq, heads, head_dim)).sum(-1, keepdim=True)
+            else:
+                D = (doh * _heads(saved.out[rows], Lq, heads, head_dim)).sum(-1, keepdim=True)
+            P = torch.exp2(qh @ k.transpose(1, 2) * scale * math.log2(math.e) - saved.lse[si, b, :, :Lq, None])
+            dS = r(P * (w * (doh @ v.transpose(1, 2)) - D))
+            dq_acc += dS @ k
+            if pair is not None:
+                krows = slice(b * s.sample_rows, b * s.sample_rows + s.length)
+                pair[0][krows, :C] = (scale * (dS.transpose(1, 2) @ qh)).transpose(0, 1).reshape(s.length, C).to(BF)
+                pair[1][krows, :C] = (w * (r(P).transpose(1, 2) @ doh)).transpose(0, 1).reshape(s.length, C).to(BF)
+        if dq is not None:
+            dq[rows, :C] = (scale * dq_acc).transpose(0, 1).reshape(Lq, C).to(BF)
+
+
+def transpose(x, pad_to=8):
+    rows, cols = x.shape
+    rp = (rows + pad_to - 1) // pad_to * pad_to
+    out = torch.zeros(cols, rp, dtype=BF)
+    out[:, :rows] = x.t()
+    return out
+
+
+def im2col3x3_t(x):
+    NB, H, W, C = x.shape
+    P = NB * H * W
+    cols = F.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1).view(NB, C, 9, H * W).permute(2, 1, 0, 3).reshape(9 * C, P)
+    out = torch.zeros((9 * C + 7) // 8 * 8, (P + 7) // 8 * 8, dtype=BF)
+    out[:9 * C, :P] = cols.to(BF)
+    return out
+
+
+def col2im3x3_s2(dcol, H, W):
+    NB, Ho, Wo, C9 = dcol.shape
+    C = C9 // 9
+    cols = dcol.float().view(NB, Ho * Wo, 9, C).permute(0, 3, 2, 1).reshape(NB, C * 9, Ho * Wo)  # channel-major for fold
+    return F.fold(cols, (H, W), 3, padding=1, stride=2).permute(0, 2, 3, 1).to(BF).contiguous()
+
+
+def downsum2x(dy):
+    NB, H2, W2, C = dy.shape
+    return dy.float().view(NB, H2 // 2, 2, W2 // 2, 2, C).sum((2, 4)).to(BF)
+
+
+def colsum(x, rows_per_group=None):
+    x2 = x.reshape(-1, x.shape[-1]).float()
+    rpg = x2.shape[0] if rows_per_group is None else rows_per_group
+    return x2.view(-1, rpg, x2.shape[1]).sum(1)
+
+
+def layernorm_bwd(x, dy, gamma, eps, need_affine):
+    xf, g = x.float(), dy.float() * (gamma.float() if gamma is not None else 1.0)
+    mean = xf.mean(-1, keepdim=True)
+    rstd = torch.rsqrt(xf.var(-1, unbiased=False, keepdim=True) + eps)
+    xh = (xf - mean) * rstd
+    dx = rstd * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+    C = x.shape[-1]
+    if not need_affine:
+        return dx.to(BF), None, None
+    return dx.to(BF), (dy.float() * xh).reshape(-1, C).sum(0), dy.float().reshape(-1, C).sum(0)
+
+
+def _dsilu(z):
+    s = torch.sigmoid(z)
+    return s * (1 + z * (1 - s))
+
+
+def groupnorm_bwd(x, dy, gamma, beta, groups, eps, silu, need_affine):
+    NB, C = x.shape[0], x.shape[-1]
+    xf = x.float().reshape(NB, -1, groups, C // groups)
+    mean = xf.mean((1, 3), keepdim=True)
+    rstd = torch.rsqrt(xf.var((1, 3), unbiased=False, keepdim=True) + eps)
+    xh = ((xf - mean) * rstd).reshape(NB, -1, C)
+    dz = dy.float().reshape(NB, -1, C)
+    if silu:
+        dz = dz * _dsilu(xh * gamma.float() + beta.float())
+    g = (dz * gamma.float()).reshape(NB, -1, groups, C // groups)
+    xg = xh.reshape(NB, -1, groups, C // groups)
+    dx = rstd * (g - g.mean((1, 3), keepdim=True) - xg * (g * xg).mean((1, 3), keepdim=True))
+    dx = dx.reshape(x.shape).to(BF)
+    if not need_affine:
+        return dx, None, None
+    return dx, (dz * xh).sum((0, 1)), dz.sum((0, 1))
+
+
+def _dgelu(x):
+    return 0.5 * (1 + torch.erf(x / math.sqrt(2.0))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
+
+
+def act(x, mode, dy=None):
+    xf = x.float()
+    if dy is None:
+        return _act(xf, mode).to(BF)
+    return (dy.float() * (_dsilu(xf) if mode == ACT_SILU else _dgelu(xf))).to(BF)
+
+
+def geglu(h, dout=None):
+    v, g = h.float().chunk(2, -1)
+    if dout is None:
+        return (v * F.gelu(g)).to(BF)
+    d = dout.float()
+    return torch.cat([d * F.gelu(g), d * v * _dgelu(g)], -1).to(BF)
+
+
+def mse_loss_grad(pred, target, grad_scale=1.0):
+    d = pred - target
+    return (d * d).mean().reshape(1), grad_scale * 2.0 * d / d.numel()
+
+
+def adamw_step(master, param, grad, m, v, *, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    g = grad.float() * grad_scale
+    m.mul_(beta1).add_(g, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    master.mul_(1 - lr * weight_decay)
+    master.addcdiv_(m / (1 - beta1 ** step), (v / (1 - beta2 ** step)).sqrt() + eps, value=-lr)
+    param.copy_(master.to(BF))
+
+
+TRAIN_OPS = ("attention_train", "attention_bwd", "transpose", "im2col3x3_t", "col2im3x3_s2", "downsum2x", "colsum",
+             "layernorm_bwd", "groupnorm_bwd", "act", "geglu", "mse_loss_grad", "adamw_step")
+
+
 def install(monkeypatch):
     from imagdressing_b200 import ops
 
     for name in ("gemm", "conv3x3", "conv3x3_direct", "groupnorm", "layernorm", "kv_stream", "attention", "concat_add",
                  "upsample2x", "im2col3x3_s2", "nchw_f32_to_nhwc_bf16", "timestep_embedding", "linear_small_m",
-                 "cfg_ddim_step", "gemm_tile_count_n", "upconv3x3", "softmax_rows", "embed_tokens", "patchify", "broadcast_row"):
+                 "cfg_ddim_step", "gemm_tile_count_n", "upconv3x3", "softmax_rows", "embed_tokens", "patchify", "broadcast_row",
+                 *TRAIN_OPS):
         monkeypatch.setattr(ops, name, globals()[name])

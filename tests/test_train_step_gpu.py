@@ -1,0 +1,146 @@
+"""GPU parity of the whole training step (BASELINE.json configs[4]) on the kernels: full-width SD1.5 denoising
+UNet (frozen, RefS / C processors) + garment UNet (trainable, cache processors) + Resampler (depth 4, 12 x 64 heads,
+16 queries on 257 x 1280 CLIP tokens), SDModel.forward -> MSE -> backward, against the fp32 oracle
+(oracle/train_step.py, restating /root/reference/train.py:255-281,338-379,573-605) with identical synthetic weights.
+
+Compared: the loss; which parameters receive gradients; the gradients of the adapter modules (to_k_ref / to_v_ref), the
+Resampler and the garment UNet. Tolerance is calibrated as everywhere else in this suite: the same oracle run in torch bf16
+autocast-free bf16 (weights and activations bf16, torch's own bf16 kernels) gives the drift of a bf16 training step; the
+kernels' aggregate gradient error must stay within 2x of it (floor 3e-2), and is printed next to it."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def rel(a, b):
+    return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))
+
+
+def build(dev):
+    from adapter.resampler import Resampler
+    from imagdressing_b200 import modeling, train
+    from oracle import processors as op
+    from oracle import train_step as ts
+    from oracle import unet as ou
+
+    rs_kw = dict(dim=768, depth=4, dim_head=64, heads=12, num_queries=16, embedding_dim=1280, output_dim=768, ff_mult=4)
+    with modeling.skip_default_init():
+        o_unet, o_ref = ou.UNet2DConditionModel(), ou.UNet2DConditionModel()
+        p_unet, p_ref = modeling.UNet2DConditionModel(), modeling.UNet2DConditionModel()
+    o_proj, p_proj = op.Resampler(**rs_kw), Resampler(**rs_kw)
+    ou.init_synthetic_(o_unet, 0)
+    ou.init_synthetic_(o_ref, 1)
+    ou.init_synthetic_(o_proj, 2)
+    for m in (o_unet, o_ref, o_proj):  # bf16-representable weights: both sides start from identical values
+        with torch.no_grad():
+            for p in m.parameters():
+                p.copy_(p.to(BF).float())
+    p_unet.load_state_dict(o_unet.state_dict())
+    p_ref.load_state_dict(o_ref.state_dict())
+    p_proj.load_state_dict(o_proj.state_dict())
+    for m in (o_unet, o_ref, o_proj):
+        m.to(dev)
+    for m in (p_unet, p_ref, p_proj):
+        m.to(device=dev, dtype=BF)
+    o_ad = ts.install_training_processors(o_unet, o_ref).to(dev)
+    p_ad = train.install_training_processors(p_unet, p_ref).to(device=dev, dtype=BF)
+    ts.set_trainable(o_unet, o_ref, o_proj, o_ad)
+    train.set_trainable(p_unet, p_ref, p_proj, p_ad)
+    return (o_unet, o_ref, o_proj, o_ad), (p_unet, p_ref, p_proj, p_ad)
+
+
+def batch(dev, B, h, w):
+    g = torch.Generator().manual_seed(7)
+    r = lambda *s: torch.randn(*s, generator=g).to(BF).float().to(dev)
+    return dict(latents=r(B, 4, h, w), ref_latents=r(B, 4, h, w) * 0.9, clip_image_embeddings=r(B, 257, 1280),
+                encoder_hidden_states=r(B, 77, 768), noise=r(B, 4, h, w), timesteps=torch.tensor([981, 40, 500, 7][:B], device=dev))
+
+
+def grads(ref, proj, ad):
+    out = {}
+    for pre, m in (("ref.", ref), ("proj.", proj), ("ad.", ad)):
+        for n, p in m.named_parameters():
+            out[pre + n] = None if p.grad is None else p.grad.detach().float().clone()
+    return out
+
+
+def aggregate(ga, gb, prefix):
+    num = den = 0.0
+    for n, g in gb.items():
+        if not n.startswith(prefix) or g is None or float(g.norm()) == 0.0:
+            continue
+        assert ga[n] is not None, n
+        num += float((ga[n] - g).norm()) ** 2
+        den += float(g.norm()) ** 2
+    return (num / max(den, 1e-30)) ** 0.5
+
+
+@pytest.mark.parametrize("B,h,w", [(2, 16, 16), (2, 40, 32)])  # 128 x 128 px (ragged tiles everywhere) and 320 x 256 px
+def test_training_step_gradients_match_oracle(cuda_device, B, h, w):
+    from imagdressing_b200 import _lib, train
+    from imagdressing_b200.scheduler import DDIMScheduler
+    from oracle import train_step as ts
+    from oracle.ddim import DDIMOracle
+
+    dev = cuda_device
+    (o_unet, o_ref, o_proj, o_ad), (p_unet, p_ref, p_proj, p_ad) = build(dev)
+    b = batch(dev, B, h, w)
+
+    loss_o = ts.train_step(o_unet, o_ref, o_proj, DDIMOracle(), **b)
+    g_o = grads(o_ref, o_proj, o_ad)
+
+    sd = train.SDModel(p_unet, p_ref, p_proj, p_ad)
+    sched = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False)
+    before = _lib.launch_count
+    loss_p = train.train_step(sd, sched, **b)
+    torch.cuda.synchronize()
+    launched = _lib.launch_count - before
+    g_p = grads(p_ref, p_proj, p_ad)
+    assert launched > 3000, launched
+    for n, p in p_unet.named_parameters():
+        assert (p.grad is not None) == ("processor" in n), n  # the denoising UNet itself is frozen (train.py:374)
+
+    # calibration: the oracle's own step in torch bf16
+    for m in (o_unet, o_ref, o_proj, o_ad):
+        m.zero_grad(set_to_none=True)
+        m.to(BF)
+    bb = {k: (v.to(BF) if v.is_floating_point() else v) for k, v in b.items()}
+    loss_b = ts.train_step(o_unet, o_ref, o_proj, DDIMOracle(), **bb)
+    g_b = grads(o_ref, o_proj, o_ad)
+
+    print(f"\n[{B}x{h}x{w}] loss: oracle fp32 {float(loss_o):.5f} | kernels {float(loss_p):.5f} | torch-bf16 {float(loss_b):.5f}; "
+          f"{launched} kernel launches in the step")
+    assert abs(float(loss_p) - float(loss_o)) < 2e-2 * float(loss_o)
+    for prefix, name in (("ad.", "adapter to_k_ref/to_v_ref"), ("proj.", "Resampler"), ("ref.", "garment UNet")):
+        ek, eb = aggregate(g_p, g_o, prefix), aggregate(g_b, g_o, prefix)
+        print(f"  grad rel-L2 vs fp32 oracle, {name}: kernels {ek:.4f} | torch-bf16 {eb:.4f}")
+        assert ek < max(2 * eb, 3e-2) and ek < 0.1, (name, ek, eb)
+    # same set of parameters with (non-zero) gradients
+    for n, g in g_o.items():
+        has_o = g is not None and float(g.norm()) > 0
+        has_p = g_p[n] is not None and float(g_p[n].norm()) > 0
+        assert has_o == has_p, n
+
+
+def test_optimizer_step_changes_only_trainable_parameters(cuda_device):
+    """train_step with FlatAdamW: the trainable parameters (now views of one flat bf16 buffer) move, the frozen UNet does not,
+    and a second step with the same batch lowers the loss."""
+    from imagdressing_b200 import train
+    from imagdressing_b200.scheduler import DDIMScheduler
+
+    dev = cuda_device
+    _, (p_unet, p_ref, p_proj, p_ad) = build(dev)
+    b = batch(dev, 2, 16, 16)
+    sd = train.SDModel(p_unet, p_ref, p_proj, p_ad)
+    params = train.set_trainable(p_unet, p_ref, p_proj, p_ad)
+    opt = train.FlatAdamW(params, lr=1e-4, weight_decay=1e-2)
+    frozen_before = p_unet.conv_in.weight.detach().clone()
+    w_before = p_ref.conv_in.weight.detach().clone()
+    sched = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False)
+    losses = [float(train.train_step(sd, sched, **b, optimizer=opt)) for _ in range(3)]
+    print("losses over 3 AdamW steps on one batch:", losses)
+    assert torch.equal(p_unet.conv_in.weight, frozen_before)
+    assert not torch.equal(p_ref.conv_in.weight, w_before)
+    assert losses[2] < losses[0]
