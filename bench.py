@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the batch-8/16/32 and configs[2]/[3] sub-records")
     # non-default workloads (BASELINE.json configs[2] / configs[3]); the driver's contract run never passes these
-    ap.add_argument("--workload", default="base", choices=["base", "ipa_controlnet", "inpaint"],
+    ap.add_argument("--workload", default="base", choices=["base", "ipa_controlnet", "inpaint", "train"],
                     help="base = configs[1] (the metric); ipa_controlnet = configs[2]; inpaint = configs[3]")
     ap.add_argument("--height", type=int, default=512)
     ap.add_argument("--width", type=int, default=512)
@@ -201,6 +201,98 @@ def run_pipe(pipe, x, workload="base"):
                     face_tokens=x["face"], face_null_tokens=x["face_null"], **kw).images
     return pipe(control_image=x["pose"], strength=1.0, controlnet_conditioning_scale=1.0, image_latents=x["image_latents"],
                 mask_latents=x["mask"], **kw).images
+
+
+# ------------------------------------------------------------------------------------------------ training step (configs[4])
+TRAIN_TFLOP_PER_SAMPLE_640x512 = 5.7  # 2 x 1.265 (frozen hybrid UNet fwd + dgrad) + 3 x 1.042 (garment UNet)
+
+
+def build_train(dev):
+    """SDModel of reference train.py:244-281 on the product modules: frozen denoising UNet with RefS / C processors, trainable
+    garment UNet (cache processors), Resampler and adapter modules; FlatAdamW over the trainable set (train.py:368-398)."""
+    from adapter.resampler import Resampler
+    from imagdressing_b200 import modeling, train
+
+    pipe = build_product(dev, "base")
+    unet, ref = pipe.unet, pipe.reference_unet
+    proj = Resampler(dim=768, depth=4, dim_head=64, heads=12, num_queries=16, embedding_dim=1280, output_dim=768, ff_mult=4)
+    proj = proj.to(dev, torch.bfloat16)
+    modeling.init_synthetic_fast_(proj, 3)
+    adapters = torch.nn.ModuleList(unet.attn_processors.values())
+    params = train.set_trainable(unet, ref, proj, adapters)
+    sd = train.SDModel(unet, ref, proj, adapters)
+    opt = train.FlatAdamW(params, lr=1e-5, weight_decay=1e-2)
+    return sd, opt, pipe.scheduler
+
+
+def synth_train_batch(B, dev, rank, pinned, lh, lw):
+    g = torch.Generator().manual_seed(4242 + 1000 * rank)
+    t = dict(latents=torch.randn(B, 4, lh, lw, generator=g) * 0.18215 * 5, ref_latents=torch.randn(B, 4, lh, lw, generator=g) * 0.18215 * 5,
+             clip_image_embeddings=torch.randn(B, 257, 1280, generator=g), encoder_hidden_states=torch.randn(B, 77, 768, generator=g),
+             noise=torch.randn(B, 4, lh, lw, generator=g), timesteps=torch.randint(0, 1000, (B,), generator=g))
+    if pinned:
+        return {k: v.pin_memory() for k, v in t.items()}
+    return {k: v.to(dev) for k, v in t.items()}
+
+
+def train_record(a, dev, rank, local, world, B, h, w, steps, warm):
+    """Training micro-step measured like the sampling workloads: forward + backward of SDModel on the kernels, bucketed NCCL
+    gradient all-reduce overlapped with the backward, AdamW; device events, barrier + synchronize, max over ranks."""
+    import torch.distributed as dist
+
+    from imagdressing_b200 import _lib, train
+
+    sd, opt, sched = build_train(dev)
+    lh, lw = h // 8, w // 8
+    xd = synth_train_batch(B, dev, rank, False, lh, lw)
+    xh = synth_train_batch(B, dev, rank, True, lh, lw)
+
+    def step(x):
+        return train.train_step(sd, sched, optimizer=opt, **x)
+
+    def step_e2e():
+        x = {k: v.to(dev, non_blocking=True) for k, v in xh.items()}
+        return float(step(x).cpu())
+
+    def timed(fn, K):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    losses = [float(step(xd)) for _ in range(max(warm, 1))]
+    c = ClockSampler(local)
+    if rank == 0:
+        c.start()
+    l0 = _lib.launch_count
+    ms = timed(lambda: step(xd), steps)
+    launches = _lib.launch_count - l0
+    ck = c.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, steps)
+    _, tf_burst, tf_sus, _ = peaks()
+    sps = world * B * steps / (ms * 1e-3)
+    rec = {"workload": "train", "micro_batch_per_gpu": B, "global_batch": world * B, "height": h, "width": w,
+           "samples_per_s": round(sps, 4), "ms_per_step": round(ms / steps, 2), "steps": steps, "warmup": max(warm, 1),
+           "e2e_samples_per_s": round(world * B * steps / (ms_e2e * 1e-3), 4),
+           "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in xh.values()), "d2h_bytes_per_step": 4,
+           "gpu_launches_per_step": launches // steps, "loss_first_steps": [round(v, 5) for v in losses], "clocks": ck,
+           "what": "SDModel.forward (Resampler -> garment UNet taps -> hybrid denoising UNet) + MSE + backward + bucketed "
+                   "gradient all-reduce + AdamW, bf16, random-init SD1.5 weights (reference train.py:517-609)"}
+    if (h, w) == (640, 512):
+        rec["model_tflops"] = round(sps / world * TRAIN_TFLOP_PER_SAMPLE_640x512, 1)
+        rec["model_frac_of_sustained_bf16"] = round(sps / world * TRAIN_TFLOP_PER_SAMPLE_640x512 / tf_sus, 4)
+    del sd, opt
+    torch.cuda.empty_cache()
+    return rec
 
 
 # ------------------------------------------------------------------------------------------------ roofline legs
@@ -441,6 +533,24 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B = a.batch
     lh, lw = a.height // 8, a.width // 8
+    if a.workload == "train":  # BASELINE.json configs[4]: micro-batch 4 per GPU at 640 x 512 unless overridden
+        Bt = a.batch if a.batch != 1 else 4
+        h, w = (640, 512) if (a.height, a.width) == (512, 512) else (a.height, a.width)
+        rec = train_record(a, dev, rank, local, world, Bt, h, w, a.steps, max(a.warmup, 3))
+        if rank == 0:
+            print(json.dumps({
+                "metric": f"training samples/sec, {h}x{w} bf16 forward+backward+AdamW, micro-batch {Bt}/GPU", "value": rec["samples_per_s"],
+                "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": rec["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"train.py step (BASELINE.json configs[4]): garment UNet + Resampler + adapters trainable, "
+                                       f"denoising UNet frozen, micro-batch {Bt}/GPU, {h}x{w}", "global_batch": world * Bt,
+                           "parallelism": f"dp{world}"},
+                "e2e": {"value": rec["e2e_samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": rec["h2d_bytes_per_step"],
+                        "d2h_bytes_per_step": 4},
+                "gpu_launches": rec["gpu_launches_per_step"] * a.steps, "clocks": rec["clocks"], "train": rec}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     pipe = build_product(dev, a.workload)
     x_dev = synth_inputs(B, dev, rank, False, a.workload, lh, lw)
     x_host = synth_inputs(B, dev, rank, True, a.workload, lh, lw)
@@ -518,6 +628,10 @@ def main():
             other_configs.append(extra(workload, Bx, h, w, p2))
             del p2
             torch.cuda.empty_cache()
+
+    if standard_run(a) and not a.no_extras:
+        # BASELINE.json configs[4]: the training step (micro-batch 4 per GPU, 640 x 512), data-parallel over the ranks
+        other_configs.append(train_record(a, dev, rank, local, world, 4, 640, 512, 2, 1))
 
     edges = None
     if rank == 0 and standard_run(a) and not a.no_extras:

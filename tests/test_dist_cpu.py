@@ -62,3 +62,65 @@ def test_shard_range_covers_everything():
                 lo, hi = shard_range(B, r, W)
                 got += list(range(lo, hi))
             assert got == list(range(B))
+
+
+# ------------------------------------------------------------------------------------------------ training: gradient all-reduce
+def _train_worker(rank, world, port, out_q):
+    """Data-parallel step of FlatAdamW (imagdressing_b200/train.py; reference train.py:601-609 DeepSpeed gradient reduction):
+    each rank back-propagates its own shard, the per-bucket hooks all-reduce the flat gradient buffer, the update uses the
+    mean gradient — both ranks must end with the parameters of a single-process step on the whole batch."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import emulated_ops
+    from imagdressing_b200 import train
+
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 4), torch.nn.Linear(4, 3)).to(torch.bfloat16)
+    net[3].requires_grad_(False)  # a frozen tail layer: no hook fires for it, nothing is reduced for it
+    opt = train.FlatAdamW(net.parameters(), lr=1e-2, weight_decay=0.0, bucket_bytes=32, step_fn=emulated_ops.adamw_step)
+    assert opt._dist and len(opt._buckets) >= 2
+    x = torch.randn(8, 6, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16)
+    lo, hi = shard_range(8, rank, world)
+    for _ in range(2):
+        opt.zero_grad()
+        net(x[lo:hi]).float().square().mean().backward()
+        opt.step()
+    out_q.put((rank, opt.param.float().numpy().copy(), opt.grad.float().numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_adamw_gradient_allreduce_world2():
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import emulated_ops
+    from imagdressing_b200 import train
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process reference: the mean loss over the whole batch has the mean of the shard gradients
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 4), torch.nn.Linear(4, 3)).to(torch.bfloat16)
+    net[3].requires_grad_(False)
+    opt = train.FlatAdamW(net.parameters(), lr=1e-2, weight_decay=0.0, bucket_bytes=32, step_fn=emulated_ops.adamw_step)
+    x = torch.randn(8, 6, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16)
+    for _ in range(2):
+        opt.zero_grad()
+        net(x).float().square().mean().backward()
+        opt.step()
+    p0, p1 = torch.from_numpy(res[0][1]), torch.from_numpy(res[1][1])
+    assert torch.equal(p0, p1)  # ranks agree bit for bit
+    assert float((p0 - opt.param.float()).abs().max()) < 2e-2  # and match the whole-batch step to bf16 gradient rounding
+    assert torch.equal(torch.from_numpy(res[0][2]), torch.from_numpy(res[1][2]))  # reduced gradient buffers identical
