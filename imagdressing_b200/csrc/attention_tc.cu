@@ -548,10 +548,22 @@ static int launch_attn_pp(const CUtensorMap* tms, AttnParams p, cudaStream_t str
     dim3 grid((p.Lq + 255) / 256, p.heads, p.B);
     if (variant == 1) {
         using C = AttnPP1Cfg<kStages>;
-        IMAGD_SET_MAX_SMEM((attention_pp1_kernel<HD_MMA, kStages>), C::kTotal);
-        IMAGD_CUDA(launch_pdl(attention_pp1_kernel<HD_MMA, kStages>, grid, dim3(576), C::kTotal, stream, tms[0], tms[1],
-                              tms[2], tms[3], tms[4], p));
-        return IMAGD_OK;
+        static const int poly = env_int("IMAGD_ATTN_POLY", IMAGD_ATTN_POLY);  // exponentials per 8 on the FMA pipe
+#define IMAGD_PP1_LAUNCH(P)                                                                                              \
+    do {                                                                                                                 \
+        IMAGD_SET_MAX_SMEM((attention_pp1_kernel<HD_MMA, kStages, P>), C::kTotal);                                       \
+        IMAGD_CUDA(launch_pdl(attention_pp1_kernel<HD_MMA, kStages, P>, grid, dim3(576), C::kTotal, stream, tms[0],      \
+                              tms[1], tms[2], tms[3], tms[4], p));                                                       \
+        return IMAGD_OK;                                                                                                 \
+    } while (0)
+        switch (poly) {
+            case 1: IMAGD_PP1_LAUNCH(1);
+            case 2: IMAGD_PP1_LAUNCH(2);
+            case 3: IMAGD_PP1_LAUNCH(3);
+            case 4: IMAGD_PP1_LAUNCH(4);
+            default: IMAGD_PP1_LAUNCH(0);
+        }
+#undef IMAGD_PP1_LAUNCH
     }
     using C = AttnPPCfg<kStages>;
     IMAGD_SET_MAX_SMEM((attention_pp_kernel<HD_MMA, kStages>), C::kTotal);
