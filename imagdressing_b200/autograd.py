@@ -192,17 +192,18 @@ class GroupNorm(Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, groups, eps, silu):
         g32, b32 = _f32c(gamma), _f32c(beta)
-        y = ops.groupnorm(x, g32, b32, groups, eps, silu=bool(silu))
-        ctx.save_for_backward(x, g32, b32)
-        ctx.cfg = (int(groups), float(eps), bool(silu), gamma, beta)
+        stats = torch.empty(x.shape[0], int(groups), 2, device=x.device, dtype=torch.float32)
+        y = ops.groupnorm(x, g32, b32, groups, eps, silu=bool(silu), stats_out=stats)
+        ctx.save_for_backward(x, g32, b32, stats)
+        ctx.cfg = (int(groups), bool(silu), gamma, beta)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, g32, b32 = ctx.saved_tensors
-        groups, eps, silu, gamma, beta = ctx.cfg
+        x, g32, b32, stats = ctx.saved_tensors
+        groups, silu, gamma, beta = ctx.cfg
         need_aff = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        dx, dg, db = ops.groupnorm_bwd(x, _bf(dy).contiguous(), g32, b32, groups, eps, silu, need_aff)
+        dx, dg, db = ops.groupnorm_bwd(x, _bf(dy).contiguous(), g32, b32, groups, stats, silu, need_aff)
         return (dx if ctx.needs_input_grad[0] else None, _as(dg, gamma) if ctx.needs_input_grad[1] else None,
                 _as(db, beta) if ctx.needs_input_grad[2] else None, None, None, None)
 

@@ -54,7 +54,7 @@ inline int gn_chunks(int HW, int NB) {
 __global__ void __launch_bounds__(kGnThreads, 2) groupnorm_fused_kernel(
     const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y, int64_t ldy, int HW, int C,
     int groups, int chunks, float* __restrict__ ws, const float* __restrict__ gamma, const float* __restrict__ beta,
-    float eps, int fuse_silu) {
+    float eps, int fuse_silu, float* __restrict__ stats_out) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float s_a[kGnThreads * 8];  // phase 1: per (row slot, channel) sums      | phase 2: per-channel scale
@@ -212,6 +212,10 @@ __global__ void __launch_bounds__(kGnThreads, 2) groupnorm_fused_kernel(
             const float var = fmaxf((tb - ta * dm) / cnt, 0.f);
             s_mean[threadIdx.x] = pivot + dm;
             s_rstd[threadIdx.x] = rsqrtf(var + eps);
+            if (stats_out != nullptr && chunk == 0) {  // training: {mean, rstd} per (sample, group) for the backward
+                stats_out[(static_cast<int64_t>(n) * groups + threadIdx.x) * 2] = pivot + dm;
+                stats_out[(static_cast<int64_t>(n) * groups + threadIdx.x) * 2 + 1] = s_rstd[threadIdx.x];
+            }
         }
         __syncthreads();
     }
@@ -377,6 +381,12 @@ int64_t imagd_groupnorm_ws_bytes(int NB, int HW, int C, int groups) {
 
 int imagd_groupnorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int NB, int HW, int C, int groups,
                          const float* gamma, const float* beta, float eps, int fuse_silu, void* ws, imagd_stream stream) {
+    return imagd_groupnorm_stats_bf16(x, ldx, y, ldy, NB, HW, C, groups, gamma, beta, eps, fuse_silu, ws, nullptr, stream);
+}
+
+int imagd_groupnorm_stats_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int NB, int HW, int C, int groups,
+                               const float* gamma, const float* beta, float eps, int fuse_silu, void* ws, float* stats_out,
+                               imagd_stream stream) {
     using namespace imagd;
     IMAGD_CHECK_ARG(x && y && ws, "groupnorm: null pointer");
     IMAGD_CHECK_ARG(NB > 0 && 2 * NB <= kGnCounters && NB <= 148 * 2 && HW > 0 && C > 0 && C % 8 == 0 && C <= kGnMaxC,
@@ -389,7 +399,7 @@ int imagd_groupnorm_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int N
     IMAGD_SET_MAX_SMEM(groupnorm_fused_kernel, 64 * 1024);
     IMAGD_CUDA(launch_pdl(groupnorm_fused_kernel, dim3(chunks, NB), dim3(kGnThreads), 3 * C * sizeof(float), st,
                           reinterpret_cast<const __nv_bfloat16*>(x), ldx, reinterpret_cast<__nv_bfloat16*>(y), ldy, HW, C,
-                          groups, chunks, reinterpret_cast<float*>(ws) + kGnCounters, gamma, beta, eps, fuse_silu));
+                          groups, chunks, reinterpret_cast<float*>(ws) + kGnCounters, gamma, beta, eps, fuse_silu, stats_out));
     return IMAGD_OK;
 }
 

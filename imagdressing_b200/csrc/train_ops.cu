@@ -228,8 +228,10 @@ __global__ void colreduce_fold_kernel(const float* __restrict__ part, float* __r
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm backward
-// One warp per row (C <= 2048): recompute mean / rstd (two-pass on the registers), dx = rstd * (g - mean(g) - xhat * mean(g xhat))
-// with g = dy * gamma; writes {mean, rstd} per row for the column reduction that produces dgamma / dbeta.
+// One warp per row, VPL 128-bit vectors per lane (C <= VPL * 256): recompute mean / rstd (two-pass on the registers),
+// dx = rstd * (g - mean(g) - xhat * mean(g xhat)) with g = dy * gamma; writes {mean, rstd} per row for the column reduction that
+// produces dgamma / dbeta.
+template <int VPL>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
                                                             const __nv_bfloat16* __restrict__ dy, int64_t lddy,
                                                             __nv_bfloat16* __restrict__ dx, int64_t lddx,
@@ -238,22 +240,27 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    constexpr int kMax = 2048 / 64;  // bf16 pairs per lane; fixed-trip loops keep xv / dv in registers
-    float xv[2 * kMax], dv[2 * kMax];
-    const int pairs = C / 2;
+    const int CV = C / 8;
+    float xv[VPL][8], gv[VPL][8];
     float sum = 0.f;
 #pragma unroll
-    for (int n = 0; n < kMax; ++n) {
-        const int i = lane + 32 * n;
-        xv[2 * n] = xv[2 * n + 1] = dv[2 * n] = dv[2 * n + 1] = 0.f;
-        if (i < pairs) {
-            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + static_cast<int64_t>(row) * ldx + 2 * i);
-            const __nv_bfloat162 d = *reinterpret_cast<const __nv_bfloat162*>(dy + static_cast<int64_t>(row) * lddy + 2 * i);
-            xv[2 * n] = __bfloat162float(v.x);
-            xv[2 * n + 1] = __bfloat162float(v.y);
-            dv[2 * n] = __bfloat162float(d.x) * (gamma ? gamma[2 * i] : 1.f);
-            dv[2 * n + 1] = __bfloat162float(d.y) * (gamma ? gamma[2 * i + 1] : 1.f);
-            sum += xv[2 * n] + xv[2 * n + 1];
+    for (int i = 0; i < VPL; ++i) {
+        const int cv = lane + 32 * i;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xv[i][k] = gv[i][k] = 0.f;
+        if (cv < CV) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx + cv * 8));
+            const uint4 d = __ldg(reinterpret_cast<const uint4*>(dy + static_cast<int64_t>(row) * lddy + cv * 8));
+            const uint32_t au[4] = {a.x, a.y, a.z, a.w}, du[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                xv[i][2 * k] = bf16lo(au[k]);
+                xv[i][2 * k + 1] = bf16hi(au[k]);
+                gv[i][2 * k] = bf16lo(du[k]) * (gamma ? __ldg(gamma + cv * 8 + 2 * k) : 1.f);
+                gv[i][2 * k + 1] = bf16hi(du[k]) * (gamma ? __ldg(gamma + cv * 8 + 2 * k + 1) : 1.f);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sum += xv[i][k];
         }
     }
 #pragma unroll
@@ -261,22 +268,25 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     const float mean = sum / C;
     float var = 0.f;
 #pragma unroll
-    for (int n = 0; n < kMax; ++n) {
-        if (lane + 32 * n < pairs) var += (xv[2 * n] - mean) * (xv[2 * n] - mean) + (xv[2 * n + 1] - mean) * (xv[2 * n + 1] - mean);
-    }
+    for (int i = 0; i < VPL; ++i)
+        if (lane + 32 * i < CV) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) var += (xv[i][k] - mean) * (xv[i][k] - mean);
+        }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
     const float rstd = rsqrtf(var / C + eps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int n = 0; n < kMax; ++n) {
-        if (lane + 32 * n < pairs) {
-            xv[2 * n] = (xv[2 * n] - mean) * rstd;  // xhat from here on
-            xv[2 * n + 1] = (xv[2 * n + 1] - mean) * rstd;
-            s1 += dv[2 * n] + dv[2 * n + 1];
-            s2 += dv[2 * n] * xv[2 * n] + dv[2 * n + 1] * xv[2 * n + 1];
+    for (int i = 0; i < VPL; ++i)
+        if (lane + 32 * i < CV) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                xv[i][k] = (xv[i][k] - mean) * rstd;  // xhat from here on
+                s1 += gv[i][k];
+                s2 += gv[i][k] * xv[i][k];
+            }
         }
-    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
@@ -285,13 +295,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     s1 /= C;
     s2 /= C;
 #pragma unroll
-    for (int n = 0; n < kMax; ++n) {
-        const int i = lane + 32 * n;
-        if (i < pairs) {
-            __nv_bfloat162 o;
-            o.x = __float2bfloat16(rstd * (dv[2 * n] - s1 - xv[2 * n] * s2));
-            o.y = __float2bfloat16(rstd * (dv[2 * n + 1] - s1 - xv[2 * n + 1] * s2));
-            *reinterpret_cast<__nv_bfloat162*>(dx + static_cast<int64_t>(row) * lddx + 2 * i) = o;
+    for (int i = 0; i < VPL; ++i) {
+        const int cv = lane + 32 * i;
+        if (cv < CV) {
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = rstd * (gv[i][k] - s1 - xv[i][k] * s2);
+            *reinterpret_cast<uint4*>(dx + static_cast<int64_t>(row) * lddx + cv * 8) =
+                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
         }
     }
     if (lane == 0) {
@@ -306,81 +317,108 @@ __device__ __forceinline__ float silu_grad(float z) {
     return s * (1.f + z * (1.f - s));
 }
 
-// One CTA per (group, sample): thread = (pixel lane, channel of the group). Pass A mean, pass B variance (two-pass: no
-// cancellation), pass C the four sums of the backward formula. Writes stat[n][g] = {mean, rstd, S1/m, S2/m} with
-// S1 = sum dz gamma, S2 = sum dz gamma xhat (dz = dy * act'(z), z = xhat gamma + beta), and the per-(sample, channel) partials
-// pc[0][n][c] = sum_p dz xhat, pc[1][n][c] = sum_p dz that fold into dgamma / dbeta.
-__global__ void __launch_bounds__(256) groupnorm_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ x,
-                                                                   const __nv_bfloat16* __restrict__ dy, int HW, int C,
-                                                                   int groups, const float* __restrict__ gamma,
-                                                                   const float* __restrict__ beta, float eps, int fuse_silu,
-                                                                   float* __restrict__ stat, float* __restrict__ pc, int NB) {
-    __shared__ float red[4][256];
-    __shared__ float bc[4];
-    const int g = blockIdx.x, n = blockIdx.y;
+// Forward-pass statistics (mean, rstd per sample and group; imagd_groupnorm_stats_bf16) come in as `fstat`. Two steps, both
+// with the forward kernel's coalesced layout (thread = (pixel row slot, 8-channel vector), 128-bit loads):
+//   groupnorm_bwd_partial_kernel  grid (chunks, NB): per channel of its pixel chunk  a = sum dz xhat,  b = sum dz
+//                                 (dz = dy * act'(z), z = xhat gamma + beta) -> part[n][chunk][{a, b}][C]
+//   groupnorm_bwd_fold_kernel     grid (NB): chunks -> sample in a fixed order -> pc[{a, b}][n][c] (these fold over n into
+//                                 dgamma / dbeta) and per group S1 = sum_c gamma_c b_c, S2 = sum_c gamma_c a_c ->
+//                                 stat[n][g] = {mean, rstd, S1 / m, S2 / m}
+constexpr int kGbThreads = 512;
+__global__ void __launch_bounds__(kGbThreads) groupnorm_bwd_partial_kernel(
+    const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int HW, int C, int groups, int chunks,
+    const float* __restrict__ gamma, const float* __restrict__ beta, int fuse_silu, const float* __restrict__ fstat,
+    float* __restrict__ part) {
+    extern __shared__ float sm[];  // [rows][C] a | [rows][C] b  (rows = kGbThreads / CV row slots)
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int CV = C / 8;
+    const int rows = kGbThreads / CV;
     const int cpg = C / groups;
-    const int lanes = 256 / cpg;  // pixel lanes (cpg <= 256)
-    const int ch = threadIdx.x % cpg, pl = threadIdx.x / cpg;
-    const bool active = pl < lanes;
-    const int c = g * cpg + ch;
-    const __nv_bfloat16* xb = x + static_cast<int64_t>(n) * HW * C + c;
-    const __nv_bfloat16* db = dy + static_cast<int64_t>(n) * HW * C + c;
-    const float m = static_cast<float>(HW) * cpg;
-
-    auto block_sum = [&](float v, int slot) {  // fixed-order tree over the 256 threads
-        red[slot][threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 128; o > 0; o >>= 1) {
-            if (threadIdx.x < o) red[slot][threadIdx.x] += red[slot][threadIdx.x + o];
-            __syncthreads();
+    const int ppc = (HW + chunks - 1) / chunks;
+    const int p_begin = chunk * ppc, p_end = min(HW, p_begin + ppc);
+    const int cv = threadIdx.x % CV, prow = threadIdx.x / CV;
+    float* sa = sm;
+    float* sb = sm + rows * C;
+    if (prow < rows) {
+        float a[8], b[8], sc[8], sh[8], ga[8], be[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = cv * 8 + k;
+            const float* st = fstat + (static_cast<int64_t>(n) * groups + c / cpg) * 2;
+            sc[k] = st[1];
+            sh[k] = -st[0] * st[1];
+            ga[k] = gamma ? gamma[c] : 1.f;
+            be[k] = beta ? beta[c] : 0.f;
+            a[k] = b[k] = 0.f;
         }
-        if (threadIdx.x == 0) bc[slot] = red[slot][0];
-        __syncthreads();
-        return bc[slot];
-    };
-
-    float s = 0.f;
-    if (active)
-        for (int p = pl; p < HW; p += lanes) s += __bfloat162float(xb[static_cast<int64_t>(p) * C]);
-    const float mean = block_sum(s, 0) / m;
-    s = 0.f;
-    if (active)
-        for (int p = pl; p < HW; p += lanes) {
-            const float d = __bfloat162float(xb[static_cast<int64_t>(p) * C]) - mean;
-            s += d * d;
+        const int64_t base = static_cast<int64_t>(n) * HW * C + cv * 8;
+        for (int p = p_begin + prow; p < p_end; p += rows) {
+            const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + base + static_cast<int64_t>(p) * C));
+            const uint4 dv = __ldg(reinterpret_cast<const uint4*>(dy + base + static_cast<int64_t>(p) * C));
+            const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w}, du[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float xe = (k & 1) ? bf16hi(xu[k >> 1]) : bf16lo(xu[k >> 1]);
+                float dz = (k & 1) ? bf16hi(du[k >> 1]) : bf16lo(du[k >> 1]);
+                const float xh = fmaf(xe, sc[k], sh[k]);
+                if (fuse_silu) dz *= silu_grad(fmaf(xh, ga[k], be[k]));
+                a[k] = fmaf(dz, xh, a[k]);
+                b[k] += dz;
+            }
         }
-    const float rstd = rsqrtf(block_sum(s, 1) / m + eps);
-    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
-    float a = 0.f, b = 0.f;  // per channel: sum dz xhat, sum dz
-    if (active)
-        for (int p = pl; p < HW; p += lanes) {
-            const float xh = (__bfloat162float(xb[static_cast<int64_t>(p) * C]) - mean) * rstd;
-            float dz = __bfloat162float(db[static_cast<int64_t>(p) * C]);
-            if (fuse_silu) dz *= silu_grad(fmaf(xh, ga, be));
-            a += dz * xh;
-            b += dz;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            sa[prow * C + cv * 8 + k] = a[k];
+            sb[prow * C + cv * 8 + k] = b[k];
         }
-    const float S2 = block_sum(active ? a * ga : 0.f, 2);
-    const float S1 = block_sum(active ? b * ga : 0.f, 3);
-    // per-channel fold over the pixel lanes (fixed order): reuse red[0] / red[1]
-    red[0][threadIdx.x] = active ? a : 0.f;
-    red[1][threadIdx.x] = active ? b : 0.f;
-    __syncthreads();
-    if (threadIdx.x < cpg) {
-        float fa = 0.f, fb = 0.f;
-        for (int l = 0; l < lanes; ++l) {
-            fa += red[0][l * cpg + threadIdx.x];
-            fb += red[1][l * cpg + threadIdx.x];
-        }
-        pc[static_cast<int64_t>(n) * C + g * cpg + threadIdx.x] = fa;
-        pc[static_cast<int64_t>(NB) * C + static_cast<int64_t>(n) * C + g * cpg + threadIdx.x] = fb;
     }
-    if (threadIdx.x == 0) {
+    __syncthreads();
+    float* dst = part + (static_cast<int64_t>(n) * chunks + chunk) * 2 * C;
+    for (int c = threadIdx.x; c < C; c += kGbThreads) {
+        float fa = 0.f, fb = 0.f;
+        for (int r = 0; r < rows; ++r) {
+            fa += sa[r * C + c];
+            fb += sb[r * C + c];
+        }
+        dst[c] = fa;
+        dst[C + c] = fb;
+    }
+}
+
+__global__ void __launch_bounds__(kGbThreads) groupnorm_bwd_fold_kernel(const float* __restrict__ part, int HW, int C, int groups,
+                                                                        int chunks, const float* __restrict__ gamma,
+                                                                        const float* __restrict__ fstat,
+                                                                        float* __restrict__ stat, float* __restrict__ pc,
+                                                                        int NB) {
+    extern __shared__ float sm[];  // gamma_c a_c | gamma_c b_c
+    const int n = blockIdx.x;
+    const int cpg = C / groups;
+    for (int c = threadIdx.x; c < C; c += kGbThreads) {
+        float a = 0.f, b = 0.f;
+        const float* src = part + static_cast<int64_t>(n) * chunks * 2 * C + c;
+        for (int k = 0; k < chunks; ++k) {
+            a += src[static_cast<int64_t>(k) * 2 * C];
+            b += src[static_cast<int64_t>(k) * 2 * C + C];
+        }
+        pc[static_cast<int64_t>(n) * C + c] = a;
+        pc[static_cast<int64_t>(NB) * C + static_cast<int64_t>(n) * C + c] = b;
+        const float ga = gamma ? gamma[c] : 1.f;
+        sm[c] = ga * a;
+        sm[C + c] = ga * b;
+    }
+    __syncthreads();
+    const float m = static_cast<float>(HW) * cpg;
+    for (int g = threadIdx.x; g < groups; g += kGbThreads) {
+        float s2 = 0.f, s1 = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            s2 += sm[c];
+            s1 += sm[C + c];
+        }
         float* o = stat + (static_cast<int64_t>(n) * groups + g) * 4;
-        o[0] = mean;
-        o[1] = rstd;
-        o[2] = S1 / m;
-        o[3] = S2 / m;
+        o[0] = fstat[(static_cast<int64_t>(n) * groups + g) * 2];
+        o[1] = fstat[(static_cast<int64_t>(n) * groups + g) * 2 + 1];
+        o[2] = s1 / m;
+        o[3] = s2 / m;
     }
 }
 
@@ -597,8 +635,14 @@ extern "C" int imagd_layernorm_bwd_bf16(const void* x, int64_t ldx, const void* 
                                         float* rowstat, void* ws, imagd_stream stream) {
     IMAGD_CHECK_ARG(x && dy && dx && rowstat && rows > 0 && C > 0 && C % 2 == 0 && C <= 2048, "layernorm_bwd: bad argument");
     IMAGD_CHECK_ARG(ldx % 2 == 0 && lddy % 2 == 0 && lddx % 2 == 0, "layernorm_bwd: odd row stride");
-    layernorm_bwd_kernel<<<(rows + 7) / 8, 256, 0, ST(stream)>>>(BF(x), ldx, BF(dy), lddy, BFW(dx), lddx, gamma, rowstat, rows,
-                                                                C, eps);
+    IMAGD_CHECK_ARG(C % 8 == 0 && ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && imagd::aligned16(x) && imagd::aligned16(dy) &&
+                        imagd::aligned16(dx), "layernorm_bwd: C / strides must be multiples of 8, pointers 16-byte aligned");
+#define IMAGD_LNB(V) layernorm_bwd_kernel<V><<<(rows + 7) / 8, 256, 0, ST(stream)>>>(BF(x), ldx, BF(dy), lddy, BFW(dx), lddx, gamma, rowstat, rows, C, eps)
+    if (C <= 512) IMAGD_LNB(2);
+    else if (C <= 768) IMAGD_LNB(3);
+    else if (C <= 1280) IMAGD_LNB(5);
+    else IMAGD_LNB(8);
+#undef IMAGD_LNB
     IMAGD_LAUNCH_CHECK("layernorm_bwd_kernel");
     if (dgamma != nullptr) {
         IMAGD_CHECK_ARG(dbeta && ws, "layernorm_bwd: dbeta / ws");
@@ -614,17 +658,37 @@ extern "C" int imagd_layernorm_bwd_bf16(const void* x, int64_t ldx, const void* 
     return IMAGD_OK;
 }
 
+static int gn_bwd_chunks(int HW, int NB) {
+    int c = (HW + 15) / 16;
+    const int cap = (148 * 2) / (NB > 0 ? NB : 1);
+    if (c > 64) c = 64;
+    if (c > cap) c = cap;
+    return c < 1 ? 1 : c;
+}
+
+extern "C" int64_t imagd_groupnorm_bwd_ws_bytes(int NB, int HW, int C, int groups) {
+    // stat [NB * groups * 4] | pc [2 * NB * C] | part [NB * chunks * 2 * C]
+    return (static_cast<int64_t>(NB) * groups * 4 + static_cast<int64_t>(2) * NB * C +
+            static_cast<int64_t>(NB) * gn_bwd_chunks(HW, NB) * 2 * C) * 4;
+}
+
 extern "C" int imagd_groupnorm_bwd_bf16(const void* x, const void* dy, void* dx, int NB, int HW, int C, int groups,
-                                        const float* gamma, const float* beta, float eps, int fuse_silu, float* dgamma,
-                                        float* dbeta, void* ws, imagd_stream stream) {
-    IMAGD_CHECK_ARG(x && dy && dx && ws && NB > 0 && HW > 0 && C % 8 == 0 && groups > 0 && C % groups == 0 && C / groups <= 256,
+                                        const float* gamma, const float* beta, const float* fwd_stats, int fuse_silu,
+                                        float* dgamma, float* dbeta, void* ws, imagd_stream stream) {
+    IMAGD_CHECK_ARG(x && dy && dx && ws && fwd_stats && NB > 0 && HW > 0 && C % 8 == 0 && C <= 2560 && groups > 0 && C % groups == 0,
                     "groupnorm_bwd: bad argument");
-    // ws: stat [NB * groups * 4] | pc [2 * NB * C]
     float* stat = static_cast<float*>(ws);
     float* pc = stat + static_cast<int64_t>(NB) * groups * 4;
-    groupnorm_bwd_reduce_kernel<<<dim3(groups, NB), 256, 0, ST(stream)>>>(BF(x), BF(dy), HW, C, groups, gamma, beta, eps,
-                                                                         fuse_silu, stat, pc, NB);
-    IMAGD_LAUNCH_CHECK("groupnorm_bwd_reduce_kernel");
+    float* part = pc + static_cast<int64_t>(2) * NB * C;
+    const int chunks = gn_bwd_chunks(HW, NB);
+    const int rows = kGbThreads / (C / 8);
+    const size_t smem1 = static_cast<size_t>(2) * rows * C * 4;  // <= 2 * 512 * 8 * 4 = 32 KB
+    groupnorm_bwd_partial_kernel<<<dim3(chunks, NB), kGbThreads, smem1, ST(stream)>>>(BF(x), BF(dy), HW, C, groups, chunks, gamma,
+                                                                                      beta, fuse_silu, fwd_stats, part);
+    IMAGD_LAUNCH_CHECK("groupnorm_bwd_partial_kernel");
+    groupnorm_bwd_fold_kernel<<<NB, kGbThreads, static_cast<size_t>(2) * C * 4, ST(stream)>>>(part, HW, C, groups, chunks, gamma,
+                                                                                             fwd_stats, stat, pc, NB);
+    IMAGD_LAUNCH_CHECK("groupnorm_bwd_fold_kernel");
     const int64_t total = static_cast<int64_t>(NB) * HW * (C / 8);
     groupnorm_bwd_apply_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(BF(x), BF(dy), BFW(dx), HW, C, groups, gamma, beta,
                                                                               fuse_silu, stat, total);
@@ -636,10 +700,6 @@ extern "C" int imagd_groupnorm_bwd_bf16(const void* x, const void* dy, void* dx,
         IMAGD_LAUNCH_CHECK("colreduce_fold_kernel");
     }
     return IMAGD_OK;
-}
-
-extern "C" int64_t imagd_groupnorm_bwd_ws_bytes(int NB, int C, int groups) {
-    return (static_cast<int64_t>(NB) * groups * 4 + static_cast<int64_t>(2) * NB * C) * 4;
 }
 
 extern "C" int imagd_act_bf16(const void* x, const void* dy, void* y, int64_t n, int mode, imagd_stream stream) {

@@ -190,8 +190,9 @@ def _gn_workspace(device, nbytes: int) -> torch.Tensor:
 
 
 def groupnorm(x: torch.Tensor, gamma, beta, groups: int, eps: float, *, silu: bool, out: Optional[torch.Tensor] = None,
-              ws: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x: [NB, HW..., C] bf16 token-major (contiguous). GroupNorm over (HW, C/groups) per sample, optional SiLU."""
+              ws: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: [NB, HW..., C] bf16 token-major (contiguous). GroupNorm over (HW, C/groups) per sample, optional SiLU.
+    stats_out: fp32 [NB, groups, 2] that receives {mean, rstd} (training-mode forward)."""
     lib = _lib.load()
     assert x.is_contiguous() and x.dtype == BF16
     NB, C = x.shape[0], x.shape[-1]
@@ -200,6 +201,12 @@ def groupnorm(x: torch.Tensor, gamma, beta, groups: int, eps: float, *, silu: bo
         out = torch.empty_like(x)
     if ws is None:
         ws = _gn_workspace(x.device, lib.imagd_groupnorm_ws_bytes(NB, HW, C, groups))
+    if stats_out is not None:
+        assert stats_out.dtype == torch.float32 and stats_out.is_contiguous() and stats_out.numel() == NB * groups * 2
+        rc = lib.imagd_groupnorm_stats_bf16(x.data_ptr(), C, out.data_ptr(), C, NB, HW, C, groups, _ptr(gamma), _ptr(beta),
+                                            float(eps), 1 if silu else 0, ws.data_ptr(), stats_out.data_ptr(), _stream())
+        _lib.check(rc, "imagd_groupnorm_stats_bf16")
+        return out
     rc = lib.imagd_groupnorm_bf16(x.data_ptr(), C, out.data_ptr(), C, NB, HW, C, groups, _ptr(gamma), _ptr(beta),
                                   float(eps), 1 if silu else 0, ws.data_ptr(), _stream())
     _lib.check(rc, "imagd_groupnorm_bf16")
@@ -533,18 +540,21 @@ def layernorm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma, eps: float, need_aff
     return dx, dg, db
 
 
-def groupnorm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma, beta, groups: int, eps: float, silu: bool, need_affine: bool):
-    """x, dy: contiguous [NB, HW..., C] bf16 -> (dx, dgamma | None, dbeta | None)."""
+def groupnorm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma, beta, groups: int, stats: torch.Tensor, silu: bool,
+                  need_affine: bool):
+    """x, dy: contiguous [NB, HW..., C] bf16; stats: the forward's {mean, rstd} [NB, groups, 2] fp32 (groupnorm(stats_out=))
+    -> (dx, dgamma | None, dbeta | None)."""
     lib = _lib.load()
     assert x.is_contiguous() and dy.is_contiguous() and x.dtype == BF16 and dy.dtype == BF16
     NB, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (NB * C)
+    assert stats.dtype == torch.float32 and stats.is_contiguous() and stats.numel() == NB * groups * 2
     dx = torch.empty_like(x)
     dg = torch.empty(C, device=x.device, dtype=torch.float32) if need_affine else None
     db = torch.empty(C, device=x.device, dtype=torch.float32) if need_affine else None
-    ws = _workspace(x.device, lib.imagd_groupnorm_bwd_ws_bytes(NB, C, groups))
+    ws = _workspace(x.device, lib.imagd_groupnorm_bwd_ws_bytes(NB, HW, C, groups))
     rc = lib.imagd_groupnorm_bwd_bf16(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), NB, HW, C, groups, _ptr(gamma), _ptr(beta),
-                                      float(eps), 1 if silu else 0, _ptr(dg), _ptr(db), ws.data_ptr(), _stream())
+                                      stats.data_ptr(), 1 if silu else 0, _ptr(dg), _ptr(db), ws.data_ptr(), _stream())
     _lib.check(rc, "imagd_groupnorm_bwd_bf16")
     return dx, dg, db
 

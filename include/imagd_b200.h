@@ -283,10 +283,16 @@ int imagd_colsum_bf16(const void* x, int64_t ldx, int rows_per_group, int groups
 int imagd_layernorm_bwd_bf16(const void* x, int64_t ldx, const void* dy, int64_t lddy, void* dx, int64_t lddx, int rows, int C,
                              const float* gamma, float eps, float* dgamma, float* dbeta, float* rowstat, void* ws,
                              imagd_stream stream);
-/* GroupNorm (+SiLU) backward over contiguous [NB, HW, C]: dx, and (dgamma non-NULL) dgamma / dbeta [C] fp32. */
-int64_t imagd_groupnorm_bwd_ws_bytes(int NB, int C, int groups);
+/* imagd_groupnorm_bf16 that also writes {mean, rstd} of every (sample, group) to stats_out [NB, groups, 2] fp32 (may be NULL):
+ * the training-mode forward; the backward reuses the statistics instead of recomputing them. */
+int imagd_groupnorm_stats_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int NB, int HW, int C, int groups,
+                               const float* gamma, const float* beta, float eps, int fuse_silu, void* ws, float* stats_out,
+                               imagd_stream stream);
+/* GroupNorm (+SiLU) backward over contiguous [NB, HW, C] given the forward statistics fwd_stats [NB, groups, 2]: dx, and
+ * (dgamma non-NULL) dgamma / dbeta [C] fp32. Three coalesced passes (per-chunk channel partials, fixed-order fold, apply). */
+int64_t imagd_groupnorm_bwd_ws_bytes(int NB, int HW, int C, int groups);
 int imagd_groupnorm_bwd_bf16(const void* x, const void* dy, void* dx, int NB, int HW, int C, int groups, const float* gamma,
-                             const float* beta, float eps, int fuse_silu, float* dgamma, float* dbeta, void* ws,
+                             const float* beta, const float* fwd_stats, int fuse_silu, float* dgamma, float* dbeta, void* ws,
                              imagd_stream stream);
 /* Elementwise activation (mode IMAGD_ACT_SILU / IMAGD_ACT_GELU): dy NULL: y = act(x); else y = dy * act'(x). */
 int imagd_act_bf16(const void* x, const void* dy, void* y, int64_t n, int mode, imagd_stream stream);

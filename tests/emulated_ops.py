@@ -111,7 +111,11 @@ def conv3x3_direct(x, w, bias, *, stride=1, act=ACT_NONE, out_nchw_f32=False, ad
     return _store(y.permute(0, 2, 3, 1).to(BF).contiguous(), out)
 
 
-def groupnorm(x, gamma, beta, groups, eps, *, silu, out=None, ws=None):
+def groupnorm(x, gamma, beta, groups, eps, *, silu, out=None, ws=None, stats_out=None):
+    if stats_out is not None:
+        xg = x.float().reshape(x.shape[0], -1, groups, x.shape[-1] // groups)
+        stats_out[:, :, 0] = xg.mean((1, 3))
+        stats_out[:, :, 1] = torch.rsqrt(xg.var((1, 3), unbiased=False) + eps)
     y = F.group_norm(x.float().movedim(-1, 1), groups, gamma, beta, eps)
     if silu:
         y = F.silu(y)
@@ -354,11 +358,11 @@ def _dsilu(z):
     return s * (1 + z * (1 - s))
 
 
-def groupnorm_bwd(x, dy, gamma, beta, groups, eps, silu, need_affine):
+def groupnorm_bwd(x, dy, gamma, beta, groups, stats, silu, need_affine):
     NB, C = x.shape[0], x.shape[-1]
     xf = x.float().reshape(NB, -1, groups, C // groups)
-    mean = xf.mean((1, 3), keepdim=True)
-    rstd = torch.rsqrt(xf.var((1, 3), unbiased=False, keepdim=True) + eps)
+    mean = stats[:, :, 0].reshape(NB, 1, groups, 1)
+    rstd = stats[:, :, 1].reshape(NB, 1, groups, 1)
     xh = ((xf - mean) * rstd).reshape(NB, -1, C)
     dz = dy.float().reshape(NB, -1, C)
     if silu:

@@ -186,12 +186,17 @@ def test_groupnorm_backward(cuda_device, C, HW, groups, silu):
     if silu:
         y = F.silu(y)
     y.movedim(1, -1).backward(dy.float())
-    dx, dg, db = ops.groupnorm_bwd(x, dy, gamma, beta, groups, 1e-5, silu, True)
+    stats = torch.empty(2, groups, 2, device=dev, dtype=torch.float32)
+    fwd = ops.groupnorm(x, gamma, beta, groups, 1e-5, silu=silu, stats_out=stats)
+    assert rel_l2(fwd, y.detach().movedim(1, -1)) < 1e-2
+    xg = x.float().view(2, HW, groups, C // groups)
+    assert rel_l2(stats[:, :, 0], xg.mean((1, 3))) < 1e-4
+    assert rel_l2(stats[:, :, 1], torch.rsqrt(xg.var((1, 3), unbiased=False) + 1e-5)) < 1e-4
+    dx, dg, db = ops.groupnorm_bwd(x, dy, gamma, beta, groups, stats, silu, True)
     assert rel_l2(dx, xl.grad) < 1e-2
     assert rel_l2(dg, gl.grad) < 2e-3 and rel_l2(db, bl.grad) < 2e-3
-    dx2, none_g, _ = ops.groupnorm_bwd(x, dy, gamma, beta, groups, 1e-5, silu, False)
+    dx2, none_g, _ = ops.groupnorm_bwd(x, dy, gamma, beta, groups, stats, silu, False)
     assert none_g is None and torch.equal(dx, dx2)
-    assert rel_l2(ops.groupnorm(x, gamma, beta, groups, 1e-5, silu=silu), y.detach().movedim(1, -1)) < 1e-2
 
 
 @pytest.mark.parametrize("rows,C", [(640, 320), (77, 768), (1000, 1280), (32, 1280)])
