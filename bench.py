@@ -536,7 +536,7 @@ def main():
     if a.workload == "train":  # BASELINE.json configs[4]: micro-batch 4 per GPU at 640 x 512 unless overridden
         Bt = a.batch if a.batch != 1 else 4
         h, w = (640, 512) if (a.height, a.width) == (512, 512) else (a.height, a.width)
-        rec = train_record(a, dev, rank, local, world, Bt, h, w, a.steps, max(a.warmup, 3))
+        rec = train_record(a, dev, rank, local, world, Bt, h, w, a.steps, max(a.warmup, 5))
         if rank == 0:
             print(json.dumps({
                 "metric": f"training samples/sec, {h}x{w} bf16 forward+backward+AdamW, micro-batch {Bt}/GPU", "value": rec["samples_per_s"],

@@ -290,7 +290,7 @@ class FlatAdamW:
     applies the update with the 1/world scale folded into the kernel."""
 
     def __init__(self, params: Iterable[nn.Parameter], lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
-                 bucket_bytes: int = 256 << 20, step_fn=None):
+                 bucket_bytes: int = 256 << 20, step_fn=None, shard_states: bool = False):
         self.params = [p for p in params if p.requires_grad]
         assert self.params, "no trainable parameters"
         dev = self.params[0].device
@@ -301,24 +301,34 @@ class FlatAdamW:
         # complete front to back
         order = list(reversed(self.params))
         sizes = [(p.numel() + 7) // 8 * 8 for p in order]  # 16-byte aligned views
-        total = sum(sizes)
-        self.master = torch.empty(total, device=dev, dtype=torch.float32)
+        self._dist = torch.distributed.is_available() and torch.distributed.is_initialized() and \
+            torch.distributed.get_world_size() > 1
+        world = torch.distributed.get_world_size() if self._dist else 1
+        rank = torch.distributed.get_rank() if self._dist else 0
+        total = (sum(sizes) + 8 * world - 1) // (8 * world) * (8 * world)  # equal, 16-byte aligned shards
+        # shard_states (ZeRO-1 style, the reference trains under DeepSpeed ZeRO, train.py:386-398): every rank keeps fp32
+        # master weights and moments only for its own 1/world slice of the flat buffer, updates that slice, and the updated
+        # bf16 slices meet in one all-gather; without it every rank holds and updates everything (plain data parallelism)
+        self.shard = bool(shard_states) and self._dist
+        per = total // world
+        self._own = (rank * per, (rank + 1) * per) if self.shard else (0, total)
+        n_own = self._own[1] - self._own[0]
         self.param = torch.zeros(total, device=dev, dtype=BF16)
         self.grad = torch.zeros(total, device=dev, dtype=BF16)
-        self.m = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.v = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.master.zero_()
+        self.master = torch.zeros(n_own, device=dev, dtype=torch.float32)
+        self.m = torch.zeros(n_own, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(n_own, device=dev, dtype=torch.float32)
         off = 0
         self._spans = []
         with torch.no_grad():
             for p, n in zip(order, sizes):
-                self.master[off:off + p.numel()].copy_(p.detach().reshape(-1).float())
                 view = self.param[off:off + p.numel()].view(p.shape)
                 view.copy_(p.detach())
                 p.data = view
                 p.grad = self.grad[off:off + p.numel()].view(p.shape)
                 self._spans.append((off, off + n))
                 off += n
+            self.master.copy_(self.param[self._own[0]:self._own[1]].float())
         # buckets: contiguous spans of ~bucket_bytes
         per = max(1, bucket_bytes // 2)
         self._buckets, self._bucket_of = [], []
@@ -331,8 +341,6 @@ class FlatAdamW:
                 lo, cnt = b, 0
         self._pending = [b[2] for b in self._buckets]
         self._handles = []
-        self._dist = torch.distributed.is_available() and torch.distributed.is_initialized() and \
-            torch.distributed.get_world_size() > 1
         if self._dist:
             for i, p in enumerate(order):
                 p.register_post_accumulate_grad_hook(self._make_hook(self._bucket_of[i]))
@@ -367,11 +375,103 @@ class FlatAdamW:
         self.reduce_remaining()
         self.t += 1
         world = torch.distributed.get_world_size() if self._dist else 1
-        self._step_fn(self.master, self.param, self.grad, self.m, self.v, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
-                      eps=self.eps, weight_decay=self.wd, step=self.t, grad_scale=1.0 / world)
+        lo, hi = self._own
+        self._step_fn(self.master, self.param[lo:hi], self.grad[lo:hi], self.m, self.v, lr=self.lr, beta1=self.betas[0],
+                      beta2=self.betas[1], eps=self.eps, weight_decay=self.wd, step=self.t, grad_scale=1.0 / world)
+        if self.shard:  # every rank updated its own slice: gather the bf16 working copy
+            torch.distributed.all_gather_into_tensor(self.param, self.param[lo:hi].clone())
         # the kernel wrote through raw pointers: bump the version counters so that weight-derived caches keyed on
         # (data_ptr, _version) — processors._ver, autograd._cached — see the update
         torch.autograd.graph.increment_version([self.param, *self.params])
+
+
+    def state_dict(self) -> Dict[str, object]:
+        return {"t": self.t, "own": self._own, "master": self.master, "m": self.m, "v": self.v,
+                "hyper": dict(lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.wd)}
+
+    def load_state_dict(self, sd: Dict[str, object]) -> None:
+        if tuple(sd["own"]) != tuple(self._own):
+            raise ValueError(f"optimizer shard {tuple(sd['own'])} does not match this rank's {self._own}")
+        self.t = int(sd["t"])
+        for name in ("master", "m", "v"):
+            getattr(self, name).copy_(sd[name])
+        with torch.no_grad():
+            self.param[self._own[0]:self._own[1]].copy_(self.master.to(BF16))
+        if self.shard:
+            torch.distributed.all_gather_into_tensor(self.param, self.param[self._own[0]:self._own[1]].clone())
+        torch.autograd.graph.increment_version([self.param, *self.params])
+
+
+# ------------------------------------------------------------------------------------------------ the callers' side of the step
+@torch.no_grad()
+def prepare_batch(batch: Dict[str, object], vae, image_encoder, text_encoder, scheduler, device, noise_offset: float = 0.05,
+                  generator: Optional[torch.Generator] = None) -> Dict[str, torch.Tensor]:
+    """train.py:519-560: the frozen encoders either side of SDModel. VAE-encode person and garment images (latent_dist.sample()
+    * 0.18215), draw the noise (+ noise_offset per-channel offset, :530-535) and uniform timesteps, CLIP-vision
+    hidden_states[-2] of the garment image (zeros where drop_image_embed, :546-551), CLIP-text last hidden state.
+    Returns the keyword arguments of train_step."""
+    dt = next(vae.parameters()).dtype if hasattr(vae, "parameters") else torch.float32
+    lat = vae.encode(batch["vae_person"].to(device, dtype=dt)).latent_dist.sample() * 0.18215
+    ref = vae.encode(batch["vae_clothes"].to(device, dtype=dt)).latent_dist.sample() * 0.18215
+    noise = torch.randn(lat.shape, device=device, dtype=torch.float32, generator=generator)
+    if noise_offset > 0:
+        noise = noise + noise_offset * torch.randn((lat.shape[0], lat.shape[1], 1, 1), device=device, dtype=torch.float32,
+                                                   generator=generator)
+    n_t = getattr(scheduler, "num_train_timesteps", None) or scheduler.config.num_train_timesteps
+    timesteps = torch.randint(0, int(n_t), (lat.shape[0],), device=device, generator=generator).long()
+    clip = torch.stack([torch.zeros_like(c) if int(d) == 1 else c
+                        for c, d in zip(batch["clip_image"], batch["drop_image_embed"])], 0)
+    cdt = next(image_encoder.parameters()).dtype
+    image_embeds = image_encoder(clip.to(device, dtype=cdt), output_hidden_states=True).hidden_states[-2]
+    text = text_encoder(batch["input_ids"].to(device))[0]
+    return dict(latents=lat.float(), ref_latents=ref.float(), clip_image_embeddings=image_embeds,
+                encoder_hidden_states=text, noise=noise, timesteps=timesteps)
+
+
+def save_checkpoint(folder: str, ckpt_id: str, sd_model: "SDModel", optimizer: Optional[FlatAdamW], epoch: int,
+                    last_global_step: int, **client_state) -> str:
+    """train.py:179-193 (DeepSpeed `model.save_checkpoint(folder, ckpt_id, client_state)`): writes
+    `<folder>/<ckpt_id>/mp_rank_00_model_states.pt` whose `["module"]` is SDModel.state_dict() — the `unet.` / `ref_unet.` /
+    `proj.` / `adapter_modules.` key layout that inference_IMAGdressing.py:97-117 routes — plus the client state, and one
+    optimizer-state file per rank. Returns the model-states path."""
+    import os
+
+    d = os.path.join(folder, str(ckpt_id))
+    os.makedirs(d, exist_ok=True)
+    rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+    path = os.path.join(d, "mp_rank_00_model_states.pt")
+    if rank == 0:
+        module = {k: v.detach().to("cpu").clone() for k, v in sd_model.state_dict().items()}
+        torch.save({"module": module, "epoch": int(epoch), "last_global_step": int(last_global_step), **client_state}, path)
+        with open(os.path.join(folder, "latest"), "w") as f:
+            f.write(str(ckpt_id))
+    if optimizer is not None:
+        osd = {k: (v.detach().to("cpu") if torch.is_tensor(v) else v) for k, v in optimizer.state_dict().items()}
+        torch.save(osd, os.path.join(d, f"zero_pp_rank_{rank}_mp_rank_00_optim_states.pt"))
+    return path
+
+
+def load_checkpoint(load_dir: str, sd_model: "SDModel", optimizer: Optional[FlatAdamW] = None, tag: Optional[str] = None):
+    """train.py:196-207: restores the module (and this rank's optimizer shard); returns (epoch, last_global_step)."""
+    import os
+
+    if tag is None:
+        with open(os.path.join(load_dir, "latest")) as f:
+            tag = f.read().strip()
+    d = os.path.join(load_dir, tag)
+    st = torch.load(os.path.join(d, "mp_rank_00_model_states.pt"), map_location="cpu", weights_only=False)
+    with torch.no_grad():
+        own = sd_model.state_dict()
+        for k, v in st["module"].items():
+            own[k].copy_(v)  # in place: the parameters stay views of the optimizer's flat buffer
+    for m in (sd_model.unet, sd_model.ref_unet):
+        m.invalidate_packed()
+    rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+    if optimizer is not None:
+        optimizer.load_state_dict(torch.load(os.path.join(d, f"zero_pp_rank_{rank}_mp_rank_00_optim_states.pt"),
+                                             map_location=optimizer.master.device, weights_only=False))
+    ag.clear_cache()
+    return int(st["epoch"]), int(st["last_global_step"])
 
 
 def train_step(sd_model: SDModel, scheduler, latents, ref_latents, clip_image_embeddings, encoder_hidden_states, noise,
