@@ -29,17 +29,30 @@ HW = int(os.environ.get("HW", "64"))
 bench.HW = HW
 
 # ---- 1. record the problems
-pipe = bench.build_product(dev)
-cn = modeling.UNet2DConditionModel  # noqa
-controlnet = modeling.ControlNetModel().to(dev, torch.bfloat16)
-modeling.init_synthetic_fast_(controlnet, 2)
-lib.imagd_gemm_debug_log(1, None, 0)
-for B in BATCHES:
-    x = bench.synth_inputs(B, dev)
-    bench.run_pipe(pipe, x)
-    lat2 = torch.randn(2 * B, 4, HW, HW, device=dev)
-    controlnet(lat2, torch.tensor([500.0], device=dev), torch.randn(2 * B, 77, 768, device=dev),
-               torch.rand(B, 3, HW * 8, HW * 8, device=dev), return_dict=False)
+TRAIN = os.environ.get("TRAIN", "0") == "1"  # TRAIN=1 EPI=0: the problems of one training step (forward, dgrad, wgrad)
+if TRAIN:
+    from imagdressing_b200 import train
+
+    sd, opt, sched = bench.build_train(dev)
+    lib.imagd_gemm_debug_log(1, None, 0)
+    for B in BATCHES:
+        xb = bench.synth_train_batch(B, dev, 0, False, int(os.environ.get("TH", "640")) // 8, int(os.environ.get("TW", "512")) // 8)
+        train.train_step(sd, sched, optimizer=opt, **xb)
+    torch.cuda.synchronize()
+    del sd, opt
+    pipe = controlnet = None
+else:
+    pipe = bench.build_product(dev)
+    cn = modeling.UNet2DConditionModel  # noqa
+    controlnet = modeling.ControlNetModel().to(dev, torch.bfloat16)
+    modeling.init_synthetic_fast_(controlnet, 2)
+    lib.imagd_gemm_debug_log(1, None, 0)
+    for B in BATCHES:
+        x = bench.synth_inputs(B, dev)
+        bench.run_pipe(pipe, x)
+        lat2 = torch.randn(2 * B, 4, HW, HW, device=dev)
+        controlnet(lat2, torch.tensor([500.0], device=dev), torch.randn(2 * B, 77, 768, device=dev),
+                   torch.rand(B, 3, HW * 8, HW * 8, device=dev), return_dict=False)
 torch.cuda.synchronize()
 buf = ctypes.create_string_buffer(1 << 20)
 n = lib.imagd_gemm_debug_log(0, buf, len(buf))
