@@ -291,6 +291,9 @@ def train_record(a, dev, rank, local, world, B, h, w, steps, warm):
         rec["model_tflops"] = round(sps / world * TRAIN_TFLOP_PER_SAMPLE_640x512, 1)
         rec["model_frac_of_sustained_bf16"] = round(sps / world * TRAIN_TFLOP_PER_SAMPLE_640x512 / tf_sus, 4)
     del sd, opt
+    from imagdressing_b200 import autograd as _ag
+
+    _ag.clear_cache()  # derived operands / fp32 shadows of the deleted modules
     torch.cuda.empty_cache()
     return rec
 

@@ -42,14 +42,40 @@ def _cached(kind: str, w: torch.Tensor, frozen: bool, build):
 
 def clear_cache():
     _frozen_cache.clear()
+    _fp32_shadow.clear()
 
 
 def _bf(t: torch.Tensor) -> torch.Tensor:
     return t if t.dtype == BF16 else t.to(BF16)
 
 
+_fp32_shadow = {}
+
+
+def register_fp32_shadow(param: torch.Tensor, shadow: torch.Tensor) -> None:
+    """`shadow` is an always-current fp32 copy of `param` (the optimizer's master weights): the kernels' fp32 bias / affine
+    arguments then need no per-call conversion launch."""
+    _fp32_shadow[(param.data_ptr(), tuple(param.shape))] = shadow
+
+
 def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
-    return None if t is None else t.detach().float().contiguous()
+    """fp32 contiguous view of a bias / norm parameter: itself, the optimizer's master copy, a cached copy (frozen
+    parameters), or a conversion."""
+    if t is None:
+        return None
+    if t.dtype == torch.float32 and t.is_contiguous():
+        return t.detach()
+    hit = _fp32_shadow.get((t.data_ptr(), tuple(t.shape)))
+    if hit is not None:
+        return hit
+    if not t.requires_grad:
+        return _cached("f32", t, True, lambda: t.detach().float().contiguous())
+    return t.detach().float().contiguous()
+
+
+def _gdt(p: Optional[torch.Tensor]):
+    """dtype in which a bias / affine gradient is produced: the parameter's own when it is bf16 (no conversion launch)."""
+    return BF16 if p is not None and p.dtype == BF16 else torch.float32
 
 
 def _as(t: Optional[torch.Tensor], like: torch.Tensor) -> Optional[torch.Tensor]:
@@ -81,7 +107,7 @@ class Linear(Function):
             x2 = x if x.dim() == 2 else x.reshape(-1, K)
             dw = ops.gemm(ops.transpose(dy2), ops.transpose(x2))  # [N, K], reduction over the (zero-padded) tokens
         if need_b and ctx.bias is not None:
-            db = _as(ops.colsum(dy2)[0], ctx.bias)
+            db = _as(ops.colsum(dy2, None, _gdt(ctx.bias))[0], ctx.bias)
         if need_r and ctx.res is not None:
             dr = dy2.view(ctx.res.shape)
         return dx, dw, db, dr, None
@@ -91,16 +117,34 @@ def linear(x, w, bias=None, residual=None, out_fp32=False):
     return Linear.apply(x, _bf(w), bias, residual, out_fp32)
 
 
+class PackConv(Function):
+    """[Cout, Cin, 3, 3] -> tap-major [Cout, 9*Cin] (and the packed gradient back), one layout kernel each way."""
+
+    @staticmethod
+    def forward(ctx, w):
+        return ops.conv_weight_layout(w.contiguous(), 0)
+
+    @staticmethod
+    def backward(ctx, dwp):
+        return ops.conv_weight_layout(_bf(dwp).contiguous(), 1)
+
+
 def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
-    """[Cout, Cin, 3, 3] -> tap-major [Cout, 9*Cin] bf16 — differentiable (torch autograd un-permutes the gradient)."""
-    co, ci = w.shape[:2]
-    return _bf(w).permute(0, 2, 3, 1).reshape(co, 9 * ci).contiguous()
+    """[Cout, Cin, 3, 3] -> tap-major [Cout, 9*Cin] bf16, differentiable."""
+    if 9 * w.shape[1] * 2 > 48 * 1024:  # (no such layer in SD1.5: Cin <= 2560)
+        co, ci = w.shape[:2]
+        return _bf(w).permute(0, 2, 3, 1).reshape(co, 9 * ci).contiguous()
+    return PackConv.apply(_bf(w))
 
 
 def _flip_taps(wp: torch.Tensor, cin: int) -> torch.Tensor:
-    """Packed forward weight [Cout, 9*Cin] -> the dgrad weight [Cin, 9*Cout]: W'[ci, 8 - tap, co] = W[co, tap, ci]."""
+    """Packed forward weight [Cout, 9*Cin] -> the dgrad weight [Cin, 9*Cout]: W'[ci, 8 - tap, co] = W[co, tap, ci] — nine
+    strided [Cout, Cin] -> [Cin, Cout] transposes (one per tap) on the transpose kernel."""
     co = wp.shape[0]
-    return wp.view(co, 9, cin).flip(1).permute(2, 1, 0).reshape(cin, 9 * co).contiguous()
+    out = torch.empty(cin, 9 * co, device=wp.device, dtype=wp.dtype)
+    for t in range(9):
+        ops.transpose(wp[:, t * cin:(t + 1) * cin], out=out[:, (8 - t) * co:(9 - t) * co])
+    return out
 
 
 class Conv3x3(Function):
@@ -128,7 +172,7 @@ class Conv3x3(Function):
         if need_w:
             dw = ops.gemm(ops.transpose(dy2), ops.im2col3x3_t(x))[:, :9 * Cin]
         if need_b and ctx.bias is not None:
-            db = _as(ops.colsum(dy2)[0], ctx.bias)
+            db = _as(ops.colsum(dy2, None, _gdt(ctx.bias))[0], ctx.bias)
         if need_v and ctx.has_rowvec:
             dv = ops.colsum(dy2, H * W)  # fp32 [NB, Cout]
         if need_r and ctx.res is not None:
@@ -163,7 +207,7 @@ class ConvIn(Function):
         if ctx.needs_input_grad[1]:
             dw = ops.gemm(ops.transpose(dy2), ops.im2col3x3_t(x))[:, :9 * Cin].contiguous()
         if ctx.needs_input_grad[2] and ctx.bias is not None:
-            db = _as(ops.colsum(dy2)[0], ctx.bias)
+            db = _as(ops.colsum(dy2, None, _gdt(ctx.bias))[0], ctx.bias)
         return None, dw, db
 
 
@@ -203,7 +247,7 @@ class GroupNorm(Function):
         x, g32, b32, stats = ctx.saved_tensors
         groups, silu, gamma, beta = ctx.cfg
         need_aff = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        dx, dg, db = ops.groupnorm_bwd(x, _bf(dy).contiguous(), g32, b32, groups, stats, silu, need_aff)
+        dx, dg, db = ops.groupnorm_bwd(x, _bf(dy).contiguous(), g32, b32, groups, stats, silu, need_aff, _gdt(gamma))
         return (dx if ctx.needs_input_grad[0] else None, _as(dg, gamma) if ctx.needs_input_grad[1] else None,
                 _as(db, beta) if ctx.needs_input_grad[2] else None, None, None, None)
 
@@ -226,7 +270,7 @@ class LayerNorm(Function):
         x, g32 = ctx.saved_tensors
         eps, gamma, beta = ctx.cfg
         need_aff = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        dx, dg, db = ops.layernorm_bwd(x, _bf(dy).contiguous(), g32, eps, need_aff)
+        dx, dg, db = ops.layernorm_bwd(x, _bf(dy).contiguous(), g32, eps, need_aff, _gdt(gamma))
         return (dx if ctx.needs_input_grad[0] else None, _as(dg, gamma) if ctx.needs_input_grad[1] else None,
                 _as(db, beta) if ctx.needs_input_grad[2] else None, None)
 

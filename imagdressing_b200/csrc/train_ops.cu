@@ -11,81 +11,120 @@
 namespace imagd {
 
 // ------------------------------------------------------------------------------------------------ transposes
-// y[c, r] = x[r, c] for r < rows, 0 for rows <= r < rows_pad  (y: [cols, ldy], ldy >= rows_pad). 64 x 64 tiles through
-// shared memory: 4-byte global accesses on both sides (bf16 pairs along the contiguous dimension).
-__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
-                                                             __nv_bfloat16* __restrict__ y, int64_t ldy, int rows, int cols,
-                                                             int rows_pad) {
-    __shared__ __nv_bfloat16 tile[64][66];
-    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    for (int rr = ty; rr < 64; rr += 8) {
-        const int r = r0 + rr, c = c0 + tx * 2;
-        __nv_bfloat16 a = __float2bfloat16(0.f), b = a;
-        if (r < rows) {
-            if (c + 1 < cols && ((ldx & 1) == 0)) {
-                const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + static_cast<int64_t>(r) * ldx + c);
-                a = v.x;
-                b = v.y;
-            } else {
-                if (c < cols) a = x[static_cast<int64_t>(r) * ldx + c];
-                if (c + 1 < cols) b = x[static_cast<int64_t>(r) * ldx + c + 1];
-            }
-        }
-        tile[rr][tx * 2] = a;
-        tile[rr][tx * 2 + 1] = b;
+// 64 x 64 tiles through shared memory, 128-bit global accesses on both sides: rows are staged as they are (16-byte shared
+// stores), every output vector gathers 8 elements of one column with 2-byte shared loads (row pitch 66 elements = 33 words:
+// the 8 rows of a gather and the 32 lanes of a warp fall into distinct banks or share a word). `load_row` abstracts where a
+// tile row comes from, so the plain transpose and the transposed im2col share the body.
+template <typename LoadRow>
+__device__ __forceinline__ void transpose_tile_body(LoadRow load_row, __nv_bfloat16* __restrict__ y, int64_t ldy, int r0, int c0,
+                                                    int cols, int rows_pad, bool vec_ok) {
+    __shared__ __align__(16) __nv_bfloat16 tile[64][72];  // pitch 72 elements = 144 B: 16-byte aligned rows, 36-word stride
+    // stage: 64 rows x 8 vectors of 8 elements = 512 vectors, two per thread
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int v = threadIdx.x + it * 256;
+        const int rr = v >> 3, cv = v & 7;
+        uint4 val = load_row(r0 + rr, c0 + cv * 8);
+        *reinterpret_cast<uint4*>(&tile[rr][cv * 8]) = val;
     }
     __syncthreads();
-    for (int cc = ty; cc < 64; cc += 8) {
-        const int c = c0 + cc, r = r0 + tx * 2;
-        if (c < cols) {
-            __nv_bfloat16* dst = y + static_cast<int64_t>(c) * ldy + r;
-            if (r + 1 < rows_pad && ((ldy & 1) == 0)) {
-                __nv_bfloat162 v;
-                v.x = tile[tx * 2][cc];
-                v.y = tile[tx * 2 + 1][cc];
-                *reinterpret_cast<__nv_bfloat162*>(dst) = v;
-            } else {
-                if (r < rows_pad) dst[0] = tile[tx * 2][cc];
-                if (r + 1 < rows_pad) dst[1] = tile[tx * 2 + 1][cc];
-            }
+    // emit: 64 output rows (source columns) x 8 vectors of 8 source rows
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int v = threadIdx.x + it * 256;
+        const int cc = v & 63, rv = v >> 6;  // consecutive lanes -> consecutive source columns (distinct banks), same row group
+        const int c = c0 + cc, r = r0 + rv * 8;
+        if (c >= cols || r >= rows_pad) continue;
+        __nv_bfloat16 e[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e[k] = tile[rv * 8 + k][cc];
+        __nv_bfloat16* dst = y + static_cast<int64_t>(c) * ldy + r;
+        if (vec_ok && r + 8 <= rows_pad) {
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(e);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (r + k < rows_pad) dst[k] = e[k];
         }
     }
 }
 
+// y[c, r] = x[r, c] for r < rows, 0 for rows <= r < rows_pad  (y: [cols, ldy], ldy >= rows_pad).
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx,
+                                                             __nv_bfloat16* __restrict__ y, int64_t ldy, int rows, int cols,
+                                                             int rows_pad) {
+    const bool in_vec = (ldx % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    const bool out_vec = (ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    auto load_row = [&](int r, int c) -> uint4 {
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (r < rows && c < cols) {
+            const __nv_bfloat16* src = x + static_cast<int64_t>(r) * ldx + c;
+            if (in_vec && c + 8 <= cols) {
+                val = __ldg(reinterpret_cast<const uint4*>(src));
+            } else {
+                __nv_bfloat16 e[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) e[k] = c + k < cols ? src[k] : __float2bfloat16(0.f);
+                val = *reinterpret_cast<const uint4*>(e);
+            }
+        }
+        return val;
+    };
+    transpose_tile_body(load_row, y, ldy, blockIdx.y * 64, blockIdx.x * 64, cols, rows_pad, out_vec);
+}
+
 // Transposed im2col of a stride-1 pad-1 3x3 conv input: out[(tap * C + c), p] = x[n, y + ky - 1, x + kx - 1, c] (0 outside),
 // p = (n * H + y) * W + x, zero for P <= p < ldo. The B operand [9 Cin, P] of the conv weight-gradient GEMM
-// dW[Cout, 9 Cin] = dY^T[Cout, P] . col^T (K = P contiguous). grid (P tiles, C tiles, 9 taps).
+// dW[Cout, 9 Cin] = dY^T[Cout, P] . col^T (K = P contiguous). grid (C tiles, P tiles, 9 taps).
 __global__ void __launch_bounds__(256) im2col3x3_t_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                           int64_t ldo, int NB, int H, int W, int C) {
-    __shared__ __nv_bfloat16 tile[64][66];
     const int tap = blockIdx.z, ky = tap / 3, kx = tap % 3;
-    const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int P = NB * H * W;
-    for (int rr = ty; rr < 64; rr += 8) {
-        const int p = p0 + rr, c = c0 + tx * 2;
-        __nv_bfloat16 a = __float2bfloat16(0.f), b = a;
-        if (p < P) {
+    const bool in_vec = (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    const bool out_vec = (ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    auto load_row = [&](int p, int c) -> uint4 {
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (p < P && c < C) {
             const int xx = p % W, yy = (p / W) % H, n = p / (W * H);
             const int sy = yy + ky - 1, sx = xx + kx - 1;
             if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
                 const __nv_bfloat16* src = x + ((static_cast<int64_t>(n) * H + sy) * W + sx) * C + c;
-                if (c < C) a = src[0];
-                if (c + 1 < C) b = src[1];
+                if (in_vec && c + 8 <= C) {
+                    val = __ldg(reinterpret_cast<const uint4*>(src));
+                } else {
+                    __nv_bfloat16 e[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) e[k] = c + k < C ? src[k] : __float2bfloat16(0.f);
+                    val = *reinterpret_cast<const uint4*>(e);
+                }
             }
         }
-        tile[rr][tx * 2] = a;
-        tile[rr][tx * 2 + 1] = b;
-    }
+        return val;
+    };
+    transpose_tile_body(load_row, out + static_cast<int64_t>(tap) * C * ldo, ldo, blockIdx.y * 64, blockIdx.x * 64, C,
+                        static_cast<int>(ldo), out_vec);
+}
+
+// 3x3 conv weight layouts, one CTA per output channel (the row of Cin * 9 values is staged in shared memory, both global
+// sides contiguous): mode 0 packs diffusers' [Cout, Cin, 3, 3] into the kernels' tap-major [Cout, 9, Cin]; mode 1 is the
+// inverse (a packed weight GRADIENT back to the parameter's layout).
+__global__ void __launch_bounds__(256) conv_weight_layout_kernel(const __nv_bfloat16* __restrict__ src,
+                                                                 __nv_bfloat16* __restrict__ dst, int Cin, int mode) {
+    extern __shared__ __nv_bfloat16 wrow[];
+    const int n = Cin * 9;
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * n;
+    for (int i = threadIdx.x; i < n; i += 256) wrow[i] = src[base + i];
     __syncthreads();
-    for (int cc = ty; cc < 64; cc += 8) {
-        const int c = c0 + cc, p = p0 + tx * 2;
-        if (c < C) {
-            __nv_bfloat16* dst = out + (static_cast<int64_t>(tap) * C + c) * ldo + p;
-            if (p < ldo) dst[0] = tile[tx * 2][cc];
-            if (p + 1 < ldo) dst[1] = tile[tx * 2 + 1][cc];
+    for (int i = threadIdx.x; i < n; i += 256) {
+        int j;
+        if (mode == 0) {
+            const int t = i / Cin, ci = i - t * Cin;  // dst[t][ci] = src[ci][t]
+            j = ci * 9 + t;
+        } else {
+            const int ci = i / 9, t = i - ci * 9;  // dst[ci][t] = src[t][ci]
+            j = t * Cin + ci;
         }
+        dst[base + i] = wrow[j];
     }
 }
 
@@ -213,8 +252,8 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const __nv_bfloat16* __r
 }
 
 // out[k][g][c] = sum_s part[k][s][g][c]   (k < nout)
-__global__ void colreduce_fold_kernel(const float* __restrict__ part, float* __restrict__ out0, float* __restrict__ out1, int C,
-                                      int groups, int splits) {
+__global__ void colreduce_fold_kernel(const float* __restrict__ part, void* __restrict__ out0, void* __restrict__ out1, int C,
+                                      int groups, int splits, int out_bf16) {
     const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t n = static_cast<int64_t>(groups) * C;
     if (idx >= n) return;
@@ -223,8 +262,13 @@ __global__ void colreduce_fold_kernel(const float* __restrict__ part, float* __r
         a += part[static_cast<int64_t>(s) * n + idx];
         if (out1) b += part[(static_cast<int64_t>(splits) + s) * n + idx];
     }
-    out0[idx] = a;
-    if (out1) out1[idx] = b;
+    if (out_bf16) {  // parameter gradients of a bf16 model: written in the parameter's dtype, no conversion launch
+        static_cast<__nv_bfloat16*>(out0)[idx] = __float2bfloat16(a);
+        if (out1) static_cast<__nv_bfloat16*>(out1)[idx] = __float2bfloat16(b);
+    } else {
+        static_cast<float*>(out0)[idx] = a;
+        if (out1) static_cast<float*>(out1)[idx] = b;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm backward
@@ -579,9 +623,17 @@ extern "C" int imagd_transpose_bf16(const void* x, int64_t ldx, void* y, int64_t
     return IMAGD_OK;
 }
 
+extern "C" int imagd_conv_weight_layout_bf16(const void* src, void* dst, int Cout, int Cin, int mode, imagd_stream stream) {
+    IMAGD_CHECK_ARG(src && dst && Cout > 0 && Cin > 0 && Cin * 9 * 2 <= 48 * 1024 && (mode == 0 || mode == 1),
+                    "conv_weight_layout: bad argument");
+    conv_weight_layout_kernel<<<Cout, 256, static_cast<size_t>(Cin) * 9 * 2, ST(stream)>>>(BF(src), BFW(dst), Cin, mode);
+    IMAGD_LAUNCH_CHECK("conv_weight_layout_kernel");
+    return IMAGD_OK;
+}
+
 extern "C" int imagd_im2col3x3_t_bf16(const void* x, void* out, int64_t ldo, int NB, int H, int W, int C, imagd_stream stream) {
     IMAGD_CHECK_ARG(x && out && NB > 0 && H > 0 && W > 0 && C > 0 && ldo >= static_cast<int64_t>(NB) * H * W, "im2col3x3_t: bad argument");
-    dim3 grid(static_cast<unsigned>((ldo + 63) / 64), (C + 63) / 64, 9);
+    dim3 grid((C + 63) / 64, static_cast<unsigned>((ldo + 63) / 64), 9);
     im2col3x3_t_kernel<<<grid, 256, 0, ST(stream)>>>(BF(x), BFW(out), ldo, NB, H, W, C);
     IMAGD_LAUNCH_CHECK("im2col3x3_t_kernel");
     return IMAGD_OK;
@@ -616,8 +668,8 @@ extern "C" int64_t imagd_colreduce_ws_bytes(int rows_per_group, int groups, int 
     return static_cast<int64_t>(2) * colreduce_splits(rows_per_group, groups, C) * groups * C * 4;
 }
 
-extern "C" int imagd_colsum_bf16(const void* x, int64_t ldx, int rows_per_group, int groups, int C, float* out, void* ws,
-                                 imagd_stream stream) {
+extern "C" int imagd_colsum_bf16(const void* x, int64_t ldx, int rows_per_group, int groups, int C, void* out, int out_bf16,
+                                 void* ws, imagd_stream stream) {
     IMAGD_CHECK_ARG(x && out && ws && rows_per_group > 0 && groups > 0 && C > 0, "colsum: bad argument");
     const int splits = colreduce_splits(rows_per_group, groups, C);
     dim3 grid((C + 63) / 64, groups, splits);
@@ -625,14 +677,14 @@ extern "C" int imagd_colsum_bf16(const void* x, int64_t ldx, int rows_per_group,
                                                       rows_per_group, groups, splits);
     IMAGD_LAUNCH_CHECK("colreduce_kernel<0>");
     colreduce_fold_kernel<<<blocks_for(static_cast<int64_t>(groups) * C, 256), 256, 0, ST(stream)>>>(
-        static_cast<const float*>(ws), out, nullptr, C, groups, splits);
+        static_cast<const float*>(ws), out, nullptr, C, groups, splits, out_bf16);
     IMAGD_LAUNCH_CHECK("colreduce_fold_kernel");
     return IMAGD_OK;
 }
 
 extern "C" int imagd_layernorm_bwd_bf16(const void* x, int64_t ldx, const void* dy, int64_t lddy, void* dx, int64_t lddx,
-                                        int rows, int C, const float* gamma, float eps, float* dgamma, float* dbeta,
-                                        float* rowstat, void* ws, imagd_stream stream) {
+                                        int rows, int C, const float* gamma, float eps, void* dgamma, void* dbeta,
+                                        int out_bf16, float* rowstat, void* ws, imagd_stream stream) {
     IMAGD_CHECK_ARG(x && dy && dx && rowstat && rows > 0 && C > 0 && C % 2 == 0 && C <= 2048, "layernorm_bwd: bad argument");
     IMAGD_CHECK_ARG(ldx % 2 == 0 && lddy % 2 == 0 && lddx % 2 == 0, "layernorm_bwd: odd row stride");
     IMAGD_CHECK_ARG(C % 8 == 0 && ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && imagd::aligned16(x) && imagd::aligned16(dy) &&
@@ -652,7 +704,7 @@ extern "C" int imagd_layernorm_bwd_bf16(const void* x, int64_t ldx, const void* 
                                                           splits);
         IMAGD_LAUNCH_CHECK("colreduce_kernel<1>");
         colreduce_fold_kernel<<<blocks_for(C, 256), 256, 0, ST(stream)>>>(static_cast<const float*>(ws), dgamma, dbeta, C, 1,
-                                                                         splits);
+                                                                         splits, out_bf16);
         IMAGD_LAUNCH_CHECK("colreduce_fold_kernel");
     }
     return IMAGD_OK;
@@ -674,7 +726,7 @@ extern "C" int64_t imagd_groupnorm_bwd_ws_bytes(int NB, int HW, int C, int group
 
 extern "C" int imagd_groupnorm_bwd_bf16(const void* x, const void* dy, void* dx, int NB, int HW, int C, int groups,
                                         const float* gamma, const float* beta, const float* fwd_stats, int fuse_silu,
-                                        float* dgamma, float* dbeta, void* ws, imagd_stream stream) {
+                                        void* dgamma, void* dbeta, int out_bf16, void* ws, imagd_stream stream) {
     IMAGD_CHECK_ARG(x && dy && dx && ws && fwd_stats && NB > 0 && HW > 0 && C % 8 == 0 && C <= 2560 && groups > 0 && C % groups == 0,
                     "groupnorm_bwd: bad argument");
     float* stat = static_cast<float*>(ws);
@@ -696,7 +748,7 @@ extern "C" int imagd_groupnorm_bwd_bf16(const void* x, const void* dy, void* dx,
     if (dgamma != nullptr) {
         IMAGD_CHECK_ARG(dbeta, "groupnorm_bwd: dbeta");
         // fold the per-sample partials: pc is [2][NB][C] = the colreduce part layout with splits = NB, groups = 1
-        colreduce_fold_kernel<<<blocks_for(C, 256), 256, 0, ST(stream)>>>(pc, dgamma, dbeta, C, 1, NB);
+        colreduce_fold_kernel<<<blocks_for(C, 256), 256, 0, ST(stream)>>>(pc, dgamma, dbeta, C, 1, NB, out_bf16);
         IMAGD_LAUNCH_CHECK("colreduce_fold_kernel");
     }
     return IMAGD_OK;

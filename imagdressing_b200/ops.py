@@ -465,15 +465,36 @@ def attention_bwd(q: torch.Tensor, d_out: torch.Tensor, B: int, Lq: int, heads: 
     _lib.check(rc, "imagd_attention_bwd_bf16")
 
 
-def transpose(x: torch.Tensor, pad_to: int = 8) -> torch.Tensor:
-    """x: [rows, cols] bf16 (row stride arbitrary) -> [cols, rows_pad] with zero columns up to a multiple of `pad_to`."""
+def transpose(x: torch.Tensor, pad_to: int = 8, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: [rows, cols] bf16 (row stride arbitrary) -> [cols, rows_pad] with zero columns up to a multiple of `pad_to`.
+    out: a [cols, rows] view (row stride arbitrary) to write into instead (no padding then)."""
     lib = _lib.load()
     assert x.dim() == 2 and x.dtype == BF16 and x.stride(1) == 1
     rows, cols = x.shape
+    if out is not None:
+        assert out.shape == (cols, rows) and out.dtype == BF16 and out.stride(1) == 1
+        _lib.check(lib.imagd_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, cols, rows, _stream()),
+                   "imagd_transpose_bf16")
+        return out
     rows_pad = (rows + pad_to - 1) // pad_to * pad_to
     out = torch.empty(cols, rows_pad, device=x.device, dtype=BF16)
     _lib.check(lib.imagd_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), rows_pad, rows, cols, rows_pad, _stream()),
                "imagd_transpose_bf16")
+    return out
+
+
+def conv_weight_layout(w: torch.Tensor, mode: int) -> torch.Tensor:
+    """mode 0: [Cout, Cin, 3, 3] -> tap-major [Cout, 9*Cin]; mode 1: packed [Cout, 9*Cin] -> [Cout, Cin, 3, 3]. bf16, contiguous."""
+    lib = _lib.load()
+    assert w.dtype == BF16 and w.is_contiguous()
+    if mode == 0:
+        co, ci = w.shape[:2]
+        out = torch.empty(co, 9 * ci, device=w.device, dtype=BF16)
+    else:
+        co, ci = w.shape[0], w.shape[1] // 9
+        out = torch.empty(co, ci, 3, 3, device=w.device, dtype=BF16)
+    _lib.check(lib.imagd_conv_weight_layout_bf16(w.data_ptr(), out.data_ptr(), co, ci, int(mode), _stream()),
+               "imagd_conv_weight_layout_bf16")
     return out
 
 
@@ -510,51 +531,53 @@ def downsum2x(dy: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def colsum(x: torch.Tensor, rows_per_group: Optional[int] = None) -> torch.Tensor:
-    """x: [rows, C] bf16 -> fp32 [groups, C] column sums over consecutive groups of rows_per_group rows."""
+def colsum(x: torch.Tensor, rows_per_group: Optional[int] = None, out_dtype=torch.float32) -> torch.Tensor:
+    """x: [rows, C] bf16 -> [groups, C] column sums over consecutive groups of rows_per_group rows (fp32 or bf16 out)."""
     lib = _lib.load()
     rows, C, ldx = _rows2d(x)
     rpg = rows if rows_per_group is None else int(rows_per_group)
     groups = rows // rpg
-    assert groups * rpg == rows and x.dtype == BF16
-    out = torch.empty(groups, C, device=x.device, dtype=torch.float32)
+    assert groups * rpg == rows and x.dtype == BF16 and out_dtype in (torch.float32, BF16)
+    out = torch.empty(groups, C, device=x.device, dtype=out_dtype)
     ws = _workspace(x.device, lib.imagd_colreduce_ws_bytes(rpg, groups, C))
-    _lib.check(lib.imagd_colsum_bf16(x.data_ptr(), ldx, rpg, groups, C, out.data_ptr(), ws.data_ptr(), _stream()),
-               "imagd_colsum_bf16")
+    _lib.check(lib.imagd_colsum_bf16(x.data_ptr(), ldx, rpg, groups, C, out.data_ptr(), 1 if out_dtype == BF16 else 0,
+                                     ws.data_ptr(), _stream()), "imagd_colsum_bf16")
     return out
 
 
-def layernorm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma, eps: float, need_affine: bool):
-    """-> (dx bf16 like x, dgamma fp32 [C] | None, dbeta fp32 [C] | None)."""
+def layernorm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma, eps: float, need_affine: bool, out_dtype=torch.float32):
+    """-> (dx bf16 like x, dgamma [C] | None, dbeta [C] | None); the affine gradients in out_dtype (fp32 or bf16)."""
     lib = _lib.load()
     rows, C, ldx = _rows2d(x)
     _, _, lddy = _rows2d(dy)
     dx = torch.empty(*x.shape, device=x.device, dtype=BF16)
     rowstat = torch.empty(rows, 2, device=x.device, dtype=torch.float32)
-    dg = torch.empty(C, device=x.device, dtype=torch.float32) if need_affine else None
-    db = torch.empty(C, device=x.device, dtype=torch.float32) if need_affine else None
+    dg = torch.empty(C, device=x.device, dtype=out_dtype) if need_affine else None
+    db = torch.empty(C, device=x.device, dtype=out_dtype) if need_affine else None
     ws = _workspace(x.device, lib.imagd_colreduce_ws_bytes(rows, 1, C))
     rc = lib.imagd_layernorm_bwd_bf16(x.data_ptr(), ldx, dy.data_ptr(), lddy, dx.data_ptr(), _rows2d(dx)[2], rows, C, _ptr(gamma),
-                                      float(eps), _ptr(dg), _ptr(db), rowstat.data_ptr(), ws.data_ptr(), _stream())
+                                      float(eps), _ptr(dg), _ptr(db), 1 if out_dtype == BF16 else 0, rowstat.data_ptr(),
+                                      ws.data_ptr(), _stream())
     _lib.check(rc, "imagd_layernorm_bwd_bf16")
     return dx, dg, db
 
 
 def groupnorm_bwd(x: torch.Tensor, dy: torch.Tensor, gamma, beta, groups: int, stats: torch.Tensor, silu: bool,
-                  need_affine: bool):
+                  need_affine: bool, out_dtype=torch.float32):
     """x, dy: contiguous [NB, HW..., C] bf16; stats: the forward's {mean, rstd} [NB, groups, 2] fp32 (groupnorm(stats_out=))
-    -> (dx, dgamma | None, dbeta | None)."""
+    -> (dx, dgamma | None, dbeta | None); the affine gradients in out_dtype (fp32 or bf16)."""
     lib = _lib.load()
     assert x.is_contiguous() and dy.is_contiguous() and x.dtype == BF16 and dy.dtype == BF16
     NB, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (NB * C)
     assert stats.dtype == torch.float32 and stats.is_contiguous() and stats.numel() == NB * groups * 2
     dx = torch.empty_like(x)
-    dg = torch.empty(C, device=x.device, dtype=torch.float32) if need_affine else None
-    db = torch.empty(C, device=x.device, dtype=torch.float32) if need_affine else None
+    dg = torch.empty(C, device=x.device, dtype=out_dtype) if need_affine else None
+    db = torch.empty(C, device=x.device, dtype=out_dtype) if need_affine else None
     ws = _workspace(x.device, lib.imagd_groupnorm_bwd_ws_bytes(NB, HW, C, groups))
     rc = lib.imagd_groupnorm_bwd_bf16(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), NB, HW, C, groups, _ptr(gamma), _ptr(beta),
-                                      stats.data_ptr(), 1 if silu else 0, _ptr(dg), _ptr(db), ws.data_ptr(), _stream())
+                                      stats.data_ptr(), 1 if silu else 0, _ptr(dg), _ptr(db), 1 if out_dtype == BF16 else 0,
+                                      ws.data_ptr(), _stream())
     _lib.check(rc, "imagd_groupnorm_bwd_bf16")
     return dx, dg, db
 

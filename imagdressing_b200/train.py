@@ -320,15 +320,21 @@ class FlatAdamW:
         self.v = torch.zeros(n_own, device=dev, dtype=torch.float32)
         off = 0
         self._spans = []
+        self._gviews = []  # per parameter: its slot of the flat gradient buffer
         with torch.no_grad():
             for p, n in zip(order, sizes):
                 view = self.param[off:off + p.numel()].view(p.shape)
                 view.copy_(p.detach())
                 p.data = view
-                p.grad = self.grad[off:off + p.numel()].view(p.shape)
+                p.grad = None
+                self._gviews.append(self.grad[off:off + p.numel()].view(p.shape))
                 self._spans.append((off, off + n))
                 off += n
             self.master.copy_(self.param[self._own[0]:self._own[1]].float())
+        if not self.shard:  # the master weights double as the fp32 bias / norm-affine arguments of the kernels
+            for p, (a, _b) in zip(order, self._spans):
+                if p.dim() == 1:
+                    ag.register_fp32_shadow(p, self.master[a:a + p.numel()])
         # buckets: contiguous spans of ~bucket_bytes
         per = max(1, bucket_bytes // 2)
         self._buckets, self._bucket_of = [], []
@@ -340,32 +346,46 @@ class FlatAdamW:
                 self._buckets.append([lo, b, cnt])
                 lo, cnt = b, 0
         self._pending = [b[2] for b in self._buckets]
+        self._ready = [[] for _ in self._buckets]  # per bucket: indices of the parameters whose gradient has arrived
         self._handles = []
-        if self._dist:
-            for i, p in enumerate(order):
-                p.register_post_accumulate_grad_hook(self._make_hook(self._bucket_of[i]))
+        # .grad is None before every backward, so autograd hands each gradient over without an accumulation kernel; the
+        # hook of a bucket's last parameter moves the whole bucket into the flat buffer with ONE fused copy and, data
+        # parallel, launches its all-reduce at once
+        for i, p in enumerate(order):
+            p.register_post_accumulate_grad_hook(self._make_hook(i, self._bucket_of[i]))
+        self._order = order
 
-    def _make_hook(self, bucket: int):
+    def _flush_bucket(self, bucket: int):
+        idx = self._ready[bucket]
+        if idx:
+            with torch.no_grad():
+                torch._foreach_copy_([self._gviews[i] for i in idx], [self._order[i].grad for i in idx])
+            self._ready[bucket] = []
+        if self._dist:
+            lo, hi, _ = self._buckets[bucket]
+            self._handles.append(torch.distributed.all_reduce(self.grad[lo:hi], async_op=True))
+
+    def _make_hook(self, index: int, bucket: int):
         def hook(_p):
+            self._ready[bucket].append(index)
             self._pending[bucket] -= 1
             if self._pending[bucket] == 0:
-                lo, hi, _ = self._buckets[bucket]
-                self._handles.append(torch.distributed.all_reduce(self.grad[lo:hi], async_op=True))
+                self._flush_bucket(bucket)
         return hook
 
     def zero_grad(self):
         self.grad.zero_()
+        for p in self.params:
+            p.grad = None
         self._pending = [b[2] for b in self._buckets]
+        self._ready = [[] for _ in self._buckets]
         self._handles = []
 
     def reduce_remaining(self):
-        """Buckets whose parameters did not all receive a gradient this step (unused parameters) are reduced here."""
-        if not self._dist:
-            return
+        """Buckets whose parameters did not all receive a gradient this step (unused parameters) are completed here."""
         for i, n in enumerate(self._pending):
             if n > 0:
-                lo, hi, _ = self._buckets[i]
-                self._handles.append(torch.distributed.all_reduce(self.grad[lo:hi], async_op=True))
+                self._flush_bucket(i)
                 self._pending[i] = 0
         for h in self._handles:
             h.wait()

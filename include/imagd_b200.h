@@ -267,6 +267,9 @@ int imagd_attention_bwd_bf16(const void* q, int64_t q_ld, const void* d_out, int
  * dgrad / wgrad GEMMs (dX = dY W, dW = dY^T X) for imagd_gemm_bf16. */
 int imagd_transpose_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int cols, int rows_pad,
                          imagd_stream stream);
+/* 3x3 conv weight layouts: mode 0 packs [Cout, Cin, 3, 3] (diffusers) into tap-major [Cout, 9*Cin] (pack_conv3x3 of the
+ * trainable garment UNet, every step); mode 1 is the inverse, applied to the packed weight gradient. */
+int imagd_conv_weight_layout_bf16(const void* src, void* dst, int Cout, int Cin, int mode, imagd_stream stream);
 /* Transposed im2col of a stride-1 pad-1 3x3 conv input: out[tap*C + c, p] = x[n, y+ky-1, x+kx-1, c], p = (n*H + y)*W + x,
  * zero for p >= NB*H*W; out: [9*C, ldo]. The B operand of the conv weight-gradient GEMM dW[Cout, 9 Cin] = dY^T col^T. */
 int imagd_im2col3x3_t_bf16(const void* x, void* out, int64_t ldo, int NB, int H, int W, int C, imagd_stream stream);
@@ -275,13 +278,14 @@ int imagd_col2im3x3_s2_bf16(const void* dcol, void* dx, int NB, int H, int W, in
 /* Adjoint of imagd_upsample2x_bf16: dy [NB, 2H, 2W, C] -> dx [NB, H, W, C] (sum of each 2x2 block). */
 int imagd_downsum2x_bf16(const void* dy, void* dx, int NB, int H, int W, int C, imagd_stream stream);
 /* out[g, c] = sum over the rows of group g of x[r, c] (fp32; bias gradients: groups = 1; ResnetBlock2D time-embedding
- * gradients: one group per sample). Fixed-order two-stage reduction; ws >= imagd_colreduce_ws_bytes. */
+ * gradients: one group per sample). out: fp32, or bf16 when out_bf16 != 0 (a parameter gradient in the parameter's dtype).
+ * Fixed-order two-stage reduction; ws >= imagd_colreduce_ws_bytes. */
 int64_t imagd_colreduce_ws_bytes(int rows_per_group, int groups, int C);
-int imagd_colsum_bf16(const void* x, int64_t ldx, int rows_per_group, int groups, int C, float* out, void* ws,
+int imagd_colsum_bf16(const void* x, int64_t ldx, int rows_per_group, int groups, int C, void* out, int out_bf16, void* ws,
                       imagd_stream stream);
-/* LayerNorm backward: dx, and (dgamma non-NULL) dgamma / dbeta [C] fp32. rowstat: [rows, 2] fp32 scratch (mean, rstd). */
+/* LayerNorm backward: dx, and (dgamma non-NULL) dgamma / dbeta [C] (fp32, or bf16 when out_bf16 != 0). rowstat: [rows, 2] fp32 scratch (mean, rstd). */
 int imagd_layernorm_bwd_bf16(const void* x, int64_t ldx, const void* dy, int64_t lddy, void* dx, int64_t lddx, int rows, int C,
-                             const float* gamma, float eps, float* dgamma, float* dbeta, float* rowstat, void* ws,
+                             const float* gamma, float eps, void* dgamma, void* dbeta, int out_bf16, float* rowstat, void* ws,
                              imagd_stream stream);
 /* imagd_groupnorm_bf16 that also writes {mean, rstd} of every (sample, group) to stats_out [NB, groups, 2] fp32 (may be NULL):
  * the training-mode forward; the backward reuses the statistics instead of recomputing them. */
@@ -289,11 +293,11 @@ int imagd_groupnorm_stats_bf16(const void* x, int64_t ldx, void* y, int64_t ldy,
                                const float* gamma, const float* beta, float eps, int fuse_silu, void* ws, float* stats_out,
                                imagd_stream stream);
 /* GroupNorm (+SiLU) backward over contiguous [NB, HW, C] given the forward statistics fwd_stats [NB, groups, 2]: dx, and
- * (dgamma non-NULL) dgamma / dbeta [C] fp32. Three coalesced passes (per-chunk channel partials, fixed-order fold, apply). */
+ * (dgamma non-NULL) dgamma / dbeta [C] (fp32, or bf16 when out_bf16 != 0). Three coalesced passes (per-chunk channel partials, fixed-order fold, apply). */
 int64_t imagd_groupnorm_bwd_ws_bytes(int NB, int HW, int C, int groups);
 int imagd_groupnorm_bwd_bf16(const void* x, const void* dy, void* dx, int NB, int HW, int C, int groups, const float* gamma,
-                             const float* beta, const float* fwd_stats, int fuse_silu, float* dgamma, float* dbeta, void* ws,
-                             imagd_stream stream);
+                             const float* beta, const float* fwd_stats, int fuse_silu, void* dgamma, void* dbeta, int out_bf16,
+                             void* ws, imagd_stream stream);
 /* Elementwise activation (mode IMAGD_ACT_SILU / IMAGD_ACT_GELU): dy NULL: y = act(x); else y = dy * act'(x). */
 int imagd_act_bf16(const void* x, const void* dy, void* y, int64_t n, int mode, imagd_stream stream);
 /* GEGLU on an un-fused projection h = [value | gate], [M, 2F]: dout NULL: out [M, F] = value * gelu(gate);

@@ -306,12 +306,23 @@ def attention_bwd(q, d_out, B, Lq, heads, head_dim, s0, s1, saved, *, sm_scale=N
             dq[rows, :C] = (scale * dq_acc).transpose(0, 1).reshape(Lq, C).to(BF)
 
 
-def transpose(x, pad_to=8):
+def transpose(x, pad_to=8, out=None):
     rows, cols = x.shape
+    if out is not None:
+        out.copy_(x.t())
+        return out
     rp = (rows + pad_to - 1) // pad_to * pad_to
     out = torch.zeros(cols, rp, dtype=BF)
     out[:, :rows] = x.t()
     return out
+
+
+def conv_weight_layout(w, mode):
+    if mode == 0:
+        co, ci = w.shape[:2]
+        return w.permute(0, 2, 3, 1).reshape(co, 9 * ci).contiguous()
+    co, ci = w.shape[0], w.shape[1] // 9
+    return w.view(co, 3, 3, ci).permute(0, 3, 1, 2).contiguous()
 
 
 def im2col3x3_t(x):
@@ -335,13 +346,13 @@ def downsum2x(dy):
     return dy.float().view(NB, H2 // 2, 2, W2 // 2, 2, C).sum((2, 4)).to(BF)
 
 
-def colsum(x, rows_per_group=None):
+def colsum(x, rows_per_group=None, out_dtype=torch.float32):
     x2 = x.reshape(-1, x.shape[-1]).float()
     rpg = x2.shape[0] if rows_per_group is None else rows_per_group
-    return x2.view(-1, rpg, x2.shape[1]).sum(1)
+    return x2.view(-1, rpg, x2.shape[1]).sum(1).to(out_dtype)
 
 
-def layernorm_bwd(x, dy, gamma, eps, need_affine):
+def layernorm_bwd(x, dy, gamma, eps, need_affine, out_dtype=torch.float32):
     xf, g = x.float(), dy.float() * (gamma.float() if gamma is not None else 1.0)
     mean = xf.mean(-1, keepdim=True)
     rstd = torch.rsqrt(xf.var(-1, unbiased=False, keepdim=True) + eps)
@@ -350,7 +361,7 @@ def layernorm_bwd(x, dy, gamma, eps, need_affine):
     C = x.shape[-1]
     if not need_affine:
         return dx.to(BF), None, None
-    return dx.to(BF), (dy.float() * xh).reshape(-1, C).sum(0), dy.float().reshape(-1, C).sum(0)
+    return dx.to(BF), (dy.float() * xh).reshape(-1, C).sum(0).to(out_dtype), dy.float().reshape(-1, C).sum(0).to(out_dtype)
 
 
 def _dsilu(z):
@@ -358,7 +369,7 @@ def _dsilu(z):
     return s * (1 + z * (1 - s))
 
 
-def groupnorm_bwd(x, dy, gamma, beta, groups, stats, silu, need_affine):
+def groupnorm_bwd(x, dy, gamma, beta, groups, stats, silu, need_affine, out_dtype=torch.float32):
     NB, C = x.shape[0], x.shape[-1]
     xf = x.float().reshape(NB, -1, groups, C // groups)
     mean = stats[:, :, 0].reshape(NB, 1, groups, 1)
@@ -373,7 +384,7 @@ def groupnorm_bwd(x, dy, gamma, beta, groups, stats, silu, need_affine):
     dx = dx.reshape(x.shape).to(BF)
     if not need_affine:
         return dx, None, None
-    return dx, (dz * xh).sum((0, 1)), dz.sum((0, 1))
+    return dx, (dz * xh).sum((0, 1)).to(out_dtype), dz.sum((0, 1)).to(out_dtype)
 
 
 def _dgelu(x):
@@ -409,7 +420,7 @@ def adamw_step(master, param, grad, m, v, *, lr, beta1, beta2, eps, weight_decay
     param.copy_(master.to(BF))
 
 
-TRAIN_OPS = ("attention_train", "attention_bwd", "transpose", "im2col3x3_t", "col2im3x3_s2", "downsum2x", "colsum",
+TRAIN_OPS = ("attention_train", "attention_bwd", "transpose", "conv_weight_layout", "im2col3x3_t", "col2im3x3_s2", "downsum2x", "colsum",
              "layernorm_bwd", "groupnorm_bwd", "act", "geglu", "mse_loss_grad", "adamw_step")
 
 

@@ -138,6 +138,17 @@ def test_layout_kernels(cuda_device):
     xs = rnd((100, 400), dev, 2)[:, 64:192]  # column slice (row stride 400)
     assert torch.equal(ops.transpose(xs)[:, :100], xs.t())
 
+    big = rnd((1000, 328), dev, 21)                      # ragged in both directions, 16-byte-aligned strides
+    assert torch.equal(ops.transpose(big)[:, :1000], big.t())
+    w = rnd((96, 64, 3, 3), dev, 22)
+    wp = ops.conv_weight_layout(w, 0)
+    assert torch.equal(wp, w.permute(0, 2, 3, 1).reshape(96, 576))
+    assert torch.equal(ops.conv_weight_layout(wp, 1), w)
+    dst = torch.zeros(64, 9 * 96, device=dev, dtype=BF)
+    for t in range(9):                                   # the dgrad tap flip: strided source and destination views
+        ops.transpose(wp[:, t * 64:(t + 1) * 64], out=dst[:, (8 - t) * 96:(9 - t) * 96])
+    assert torch.equal(dst, wp.view(96, 9, 64).flip(1).permute(2, 1, 0).reshape(64, 864))
+
     a = rnd((2, 6, 10, 64), dev, 3)
     col = ops.im2col3x3_t(a)
     ref = F.unfold(a.float().permute(0, 3, 1, 2), 3, padding=1)          # [NB, C*9, HW], row = c*9 + tap
@@ -169,6 +180,7 @@ def test_layout_kernels(cuda_device):
     big = rnd((4 * 5120, 320), dev, 9)
     assert rel_l2(ops.colsum(big, 5120), big.float().view(4, 5120, 320).sum(1)) < 1e-5
     assert torch.equal(ops.colsum(big), ops.colsum(big))  # fixed-order: bit-reproducible
+    assert torch.equal(ops.colsum(big, None, BF), ops.colsum(big).to(BF))  # bf16 output = the rounded fp32 result
 
 
 @pytest.mark.parametrize("C,HW,groups,silu", [(320, 320, 32, True), (640, 80, 32, True), (1280, 20, 32, False),
