@@ -247,7 +247,20 @@ def train_record(a, dev, rank, local, world, B, h, w, steps, warm):
     xd = synth_train_batch(B, dev, rank, False, lh, lw)
     xh = synth_train_batch(B, dev, rank, True, lh, lw)
 
+    # The eager step is bound by host time (~5 000 launches of Python + ctypes per step); the captured graph is the product
+    # path. IMAGD_TRAIN_GRAPH=0 measures the eager sequence; data parallel the graph contains the bucket all-reduces.
+    graphed = None
+    mode = "eager"
+    if os.environ.get("IMAGD_TRAIN_GRAPH", "1") == "1":
+        try:
+            graphed = train.GraphedTrainStep(sd, sched, opt, xd)
+            mode = "cuda-graph"
+        except Exception as e:  # noqa: BLE001
+            mode = f"eager (graph capture failed: {type(e).__name__}: {e})"[:200]
+
     def step(x):
+        if graphed is not None:
+            return graphed(**x)
         return train.train_step(sd, sched, optimizer=opt, **x)
 
     def step_e2e():
@@ -280,7 +293,7 @@ def train_record(a, dev, rank, local, world, B, h, w, steps, warm):
     ms_e2e = timed(step_e2e, steps)
     _, tf_burst, tf_sus, _ = peaks()
     sps = world * B * steps / (ms * 1e-3)
-    rec = {"workload": "train", "micro_batch_per_gpu": B, "global_batch": world * B, "height": h, "width": w,
+    rec = {"workload": "train", "step_mode": mode, "micro_batch_per_gpu": B, "global_batch": world * B, "height": h, "width": w,
            "samples_per_s": round(sps, 4), "ms_per_step": round(ms / steps, 2), "steps": steps, "warmup": max(warm, 1),
            "e2e_samples_per_s": round(world * B * steps / (ms_e2e * 1e-3), 4),
            "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in xh.values()), "d2h_bytes_per_step": 4,

@@ -30,44 +30,35 @@ _frozen_cache = {}
 
 
 def _cached(kind: str, w: torch.Tensor, frozen: bool, build):
-    """Derived operands of FROZEN weights (the denoising UNet: transposed / flipped copies for dgrad) are built once."""
+    """Derived operands of FROZEN weights (the denoising UNet: transposed / flipped copies for dgrad, fp32 biases) are built
+    once. Keyed by address + in-place version; every entry also HOLDS the source's storage, so the address cannot be recycled
+    for another tensor while the entry lives (saved tensors reach backward() as new Python objects, identity is no key).
+    clear_cache() drops everything (models deleted, checkpoints loaded)."""
     if not frozen:
         return build()
-    key = (kind, w.data_ptr(), w._version, tuple(w.shape))
+    key = (kind, w.data_ptr(), w._version, tuple(w.shape), tuple(w.stride()))
     hit = _frozen_cache.get(key)
     if hit is None:
-        hit = _frozen_cache[key] = build()
-    return hit
+        hit = _frozen_cache[key] = (build(), w.untyped_storage())
+    return hit[0]
 
 
 def clear_cache():
     _frozen_cache.clear()
-    _fp32_shadow.clear()
 
 
 def _bf(t: torch.Tensor) -> torch.Tensor:
     return t if t.dtype == BF16 else t.to(BF16)
 
 
-_fp32_shadow = {}
-
-
-def register_fp32_shadow(param: torch.Tensor, shadow: torch.Tensor) -> None:
-    """`shadow` is an always-current fp32 copy of `param` (the optimizer's master weights): the kernels' fp32 bias / affine
-    arguments then need no per-call conversion launch."""
-    _fp32_shadow[(param.data_ptr(), tuple(param.shape))] = shadow
-
-
 def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
-    """fp32 contiguous view of a bias / norm parameter: itself, the optimizer's master copy, a cached copy (frozen
-    parameters), or a conversion."""
+    """fp32 contiguous copy of a bias / norm parameter for the kernels' fp32 arguments: itself, a cached conversion (frozen
+    parameters), or a conversion. (The optimizer's fp32 master weights are deliberately NOT used here: the model the
+    reference trains in bf16 mode sees the bf16-rounded bias, and so does every path of this repo.)"""
     if t is None:
         return None
     if t.dtype == torch.float32 and t.is_contiguous():
         return t.detach()
-    hit = _fp32_shadow.get((t.data_ptr(), tuple(t.shape)))
-    if hit is not None:
-        return hit
     if not t.requires_grad:
         return _cached("f32", t, True, lambda: t.detach().float().contiguous())
     return t.detach().float().contiguous()

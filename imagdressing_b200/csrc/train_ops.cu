@@ -605,6 +605,27 @@ __global__ void adamw_kernel(float* __restrict__ master, __nv_bfloat16* __restri
     param[i] = __float2bfloat16(w);
 }
 
+// The same with the step-dependent scalars in DEVICE memory — hyper = {lr, weight_decay, step (1-based, as float), grad_scale} —
+// so that a captured CUDA graph of the whole training step replays with a moving step count and learning-rate schedule.
+__global__ void adamw_dev_kernel(float* __restrict__ master, __nv_bfloat16* __restrict__ param,
+                                 const __nv_bfloat16* __restrict__ grad, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                 float b1, float b2, float eps, const float* __restrict__ hyper) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float lr = hyper[0], wd = hyper[1], t = hyper[2], gscale = hyper[3];
+    const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+    const float g = __bfloat162float(grad[i]) * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * g;
+    const float vi = b2 * v[i] + (1.f - b2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    float w = master[i];
+    w -= lr * wd * w;
+    w -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    master[i] = w;
+    param[i] = __float2bfloat16(w);
+}
+
 static inline unsigned blocks_for(int64_t n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
 
 }  // namespace imagd
@@ -788,5 +809,13 @@ extern "C" int imagd_adamw_step(float* master, void* param, const void* grad, fl
     adamw_kernel<<<blocks_for(n, 256), 256, 0, ST(stream)>>>(master, BFW(param), BF(grad), m, v, n, lr, beta1, beta2, eps,
                                                             weight_decay, bc1, bc2, grad_scale);
     IMAGD_LAUNCH_CHECK("adamw_kernel");
+    return IMAGD_OK;
+}
+
+extern "C" int imagd_adamw_step_dev(float* master, void* param, const void* grad, float* m, float* v, int64_t n, float beta1,
+                                    float beta2, float eps, const float* hyper, imagd_stream stream) {
+    IMAGD_CHECK_ARG(master && param && grad && m && v && hyper && n > 0, "adamw_dev: bad argument");
+    adamw_dev_kernel<<<blocks_for(n, 256), 256, 0, ST(stream)>>>(master, BFW(param), BF(grad), m, v, n, beta1, beta2, eps, hyper);
+    IMAGD_LAUNCH_CHECK("adamw_dev_kernel");
     return IMAGD_OK;
 }

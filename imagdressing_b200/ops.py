@@ -630,3 +630,15 @@ def adamw_step(master: torch.Tensor, param: torch.Tensor, grad: torch.Tensor, m:
     _lib.check(lib.imagd_adamw_step(master.data_ptr(), param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), n, float(lr),
                                     float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale),
                                     _stream()), "imagd_adamw_step")
+
+
+def adamw_step_dev(master: torch.Tensor, param: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: torch.Tensor,
+                   hyper: torch.Tensor, *, beta1: float, beta2: float, eps: float) -> None:
+    """adamw_step with {lr, weight_decay, step, grad_scale} in the fp32 device tensor `hyper` (CUDA-graph replayable)."""
+    lib = _lib.load()
+    n = master.numel()
+    assert master.dtype == torch.float32 and m.dtype == torch.float32 and v.dtype == torch.float32
+    assert param.dtype == BF16 and grad.dtype == BF16 and param.numel() == n and grad.numel() == n
+    assert hyper.dtype == torch.float32 and hyper.numel() >= 4 and hyper.is_contiguous()
+    _lib.check(lib.imagd_adamw_step_dev(master.data_ptr(), param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), n,
+                                        float(beta1), float(beta2), float(eps), hyper.data_ptr(), _stream()), "imagd_adamw_step_dev")

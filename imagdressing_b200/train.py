@@ -296,7 +296,7 @@ class FlatAdamW:
         dev = self.params[0].device
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.t = 0
-        self._step_fn = step_fn or ops.adamw_step
+        self._step_fn = step_fn  # test hook with the host-scalar signature of ops.adamw_step; None = the device-scalar kernel
         # backward produces gradients roughly in reverse registration order: lay the buffer out reversed so that buckets
         # complete front to back
         order = list(reversed(self.params))
@@ -318,6 +318,9 @@ class FlatAdamW:
         self.master = torch.zeros(n_own, device=dev, dtype=torch.float32)
         self.m = torch.zeros(n_own, device=dev, dtype=torch.float32)
         self.v = torch.zeros(n_own, device=dev, dtype=torch.float32)
+        # {lr, weight_decay, step, grad_scale} in device memory: what the update kernel reads, so a captured CUDA graph of the
+        # step replays with a moving step count / learning-rate schedule (set_lr rewrites it between replays)
+        self.hyper = torch.tensor([lr, weight_decay, 0.0, 1.0 / world], device=dev, dtype=torch.float32)
         off = 0
         self._spans = []
         self._gviews = []  # per parameter: its slot of the flat gradient buffer
@@ -331,10 +334,6 @@ class FlatAdamW:
                 self._spans.append((off, off + n))
                 off += n
             self.master.copy_(self.param[self._own[0]:self._own[1]].float())
-        if not self.shard:  # the master weights double as the fp32 bias / norm-affine arguments of the kernels
-            for p, (a, _b) in zip(order, self._spans):
-                if p.dim() == 1:
-                    ag.register_fp32_shadow(p, self.master[a:a + p.numel()])
         # buckets: contiguous spans of ~bucket_bytes
         per = max(1, bucket_bytes // 2)
         self._buckets, self._bucket_of = [], []
@@ -396,14 +395,34 @@ class FlatAdamW:
         self.t += 1
         world = torch.distributed.get_world_size() if self._dist else 1
         lo, hi = self._own
-        self._step_fn(self.master, self.param[lo:hi], self.grad[lo:hi], self.m, self.v, lr=self.lr, beta1=self.betas[0],
-                      beta2=self.betas[1], eps=self.eps, weight_decay=self.wd, step=self.t, grad_scale=1.0 / world)
+        self.hyper[2:3].add_(1.0)  # device-side step count (a kernel, so it is part of a captured graph)
+        if self._step_fn is not None:
+            self._step_fn(self.master, self.param[lo:hi], self.grad[lo:hi], self.m, self.v, lr=self.lr, beta1=self.betas[0],
+                          beta2=self.betas[1], eps=self.eps, weight_decay=self.wd, step=self.t, grad_scale=1.0 / world)
+        else:
+            ops.adamw_step_dev(self.master, self.param[lo:hi], self.grad[lo:hi], self.m, self.v, self.hyper,
+                               beta1=self.betas[0], beta2=self.betas[1], eps=self.eps)
         if self.shard:  # every rank updated its own slice: gather the bf16 working copy
             torch.distributed.all_gather_into_tensor(self.param, self.param[lo:hi].clone())
         # the kernel wrote through raw pointers: bump the version counters so that weight-derived caches keyed on
         # (data_ptr, _version) — processors._ver, autograd._cached — see the update
         torch.autograd.graph.increment_version([self.param, *self.params])
 
+
+    def set_lr(self, lr: float, weight_decay: Optional[float] = None) -> None:
+        """Learning-rate schedule hook: rewrites the device-side scalars (outside any graph capture)."""
+        self.lr = float(lr)
+        self.hyper[0:1].fill_(self.lr)
+        if weight_decay is not None:
+            self.wd = float(weight_decay)
+            self.hyper[1:2].fill_(self.wd)
+
+    def reset_state(self) -> None:
+        """Moments and step count back to zero (after the warm-up steps of a graph capture)."""
+        self.m.zero_()
+        self.v.zero_()
+        self.hyper[2:3].zero_()
+        self.t = 0
 
     def state_dict(self) -> Dict[str, object]:
         return {"t": self.t, "own": self._own, "master": self.master, "m": self.m, "v": self.v,
@@ -413,6 +432,7 @@ class FlatAdamW:
         if tuple(sd["own"]) != tuple(self._own):
             raise ValueError(f"optimizer shard {tuple(sd['own'])} does not match this rank's {self._own}")
         self.t = int(sd["t"])
+        self.hyper[2:3].fill_(float(self.t))
         for name in ("master", "m", "v"):
             getattr(self, name).copy_(sd[name])
         with torch.no_grad():
@@ -507,3 +527,54 @@ def train_step(sd_model: SDModel, scheduler, latents, ref_latents, clip_image_em
     if optimizer is not None:
         optimizer.step()                                                                                           # :604
     return loss.detach()
+
+
+class GraphedTrainStep:
+    """The whole micro-step — optimizer.zero_grad, SDModel forward, MSE, backward (with its gradient hand-over copies and, data
+    parallel, the bucket all-reduces), AdamW — captured ONCE as a CUDA graph and replayed per batch: ~5 000 launches per step
+    stop costing host time (the eager step is bound by Python + launch overhead, not by the GPU). Inputs live in static
+    buffers; the step count and learning rate are device scalars the update kernel reads (FlatAdamW.hyper).
+
+    Warm-up steps (required before capture: lazily built caches, workspace growth, split-K scratch) run with lr = 0 and the
+    optimizer state is reset afterwards, so training starts from the given weights at step 1."""
+
+    def __init__(self, sd_model: SDModel, scheduler, optimizer: FlatAdamW, example: Dict[str, torch.Tensor], warmup: int = 3):
+        self.sd, self.sched, self.opt = sd_model, scheduler, optimizer
+        self.static = {k: v.detach().clone() for k, v in example.items()}
+        self.static["noisy"] = scheduler.add_noise(example["latents"], example["noise"], example["timesteps"]).detach().clone()
+        lr = optimizer.lr
+        optimizer.set_lr(0.0)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        optimizer.zero_grad()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+        torch.cuda.synchronize()
+        optimizer.reset_state()
+        optimizer.set_lr(lr)
+
+    def _body(self) -> torch.Tensor:
+        st = self.static
+        self.opt.zero_grad()
+        pred = self.sd(st["encoder_hidden_states"], st["noisy"], st["ref_latents"], st["clip_image_embeddings"], st["timesteps"])
+        loss = ag.mse_loss(pred.float(), st["noise"].float())
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    def __call__(self, latents, ref_latents, clip_image_embeddings, encoder_hidden_states, noise, timesteps) -> torch.Tensor:
+        st = self.static
+        st["noisy"].copy_(self.sched.add_noise(latents, noise, timesteps))  # train.py:545 (outside the graph: table lookup)
+        for k, v in (("ref_latents", ref_latents), ("clip_image_embeddings", clip_image_embeddings),
+                     ("encoder_hidden_states", encoder_hidden_states), ("noise", noise), ("timesteps", timesteps)):
+            st[k].copy_(v)
+        self.graph.replay()
+        self.opt.t += 1  # (the device-side count advanced inside the graph)
+        torch.autograd.graph.increment_version([self.opt.param, *self.opt.params])
+        return self.loss

@@ -310,6 +310,11 @@ int imagd_mse_loss_grad(const float* pred, const float* target, float* grad, flo
 /* AdamW, decoupled weight decay (train.py:386-398), fp32 master weights + moments, bf16 gradient in, bf16 working copy out. */
 int imagd_adamw_step(float* master, void* param, const void* grad, float* m, float* v, int64_t n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int step, float grad_scale, imagd_stream stream);
+/* The same with the step-dependent scalars read from DEVICE memory: hyper = {lr, weight_decay, step (1-based, as float),
+ * grad_scale}. A CUDA graph of the whole training step (forward, backward, update) then replays with a moving step count and
+ * learning-rate schedule — the host only rewrites these four floats. */
+int imagd_adamw_step_dev(float* master, void* param, const void* grad, float* m, float* v, int64_t n, float beta1, float beta2,
+                         float eps, const float* hyper, imagd_stream stream);
 
 #ifdef __cplusplus
 }

@@ -420,7 +420,12 @@ def adamw_step(master, param, grad, m, v, *, lr, beta1, beta2, eps, weight_decay
     param.copy_(master.to(BF))
 
 
-TRAIN_OPS = ("attention_train", "attention_bwd", "transpose", "conv_weight_layout", "im2col3x3_t", "col2im3x3_s2", "downsum2x", "colsum",
+def adamw_step_dev(master, param, grad, m, v, hyper, *, beta1, beta2, eps):
+    adamw_step(master, param, grad, m, v, lr=float(hyper[0]), beta1=beta1, beta2=beta2, eps=eps, weight_decay=float(hyper[1]),
+               step=int(round(float(hyper[2]))), grad_scale=float(hyper[3]))
+
+
+TRAIN_OPS = ("adamw_step_dev", "attention_train", "attention_bwd", "transpose", "conv_weight_layout", "im2col3x3_t", "col2im3x3_s2", "downsum2x", "colsum",
              "layernorm_bwd", "groupnorm_bwd", "act", "geglu", "mse_loss_grad", "adamw_step")
 
 

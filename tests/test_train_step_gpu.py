@@ -144,3 +144,35 @@ def test_optimizer_step_changes_only_trainable_parameters(cuda_device):
     assert torch.equal(p_unet.conv_in.weight, frozen_before)
     assert not torch.equal(p_ref.conv_in.weight, w_before)
     assert losses[2] < losses[0]
+
+
+def test_graphed_step_equals_eager_step(cuda_device):
+    """GraphedTrainStep (one captured CUDA graph of zero_grad + forward + loss + backward + AdamW) against the eager sequence on
+    the same batches from the same weights: same losses, same parameters after two steps. The warm-up inside the capture runs
+    with lr = 0 and the optimizer state is reset, so both start from identical weights at step 1."""
+    from imagdressing_b200 import train
+    from imagdressing_b200.scheduler import DDIMScheduler
+
+    dev = cuda_device
+    _, (p_unet, p_ref, p_proj, p_ad) = build(dev)
+    sd = train.SDModel(p_unet, p_ref, p_proj, p_ad)
+    params = train.set_trainable(p_unet, p_ref, p_proj, p_ad)
+    opt = train.FlatAdamW(params, lr=2e-5, weight_decay=1e-2)
+    sched = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False)
+    b1, b2 = batch(dev, 2, 16, 16), batch(dev, 2, 16, 16)
+    b2 = {k: (v.flip(0) if k != "timesteps" else torch.tensor([300, 650], device=dev)) for k, v in b2.items()}
+    start = (opt.param.clone(), opt.master.clone())
+    eager = [float(train.train_step(sd, sched, optimizer=opt, **b)) for b in (b1, b2)]
+    after_eager = opt.param.clone()
+    with torch.no_grad():
+        opt.param.copy_(start[0])
+        opt.master.copy_(start[1])
+    opt.reset_state()
+    step = train.GraphedTrainStep(sd, sched, opt, b1)
+    assert torch.equal(opt.param, start[0]) and opt.t == 0  # the capture's warm-up steps left weights and state untouched
+    graphed = [float(step(**b)) for b in (b1, b2)]
+    print("eager losses", eager, "graphed", graphed)
+    assert opt.t == 2
+    for a, g in zip(eager, graphed):
+        assert abs(a - g) <= 1e-5 * abs(a)
+    assert rel(opt.param, after_eager) < 1e-4
