@@ -549,19 +549,28 @@ static int launch_attn_pp(const CUtensorMap* tms, AttnParams p, cudaStream_t str
     if (variant == 1) {
         using C = AttnPP1Cfg<kStages>;
         static const int poly = env_int("IMAGD_ATTN_POLY", IMAGD_ATTN_POLY);  // exponentials per 8 on the FMA pipe
-#define IMAGD_PP1_LAUNCH(P)                                                                                              \
+        static const int pack = env_int("IMAGD_ATTN_PACK", 0);                // bf16 packing of P: 0 F2FP, 1 truncate, 2 round + permute
+#define IMAGD_PP1_LAUNCH(P, K)                                                                                           \
     do {                                                                                                                 \
-        IMAGD_SET_MAX_SMEM((attention_pp1_kernel<HD_MMA, kStages, P>), C::kTotal);                                       \
-        IMAGD_CUDA(launch_pdl(attention_pp1_kernel<HD_MMA, kStages, P>, grid, dim3(576), C::kTotal, stream, tms[0],      \
+        IMAGD_SET_MAX_SMEM((attention_pp1_kernel<HD_MMA, kStages, P, K>), C::kTotal);                                    \
+        IMAGD_CUDA(launch_pdl(attention_pp1_kernel<HD_MMA, kStages, P, K>, grid, dim3(576), C::kTotal, stream, tms[0],   \
                               tms[1], tms[2], tms[3], tms[4], p));                                                       \
         return IMAGD_OK;                                                                                                 \
     } while (0)
+        if (pack == 1) {
+            if (poly == 2) IMAGD_PP1_LAUNCH(2, 1);
+            IMAGD_PP1_LAUNCH(0, 1);
+        }
+        if (pack == 2) {
+            if (poly == 2) IMAGD_PP1_LAUNCH(2, 2);
+            IMAGD_PP1_LAUNCH(0, 2);
+        }
         switch (poly) {
-            case 1: IMAGD_PP1_LAUNCH(1);
-            case 2: IMAGD_PP1_LAUNCH(2);
-            case 3: IMAGD_PP1_LAUNCH(3);
-            case 4: IMAGD_PP1_LAUNCH(4);
-            default: IMAGD_PP1_LAUNCH(0);
+            case 1: IMAGD_PP1_LAUNCH(1, 0);
+            case 2: IMAGD_PP1_LAUNCH(2, 0);
+            case 3: IMAGD_PP1_LAUNCH(3, 0);
+            case 4: IMAGD_PP1_LAUNCH(4, 0);
+            default: IMAGD_PP1_LAUNCH(0, 0);
         }
 #undef IMAGD_PP1_LAUNCH
     }

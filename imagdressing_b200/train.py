@@ -536,7 +536,9 @@ class GraphedTrainStep:
     buffers; the step count and learning rate are device scalars the update kernel reads (FlatAdamW.hyper).
 
     Warm-up steps (required before capture: lazily built caches, workspace growth, split-K scratch) run with lr = 0 and the
-    optimizer state is reset afterwards, so training starts from the given weights at step 1."""
+    optimizer state is reset afterwards, so training starts from the given weights at step 1. Construct it BEFORE any eager
+    backward of the same parameters on the default stream: autograd's gradient accumulators remember the stream they were
+    created on, and one created on the legacy stream cannot take part in a capture (the warm-up here runs on a side stream)."""
 
     def __init__(self, sd_model: SDModel, scheduler, optimizer: FlatAdamW, example: Dict[str, torch.Tensor], warmup: int = 3):
         self.sd, self.sched, self.opt = sd_model, scheduler, optimizer

@@ -162,17 +162,19 @@ def test_graphed_step_equals_eager_step(cuda_device):
     b1, b2 = batch(dev, 2, 16, 16), batch(dev, 2, 16, 16)
     b2 = {k: (v.flip(0) if k != "timesteps" else torch.tensor([300, 650], device=dev)) for k, v in b2.items()}
     start = (opt.param.clone(), opt.master.clone())
-    eager = [float(train.train_step(sd, sched, optimizer=opt, **b)) for b in (b1, b2)]
-    after_eager = opt.param.clone()
+    # the graph first: its capture must precede any eager backward on the default stream (autograd's gradient accumulators
+    # remember the stream they were created on; a legacy-stream accumulator cannot take part in a capture)
+    step = train.GraphedTrainStep(sd, sched, opt, b1)
+    assert torch.equal(opt.param, start[0]) and opt.t == 0  # the capture's warm-up steps left weights and state untouched
+    graphed = [float(step(**b)) for b in (b1, b2)]
+    assert opt.t == 2
+    after_graphed = opt.param.clone()
     with torch.no_grad():
         opt.param.copy_(start[0])
         opt.master.copy_(start[1])
     opt.reset_state()
-    step = train.GraphedTrainStep(sd, sched, opt, b1)
-    assert torch.equal(opt.param, start[0]) and opt.t == 0  # the capture's warm-up steps left weights and state untouched
-    graphed = [float(step(**b)) for b in (b1, b2)]
+    eager = [float(train.train_step(sd, sched, optimizer=opt, **b)) for b in (b1, b2)]
     print("eager losses", eager, "graphed", graphed)
-    assert opt.t == 2
     for a, g in zip(eager, graphed):
         assert abs(a - g) <= 1e-5 * abs(a)
-    assert rel(opt.param, after_eager) < 1e-4
+    assert rel(after_graphed, opt.param) < 1e-4
