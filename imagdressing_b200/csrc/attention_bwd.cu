@@ -48,6 +48,18 @@ struct AttnBwdParams {
 
 constexpr int kBAtom = 128 * 128;  // one [128 rows x 64 bf16] swizzled tile
 
+// fp32 pair -> bf16x2. PACK = 0: cvt.rn.bf16x2.f32 (F2FP, on the XU pipe next to MUFU.EX2); PACK = 2: add half an ulp to the
+// bit patterns, then ONE byte permute picks the two high halves (round-half-up of the magnitude; ALU pipe only). Runtime A/B
+// for the head-dim-40 kernels through IMAGD_BWD_PACK.
+template <int PACK>
+__device__ __forceinline__ uint32_t bwd_pack(float lo, float hi) {
+    if constexpr (PACK == 0) {
+        return pack_bf16x2(lo, hi);
+    } else {
+        return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ dQ kernel
 template <int HD_MMA, int NATOM, int KV_STAGES>
 struct DqCfg {
@@ -63,7 +75,7 @@ struct DqCfg {
     static_assert(256 + HD_MMA <= 512, "dq kernel: TMEM");
 };
 
-template <int HD_MMA, int NATOM, int KV_STAGES>
+template <int HD_MMA, int NATOM, int KV_STAGES, int PACK = 0>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
@@ -255,8 +267,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     }
                     const uint32_t chunk = static_cast<uint32_t>(cc * 4 + g) ^ rx;
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row + chunk * 16),
-                                 "r"(pack_bf16x2(e[0], e[1])), "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])),
-                                 "r"(pack_bf16x2(e[6], e[7]))
+                                 "r"(bwd_pack<PACK>(e[0], e[1])), "r"(bwd_pack<PACK>(e[2], e[3])),
+                                 "r"(bwd_pack<PACK>(e[4], e[5])), "r"(bwd_pack<PACK>(e[6], e[7]))
                                  : "memory");
                 }
             }
@@ -297,7 +309,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------ dK / dV kernel
-template <int HD_MMA, int NATOM, int QB, int STAGES>
+template <int HD_MMA, int NATOM, int QB, int STAGES, int CTAS = 1>
 struct DkvCfg {
     static constexpr int kQAtom = QB * 128;  // one [QB rows x 64 bf16] swizzled tile of Q / dO
     static constexpr int kPAtoms = QB / 64;  // P^T / dS^T: [128 keys x QB] = QB / 64 atoms of [128 x 64]
@@ -314,16 +326,19 @@ struct DkvCfg {
     static constexpr int kAccStride = (HD_MMA + 63) / 64 * 64;
     static constexpr int kTmemDv = 2 * QB;
     static constexpr int kTmemDk = 2 * QB + kAccStride;
-    static_assert(kTotal <= 232448, "dkv kernel: shared memory");
-    static_assert(kTmemDk + HD_MMA <= 512, "dkv kernel: TMEM");
+    static constexpr int kTmemCols = CTAS == 2 ? 256 : 512;  // two co-resident CTAs share the SM's 512 columns
+    static_assert(kTotal * CTAS <= 232448 - (CTAS - 1) * 2048, "dkv kernel: shared memory");
+    static_assert(kTmemDk + HD_MMA <= kTmemCols, "dkv kernel: TMEM");
 };
 
-template <int HD_MMA, int NATOM, int QB, int STAGES>
-__global__ void __launch_bounds__(320, 1)
+// CTAS = 2 (with QB = 64: 256 TMEM columns, ~100 KB of shared memory): two CTAs per SM, so one CTA's exponential phase runs
+// under the other's tensor-core / synchronisation phases — the forward kernel's two-CTAs-per-SM arrangement.
+template <int HD_MMA, int NATOM, int QB, int STAGES, int CTAS = 1, int PACK = 0>
+__global__ void __launch_bounds__(320, CTAS)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                     const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                     const AttnBwdParams p) {
-    using C = DkvCfg<HD_MMA, NATOM, QB, STAGES>;
+    using C = DkvCfg<HD_MMA, NATOM, QB, STAGES, CTAS>;
     constexpr int kQA = C::kQAtom;
     extern __shared__ __align__(1024) uint8_t smem[];
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
@@ -370,7 +385,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         fence_barrier_init();
     }
     if (warp == 9) {
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, C::kTmemCols);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -528,12 +543,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     }
                     const uint32_t chunk = (chunk0 + static_cast<uint32_t>(cc * 4 + g)) ^ rx;
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16),
-                                 "r"(pack_bf16x2(pe[0], pe[1])), "r"(pack_bf16x2(pe[2], pe[3])),
-                                 "r"(pack_bf16x2(pe[4], pe[5])), "r"(pack_bf16x2(pe[6], pe[7]))
+                                 "r"(bwd_pack<PACK>(pe[0], pe[1])), "r"(bwd_pack<PACK>(pe[2], pe[3])),
+                                 "r"(bwd_pack<PACK>(pe[4], pe[5])), "r"(bwd_pack<PACK>(pe[6], pe[7]))
                                  : "memory");
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row + chunk * 16),
-                                 "r"(pack_bf16x2(de[0], de[1])), "r"(pack_bf16x2(de[2], de[3])),
-                                 "r"(pack_bf16x2(de[4], de[5])), "r"(pack_bf16x2(de[6], de[7]))
+                                 "r"(bwd_pack<PACK>(de[0], de[1])), "r"(bwd_pack<PACK>(de[2], de[3])),
+                                 "r"(bwd_pack<PACK>(de[4], de[5])), "r"(bwd_pack<PACK>(de[6], de[7]))
                                  : "memory");
                 }
             }
@@ -576,7 +591,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_base, 512);
+    if (warp == 9) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------ D = w * rowsum(dO o O_s)
@@ -624,24 +639,24 @@ static int make_tmap_rows(CUtensorMap* tm, const void* base, int64_t ld, int hd,
     return make_tmap_bf16(tm, base, 4, dims, strides, box);
 }
 
-template <int HD_MMA, int NATOM, int KV_STAGES>
+template <int HD_MMA, int NATOM, int KV_STAGES, int PACK = 0>
 static int launch_dq(const CUtensorMap* tms, const AttnBwdParams& p, cudaStream_t stream) {
     using C = DqCfg<HD_MMA, NATOM, KV_STAGES>;
-    IMAGD_SET_MAX_SMEM((attn_bwd_dq_kernel<HD_MMA, NATOM, KV_STAGES>), C::kTotal);
+    IMAGD_SET_MAX_SMEM((attn_bwd_dq_kernel<HD_MMA, NATOM, KV_STAGES, PACK>), C::kTotal);
     dim3 grid((p.Lq + 127) / 128, p.heads, p.B);
-    attn_bwd_dq_kernel<HD_MMA, NATOM, KV_STAGES><<<grid, 320, C::kTotal, stream>>>(tms[0], tms[1], tms[2], tms[3], tms[4],
-                                                                                   tms[5], p);
+    attn_bwd_dq_kernel<HD_MMA, NATOM, KV_STAGES, PACK><<<grid, 320, C::kTotal, stream>>>(tms[0], tms[1], tms[2], tms[3], tms[4],
+                                                                                         tms[5], p);
     IMAGD_LAUNCH_CHECK("attn_bwd_dq_kernel");
     return IMAGD_OK;
 }
 
-template <int HD_MMA, int NATOM, int QB, int STAGES>
+template <int HD_MMA, int NATOM, int QB, int STAGES, int CTAS = 1, int PACK = 0>
 static int launch_dkv(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& tk, const CUtensorMap& tv,
                       const AttnBwdParams& p, int len, cudaStream_t stream) {
-    using C = DkvCfg<HD_MMA, NATOM, QB, STAGES>;
-    IMAGD_SET_MAX_SMEM((attn_bwd_dkv_kernel<HD_MMA, NATOM, QB, STAGES>), C::kTotal);
+    using C = DkvCfg<HD_MMA, NATOM, QB, STAGES, CTAS>;
+    IMAGD_SET_MAX_SMEM((attn_bwd_dkv_kernel<HD_MMA, NATOM, QB, STAGES, CTAS, PACK>), C::kTotal);
     dim3 grid((len + 127) / 128, p.heads, p.B);
-    attn_bwd_dkv_kernel<HD_MMA, NATOM, QB, STAGES><<<grid, 320, C::kTotal, stream>>>(tq, tdo, tk, tv, p);
+    attn_bwd_dkv_kernel<HD_MMA, NATOM, QB, STAGES, CTAS, PACK><<<grid, 320, C::kTotal, stream>>>(tq, tdo, tk, tv, p);
     IMAGD_LAUNCH_CHECK("attn_bwd_dkv_kernel");
     return IMAGD_OK;
 }
@@ -721,8 +736,9 @@ extern "C" int imagd_attention_bwd_bf16(const void* q, int64_t q_ld, const void*
             tms[4] = tms[2];
             tms[5] = tms[3];
         }
+        static const int bwd_pack_mode = [] { const char* e = getenv("IMAGD_BWD_PACK"); return e ? atoi(e) : 0; }();
         switch (head_dim) {
-            case 40: rc = launch_dq<48, 1, 2>(tms, p, st); break;
+            case 40: rc = bwd_pack_mode == 2 ? launch_dq<48, 1, 2, 2>(tms, p, st) : launch_dq<48, 1, 2>(tms, p, st); break;
             case 64: rc = launch_dq<64, 1, 2>(tms, p, st); break;
             case 80: rc = launch_dq<80, 2, 2>(tms, p, st); break;
             default: rc = launch_dq<160, 3, 1>(tms, p, st); break;
@@ -734,7 +750,10 @@ extern "C" int imagd_attention_bwd_bf16(const void* q, int64_t q_ld, const void*
         void* dv = s ? dv1 : dv0;
         if (dk == nullptr) continue;
         const imagd_kv_stream* ks = s ? s1 : s0;
-        const int qb = head_dim <= 64 ? 128 : 64;
+        // head_dim 40 A/B switches: IMAGD_BWD_DKV2=1 -> 64-query blocks, two CTAs per SM; IMAGD_BWD_PACK=2 -> permute packing
+        static const int dkv2 = [] { const char* e = getenv("IMAGD_BWD_DKV2"); return e ? atoi(e) : 0; }();
+        static const int pack_mode = [] { const char* e = getenv("IMAGD_BWD_PACK"); return e ? atoi(e) : 0; }();
+        const int qb = (head_dim <= 64 && !(head_dim == 40 && dkv2)) ? 128 : 64;
         CUtensorMap tq, tdo, tk, tv;
         int rc = make_tmap_rows(&tq, q, q_ld, head_dim, heads, Lq, B, 0, qb);
         if (rc != IMAGD_OK) return rc;
@@ -750,7 +769,14 @@ extern "C" int imagd_attention_bwd_bf16(const void* q, int64_t q_ld, const void*
         p.dkv_ld = s ? dkv1_ld : dkv0_ld;
         p.kv_sample_rows = ks->sample_rows > 0 ? ks->sample_rows : ks->len;
         switch (head_dim) {
-            case 40: rc = launch_dkv<48, 1, 128, 2>(tq, tdo, tk, tv, p, ks->len, st); break;
+            case 40:
+                if (dkv2)
+                    rc = pack_mode == 2 ? launch_dkv<48, 1, 64, 2, 2, 2>(tq, tdo, tk, tv, p, ks->len, st)
+                                        : launch_dkv<48, 1, 64, 2, 2, 0>(tq, tdo, tk, tv, p, ks->len, st);
+                else
+                    rc = pack_mode == 2 ? launch_dkv<48, 1, 128, 2, 1, 2>(tq, tdo, tk, tv, p, ks->len, st)
+                                        : launch_dkv<48, 1, 128, 2>(tq, tdo, tk, tv, p, ks->len, st);
+                break;
             case 64: rc = launch_dkv<64, 1, 128, 2>(tq, tdo, tk, tv, p, ks->len, st); break;
             case 80: rc = launch_dkv<80, 2, 64, 2>(tq, tdo, tk, tv, p, ks->len, st); break;
             default: rc = launch_dkv<160, 3, 64, 2>(tq, tdo, tk, tv, p, ks->len, st); break;

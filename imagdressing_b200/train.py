@@ -554,9 +554,13 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         optimizer.zero_grad()
+        from . import _lib
+
         self.graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count
         with torch.cuda.graph(self.graph):
             self.loss = self._body()
+        self.launches_per_step = _lib.launch_count - before  # library kernels inside the graph (replays add them to the count)
         torch.cuda.synchronize()
         optimizer.reset_state()
         optimizer.set_lr(lr)
@@ -577,6 +581,9 @@ class GraphedTrainStep:
                      ("encoder_hidden_states", encoder_hidden_states), ("noise", noise), ("timesteps", timesteps)):
             st[k].copy_(v)
         self.graph.replay()
+        from . import _lib
+
+        _lib.launch_count += self.launches_per_step
         self.opt.t += 1  # (the device-side count advanced inside the graph)
         torch.autograd.graph.increment_version([self.opt.param, *self.opt.params])
         return self.loss
