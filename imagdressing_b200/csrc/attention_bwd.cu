@@ -751,7 +751,9 @@ extern "C" int imagd_attention_bwd_bf16(const void* q, int64_t q_ld, const void*
         if (dk == nullptr) continue;
         const imagd_kv_stream* ks = s ? s1 : s0;
         // head_dim 40 A/B switches: IMAGD_BWD_DKV2=1 -> 64-query blocks, two CTAs per SM; IMAGD_BWD_PACK=2 -> permute packing
-        static const int dkv2 = [] { const char* e = getenv("IMAGD_BWD_DKV2"); return e ? atoi(e) : 0; }();
+        // measured (profiles/r02_call16_attention_bwd_ab.txt, level-0 two-stream call, micro-batch 4): dK/dV kernel 785 -> 712 us
+        // with two CTAs per SM (default); the packing mode makes no difference (785 / 795, 712 / 713)
+        static const int dkv2 = [] { const char* e = getenv("IMAGD_BWD_DKV2"); return e ? atoi(e) : 1; }();
         static const int pack_mode = [] { const char* e = getenv("IMAGD_BWD_PACK"); return e ? atoi(e) : 0; }();
         const int qb = (head_dim <= 64 && !(head_dim == 40 && dkv2)) ? 128 : 64;
         CUtensorMap tq, tdo, tk, tv;
