@@ -129,13 +129,8 @@ def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
 
 
 def _flip_taps(wp: torch.Tensor, cin: int) -> torch.Tensor:
-    """Packed forward weight [Cout, 9*Cin] -> the dgrad weight [Cin, 9*Cout]: W'[ci, 8 - tap, co] = W[co, tap, ci] — nine
-    strided [Cout, Cin] -> [Cin, Cout] transposes (one per tap) on the transpose kernel."""
-    co = wp.shape[0]
-    out = torch.empty(cin, 9 * co, device=wp.device, dtype=wp.dtype)
-    for t in range(9):
-        ops.transpose(wp[:, t * cin:(t + 1) * cin], out=out[:, (8 - t) * co:(9 - t) * co])
-    return out
+    """Packed forward weight [Cout, 9*Cin] -> the dgrad weight [Cin, 9*Cout]: W'[ci, 8 - tap, co] = W[co, tap, ci]."""
+    return ops.conv_weight_flip(wp.contiguous(), cin)
 
 
 class Conv3x3(Function):

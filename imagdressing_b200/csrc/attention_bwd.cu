@@ -737,9 +737,16 @@ extern "C" int imagd_attention_bwd_bf16(const void* q, int64_t q_ld, const void*
             tms[5] = tms[3];
         }
         static const int bwd_pack_mode = [] { const char* e = getenv("IMAGD_BWD_PACK"); return e ? atoi(e) : 0; }();
+        // K/V ring depth of the one-CTA-per-SM dQ kernel (head_dim 40 / 64): with two stages only ONE key block is in flight
+        // ahead of the tensor core and the ~1 us L2 -> shared latency of every block is exposed (measured ~4000 clk per
+        // block against 1024 clk of exponentials); IMAGD_BWD_DQ_STAGES=2 restores the shallow ring for A/B.
+        static const int dq_stages = [] { const char* e = getenv("IMAGD_BWD_DQ_STAGES"); return e ? atoi(e) : 4; }();
         switch (head_dim) {
-            case 40: rc = bwd_pack_mode == 2 ? launch_dq<48, 1, 2, 2>(tms, p, st) : launch_dq<48, 1, 2>(tms, p, st); break;
-            case 64: rc = launch_dq<64, 1, 2>(tms, p, st); break;
+            case 40:
+                if (dq_stages >= 4) rc = launch_dq<48, 1, 4>(tms, p, st);
+                else rc = bwd_pack_mode == 2 ? launch_dq<48, 1, 2, 2>(tms, p, st) : launch_dq<48, 1, 2>(tms, p, st);
+                break;
+            case 64: rc = dq_stages >= 4 ? launch_dq<64, 1, 4>(tms, p, st) : launch_dq<64, 1, 2>(tms, p, st); break;
             case 80: rc = launch_dq<80, 2, 2>(tms, p, st); break;
             default: rc = launch_dq<160, 3, 1>(tms, p, st); break;
         }
@@ -755,7 +762,7 @@ extern "C" int imagd_attention_bwd_bf16(const void* q, int64_t q_ld, const void*
         // with two CTAs per SM (default); the packing mode makes no difference (785 / 795, 712 / 713)
         static const int dkv2 = [] { const char* e = getenv("IMAGD_BWD_DKV2"); return e ? atoi(e) : 1; }();
         static const int pack_mode = [] { const char* e = getenv("IMAGD_BWD_PACK"); return e ? atoi(e) : 0; }();
-        const int qb = (head_dim <= 64 && !(head_dim == 40 && dkv2)) ? 128 : 64;
+        const int qb = (head_dim <= 64 && !(head_dim == 40 && dkv2 > 0)) ? 128 : 64;
         CUtensorMap tq, tdo, tk, tv;
         int rc = make_tmap_rows(&tq, q, q_ld, head_dim, heads, Lq, B, 0, qb);
         if (rc != IMAGD_OK) return rc;
@@ -772,12 +779,14 @@ extern "C" int imagd_attention_bwd_bf16(const void* q, int64_t q_ld, const void*
         p.kv_sample_rows = ks->sample_rows > 0 ? ks->sample_rows : ks->len;
         switch (head_dim) {
             case 40:
-                if (dkv2)
+                if (dkv2 > 0)
                     rc = pack_mode == 2 ? launch_dkv<48, 1, 64, 2, 2, 2>(tq, tdo, tk, tv, p, ks->len, st)
                                         : launch_dkv<48, 1, 64, 2, 2, 0>(tq, tdo, tk, tv, p, ks->len, st);
-                else
+                else if (dkv2 == 0)
                     rc = pack_mode == 2 ? launch_dkv<48, 1, 128, 2, 1, 2>(tq, tdo, tk, tv, p, ks->len, st)
                                         : launch_dkv<48, 1, 128, 2>(tq, tdo, tk, tv, p, ks->len, st);
+                else  // IMAGD_BWD_DKV2=-1: one CTA per SM, 128-query blocks, three-stage Q / dO ring
+                    rc = launch_dkv<48, 1, 128, 3>(tq, tdo, tk, tv, p, ks->len, st);
                 break;
             case 64: rc = launch_dkv<64, 1, 128, 2>(tq, tdo, tk, tv, p, ks->len, st); break;
             case 80: rc = launch_dkv<80, 2, 64, 2>(tq, tdo, tk, tv, p, ks->len, st); break;

@@ -128,6 +128,34 @@ __global__ void __launch_bounds__(256) conv_weight_layout_kernel(const __nv_bflo
     }
 }
 
+// Packed forward weight [Cout, 9, Cin] -> the data-gradient weight [Cin, 9, Cout] with the taps reversed:
+// dst[ci, 8 - t, co] = src[co, t, ci] — nine [Cout, Cin] -> [Cin, Cout] tile transposes, blockIdx.z = tap.
+__global__ void __launch_bounds__(256) conv_weight_flip_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                               int Cout, int Cin) {
+    const int t = blockIdx.z;
+    const __nv_bfloat16* x = src + static_cast<int64_t>(t) * Cin;        // rows = co (stride 9 Cin), cols = ci
+    __nv_bfloat16* y = dst + static_cast<int64_t>(8 - t) * Cout;          // rows = ci (stride 9 Cout), cols = co
+    const int64_t ldx = static_cast<int64_t>(9) * Cin, ldy = static_cast<int64_t>(9) * Cout;
+    const bool in_vec = (Cin % 8 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const bool out_vec = (Cout % 8 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    auto load_row = [&](int r, int c) -> uint4 {
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (r < Cout && c < Cin) {
+            const __nv_bfloat16* p = x + static_cast<int64_t>(r) * ldx + c;
+            if (in_vec && c + 8 <= Cin) {
+                val = __ldg(reinterpret_cast<const uint4*>(p));
+            } else {
+                __nv_bfloat16 e[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) e[k] = c + k < Cin ? p[k] : __float2bfloat16(0.f);
+                val = *reinterpret_cast<const uint4*>(e);
+            }
+        }
+        return val;
+    };
+    transpose_tile_body(load_row, y, ldy, blockIdx.y * 64, blockIdx.x * 64, Cin, Cout, out_vec);
+}
+
 // Adjoint of im2col3x3_s2 (pad 1, stride 2): dx[n, y, x, c] = sum over taps with 2 oy + ky - 1 == y, 2 ox + kx - 1 == x of
 // dcol[n, oy, ox, (ky * 3 + kx) * C + c].  One thread per 8 channels of an input pixel.
 __global__ void col2im3x3_s2_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dx, int NB, int H,
@@ -429,34 +457,50 @@ __global__ void __launch_bounds__(kGbThreads) groupnorm_bwd_partial_kernel(
     }
 }
 
+// grid (group blocks, NB): a CTA owns `gpb` whole groups (<= 128 channels) of one sample; 4 chunk lanes per channel add the
+// chunk partials in a fixed order, the lanes meet in shared memory, then one thread per group folds its channels.
 __global__ void __launch_bounds__(kGbThreads) groupnorm_bwd_fold_kernel(const float* __restrict__ part, int HW, int C, int groups,
                                                                         int chunks, const float* __restrict__ gamma,
                                                                         const float* __restrict__ fstat,
                                                                         float* __restrict__ stat, float* __restrict__ pc,
-                                                                        int NB) {
-    extern __shared__ float sm[];  // gamma_c a_c | gamma_c b_c
-    const int n = blockIdx.x;
+                                                                        int NB, int gpb) {
+    __shared__ float sa[4][128], sb[4][128];
+    const int n = blockIdx.y;
     const int cpg = C / groups;
-    for (int c = threadIdx.x; c < C; c += kGbThreads) {
-        float a = 0.f, b = 0.f;
+    const int g0 = blockIdx.x * gpb;
+    const int ng = min(gpb, groups - g0);
+    const int nch = ng * cpg;                       // channels of this CTA (<= 128)
+    const int cl = threadIdx.x & 127, lane = threadIdx.x >> 7;  // 128 channel slots x 4 chunk lanes
+    float a = 0.f, b = 0.f;
+    if (cl < nch) {
+        const int c = g0 * cpg + cl;
         const float* src = part + static_cast<int64_t>(n) * chunks * 2 * C + c;
-        for (int k = 0; k < chunks; ++k) {
+        for (int k = lane; k < chunks; k += 4) {
             a += src[static_cast<int64_t>(k) * 2 * C];
             b += src[static_cast<int64_t>(k) * 2 * C + C];
         }
+    }
+    sa[lane][cl] = a;
+    sb[lane][cl] = b;
+    __syncthreads();
+    if (lane == 0 && cl < nch) {
+        const int c = g0 * cpg + cl;
+        a = (sa[0][cl] + sa[1][cl]) + (sa[2][cl] + sa[3][cl]);
+        b = (sb[0][cl] + sb[1][cl]) + (sb[2][cl] + sb[3][cl]);
         pc[static_cast<int64_t>(n) * C + c] = a;
         pc[static_cast<int64_t>(NB) * C + static_cast<int64_t>(n) * C + c] = b;
         const float ga = gamma ? gamma[c] : 1.f;
-        sm[c] = ga * a;
-        sm[C + c] = ga * b;
+        sa[0][cl] = ga * a;
+        sb[0][cl] = ga * b;
     }
     __syncthreads();
-    const float m = static_cast<float>(HW) * cpg;
-    for (int g = threadIdx.x; g < groups; g += kGbThreads) {
+    if (threadIdx.x < ng) {
+        const int g = g0 + threadIdx.x;
+        const float m = static_cast<float>(HW) * cpg;
         float s2 = 0.f, s1 = 0.f;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-            s2 += sm[c];
-            s1 += sm[C + c];
+        for (int k = threadIdx.x * cpg; k < (threadIdx.x + 1) * cpg; ++k) {
+            s2 += sa[0][k];
+            s1 += sb[0][k];
         }
         float* o = stat + (static_cast<int64_t>(n) * groups + g) * 4;
         o[0] = fstat[(static_cast<int64_t>(n) * groups + g) * 2];
@@ -610,10 +654,16 @@ __global__ void adamw_kernel(float* __restrict__ master, __nv_bfloat16* __restri
 __global__ void adamw_dev_kernel(float* __restrict__ master, __nv_bfloat16* __restrict__ param,
                                  const __nv_bfloat16* __restrict__ grad, float* __restrict__ m, float* __restrict__ v, int64_t n,
                                  float b1, float b2, float eps, const float* __restrict__ hyper) {
+    __shared__ float bc[2];
+    if (threadIdx.x == 0) {  // the two powf calls once per CTA, not per element
+        bc[0] = 1.f - powf(b1, hyper[2]);
+        bc[1] = 1.f - powf(b2, hyper[2]);
+    }
+    __syncthreads();
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float lr = hyper[0], wd = hyper[1], t = hyper[2], gscale = hyper[3];
-    const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+    const float lr = hyper[0], wd = hyper[1], gscale = hyper[3];
+    const float bc1 = bc[0], bc2 = bc[1];
     const float g = __bfloat162float(grad[i]) * gscale;
     const float mi = b1 * m[i] + (1.f - b1) * g;
     const float vi = b2 * v[i] + (1.f - b2) * g * g;
@@ -649,6 +699,14 @@ extern "C" int imagd_conv_weight_layout_bf16(const void* src, void* dst, int Cou
                     "conv_weight_layout: bad argument");
     conv_weight_layout_kernel<<<Cout, 256, static_cast<size_t>(Cin) * 9 * 2, ST(stream)>>>(BF(src), BFW(dst), Cin, mode);
     IMAGD_LAUNCH_CHECK("conv_weight_layout_kernel");
+    return IMAGD_OK;
+}
+
+extern "C" int imagd_conv_weight_flip_bf16(const void* src, void* dst, int Cout, int Cin, imagd_stream stream) {
+    IMAGD_CHECK_ARG(src && dst && Cout > 0 && Cin > 0, "conv_weight_flip: bad argument");
+    dim3 grid((Cin + 63) / 64, (Cout + 63) / 64, 9);
+    conv_weight_flip_kernel<<<grid, 256, 0, ST(stream)>>>(BF(src), BFW(dst), Cout, Cin);
+    IMAGD_LAUNCH_CHECK("conv_weight_flip_kernel");
     return IMAGD_OK;
 }
 
@@ -759,8 +817,12 @@ extern "C" int imagd_groupnorm_bwd_bf16(const void* x, const void* dy, void* dx,
     groupnorm_bwd_partial_kernel<<<dim3(chunks, NB), kGbThreads, smem1, ST(stream)>>>(BF(x), BF(dy), HW, C, groups, chunks, gamma,
                                                                                       beta, fuse_silu, fwd_stats, part);
     IMAGD_LAUNCH_CHECK("groupnorm_bwd_partial_kernel");
-    groupnorm_bwd_fold_kernel<<<NB, kGbThreads, static_cast<size_t>(2) * C * 4, ST(stream)>>>(part, HW, C, groups, chunks, gamma,
-                                                                                             fwd_stats, stat, pc, NB);
+    const int cpg = C / groups;
+    IMAGD_CHECK_ARG(cpg <= 128, "groupnorm_bwd: more than 128 channels per group");
+    const int gpb = 128 / cpg;  // whole groups per fold CTA
+    groupnorm_bwd_fold_kernel<<<dim3((groups + gpb - 1) / gpb, NB), kGbThreads, 0, ST(stream)>>>(part, HW, C, groups, chunks,
+                                                                                                gamma, fwd_stats, stat, pc, NB,
+                                                                                                gpb);
     IMAGD_LAUNCH_CHECK("groupnorm_bwd_fold_kernel");
     const int64_t total = static_cast<int64_t>(NB) * HW * (C / 8);
     groupnorm_bwd_apply_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(BF(x), BF(dy), BFW(dx), HW, C, groups, gamma, beta,

@@ -498,6 +498,16 @@ def conv_weight_layout(w: torch.Tensor, mode: int) -> torch.Tensor:
     return out
 
 
+def conv_weight_flip(wp: torch.Tensor, cin: int) -> torch.Tensor:
+    """Packed [Cout, 9*Cin] -> the dgrad weight [Cin, 9*Cout] (taps reversed, channel roles swapped)."""
+    lib = _lib.load()
+    assert wp.dtype == BF16 and wp.is_contiguous() and wp.shape[1] == 9 * cin
+    co = wp.shape[0]
+    out = torch.empty(cin, 9 * co, device=wp.device, dtype=BF16)
+    _lib.check(lib.imagd_conv_weight_flip_bf16(wp.data_ptr(), out.data_ptr(), co, cin, _stream()), "imagd_conv_weight_flip_bf16")
+    return out
+
+
 def im2col3x3_t(x: torch.Tensor) -> torch.Tensor:
     """x: [NB, H, W, C] bf16 -> [roundup(9*C, 8), roundup(NB*H*W, 8)] transposed stride-1 pad-1 patches (tap-major rows)."""
     lib = _lib.load()

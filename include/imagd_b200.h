@@ -270,6 +270,9 @@ int imagd_transpose_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int r
 /* 3x3 conv weight layouts: mode 0 packs [Cout, Cin, 3, 3] (diffusers) into tap-major [Cout, 9*Cin] (pack_conv3x3 of the
  * trainable garment UNet, every step); mode 1 is the inverse, applied to the packed weight gradient. */
 int imagd_conv_weight_layout_bf16(const void* src, void* dst, int Cout, int Cin, int mode, imagd_stream stream);
+/* Packed forward weight [Cout, 9*Cin] -> the conv data-gradient weight [Cin, 9*Cout]: dst[ci, 8 - tap, co] = src[co, tap, ci]
+ * (dX = conv3x3 of dY with the taps reversed and the channel roles swapped). */
+int imagd_conv_weight_flip_bf16(const void* src, void* dst, int Cout, int Cin, imagd_stream stream);
 /* Transposed im2col of a stride-1 pad-1 3x3 conv input: out[tap*C + c, p] = x[n, y+ky-1, x+kx-1, c], p = (n*H + y)*W + x,
  * zero for p >= NB*H*W; out: [9*C, ldo]. The B operand of the conv weight-gradient GEMM dW[Cout, 9 Cin] = dY^T col^T. */
 int imagd_im2col3x3_t_bf16(const void* x, void* out, int64_t ldo, int NB, int H, int W, int C, imagd_stream stream);

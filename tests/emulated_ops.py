@@ -317,6 +317,11 @@ def transpose(x, pad_to=8, out=None):
     return out
 
 
+def conv_weight_flip(wp, cin):
+    co = wp.shape[0]
+    return wp.view(co, 9, cin).flip(1).permute(2, 1, 0).reshape(cin, 9 * co).contiguous()
+
+
 def conv_weight_layout(w, mode):
     if mode == 0:
         co, ci = w.shape[:2]
@@ -425,7 +430,7 @@ def adamw_step_dev(master, param, grad, m, v, hyper, *, beta1, beta2, eps):
                step=int(round(float(hyper[2]))), grad_scale=float(hyper[3]))
 
 
-TRAIN_OPS = ("adamw_step_dev", "attention_train", "attention_bwd", "transpose", "conv_weight_layout", "im2col3x3_t", "col2im3x3_s2", "downsum2x", "colsum",
+TRAIN_OPS = ("adamw_step_dev", "attention_train", "attention_bwd", "transpose", "conv_weight_layout", "conv_weight_flip", "im2col3x3_t", "col2im3x3_s2", "downsum2x", "colsum",
              "layernorm_bwd", "groupnorm_bwd", "act", "geglu", "mse_loss_grad", "adamw_step")
 
 

@@ -148,6 +148,9 @@ def test_layout_kernels(cuda_device):
     for t in range(9):                                   # the dgrad tap flip: strided source and destination views
         ops.transpose(wp[:, t * 64:(t + 1) * 64], out=dst[:, (8 - t) * 96:(9 - t) * 96])
     assert torch.equal(dst, wp.view(96, 9, 64).flip(1).permute(2, 1, 0).reshape(64, 864))
+    assert torch.equal(ops.conv_weight_flip(wp, 64), dst)
+    w4 = rnd((4, 9 * 320), dev, 23)                      # conv_out's dgrad weight: Cout = 4
+    assert torch.equal(ops.conv_weight_flip(w4, 320), w4.view(4, 9, 320).flip(1).permute(2, 1, 0).reshape(320, 36))
 
     a = rnd((2, 6, 10, 64), dev, 3)
     col = ops.im2col3x3_t(a)
