@@ -61,27 +61,30 @@ __device__ __forceinline__ uint32_t bwd_pack(float lo, float hi) {
 }
 
 // ------------------------------------------------------------------------------------------------ dQ kernel
-template <int HD_MMA, int NATOM, int KV_STAGES>
+template <int HD_MMA, int NATOM, int KV_STAGES, int DSB = 1>
 struct DqCfg {
     static constexpr int kQOff = 0;
     static constexpr int kDoOff = NATOM * kBAtom;
     static constexpr int kKOff = 2 * NATOM * kBAtom;
     static constexpr int kVOff = kKOff + KV_STAGES * NATOM * kBAtom;
     static constexpr int kDsOff = kVOff + KV_STAGES * NATOM * kBAtom;
-    static constexpr int kBarOff = kDsOff + 2 * kBAtom;
-    static constexpr int kNumBars = 1 + 2 * KV_STAGES + 5;  // q, kv_full / kv_empty per stage, s_full, p_full, o_full, s_free, pv_done
+    static constexpr int kBarOff = kDsOff + DSB * 2 * kBAtom;  // DSB dS buffers of two atoms
+    static constexpr int kNumBars = 1 + 2 * KV_STAGES + 3 + 2 * DSB;  // q, kv_full / kv_empty per stage, s_full, o_full, s_free, p_full[DSB], pv_done[DSB]
     static constexpr int kTotal = kBarOff + kNumBars * 8 + 16;
     static_assert(kTotal <= 232448, "dq kernel: shared memory");
     static_assert(256 + HD_MMA <= 512, "dq kernel: TMEM");
 };
 
-template <int HD_MMA, int NATOM, int KV_STAGES, int PACK = 0>
+// DSB = 2: dS is double-buffered (with its own p_full / pv_done barrier pair per buffer), so the exponentials and stores of key
+// block i+1 run while the tensor core still reads dS(i) for dQ += dS K — with one buffer every block serialises
+// softmax -> dQ MMA -> softmax (measured ~3200 clk per block against 1024 clk of exponentials).
+template <int HD_MMA, int NATOM, int KV_STAGES, int PACK = 0, int DSB = 1>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
                    const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1,
                    const AttnBwdParams p) {
-    using C = DqCfg<HD_MMA, NATOM, KV_STAGES>;
+    using C = DqCfg<HD_MMA, NATOM, KV_STAGES, DSB>;
     extern __shared__ __align__(1024) uint8_t smem[];
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* sQ = smem + C::kQOff;
@@ -93,11 +96,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint64_t* kv_full = q_full + 1;
     uint64_t* kv_empty = kv_full + KV_STAGES;
     uint64_t* s_full = kv_empty + KV_STAGES;
-    uint64_t* p_full = s_full + 1;
-    uint64_t* o_full = p_full + 1;
+    uint64_t* o_full = s_full + 1;
     uint64_t* s_free = o_full + 1;
-    uint64_t* pv_done = s_free + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+    uint64_t* p_full = s_free + 1;       // [DSB]
+    uint64_t* pv_done = p_full + DSB;    // [DSB]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + DSB);
 
     const int warp = threadIdx.x >> 5;
     const int q0 = blockIdx.x * 128;
@@ -118,10 +121,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_init(&kv_empty[i], 1);
         }
         mbar_init(s_full, 1);
-        mbar_init(p_full, 256);
         mbar_init(o_full, 1);
         mbar_init(s_free, 256);
-        mbar_init(pv_done, 1);
+        for (int i = 0; i < DSB; ++i) {
+            mbar_init(&p_full[i], 256);
+            mbar_init(&pv_done[i], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 9) {
@@ -196,9 +201,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     tc_fence_after();
                     issue_s(i + 1);
                 }
-                mbar_wait(p_full, i & 1);
+                // block i uses dS buffer i % DSB: its barriers see every DSB-th block, phase index i / DSB
+                mbar_wait(&p_full[i % DSB], (i / DSB) & 1);
                 tc_fence_after();
-                const uint32_t ds_addr = smem_u32(sDS);
+                const uint32_t ds_addr = smem_u32(sDS) + (i % DSB) * 2 * kBAtom;
                 const uint32_t k_addr = smem_u32(sK + st * NATOM * kBAtom);
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
@@ -207,7 +213,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                               umma_smem_desc_sw128(k_addr + ks * 2048, kBAtom, 1024), idesc_o, (i > 0 || ks > 0) ? 1u : 0u);
                 }
                 umma_commit(&kv_empty[st]);
-                umma_commit(pv_done);
+                umma_commit(&pv_done[i % DSB]);
                 if (!kEarly && i + 1 < T) {
                     mbar_wait(s_free, i & 1);
                     tc_fence_after();
@@ -224,7 +230,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int half = warp >> 2;
         const int r = lg * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(lg * 32) << 16;
-        const uint32_t ds_row = smem_u32(sDS) + half * kBAtom + (r >> 3) * 1024 + (r & 7) * 128;
+        const uint32_t ds_row0 = smem_u32(sDS) + half * kBAtom + (r >> 3) * 1024 + (r & 7) * 128;
         const uint32_t rx = r & 7;
         const int q = q0 + r;
         const int64_t vec = (static_cast<int64_t>(b) * p.heads + h) * p.lq_pad + min(q, p.lq_pad - 1);
@@ -251,8 +257,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     tc_fence_before();
                     mbar_arrive(s_free);
                 }
-                if (cc == 0 && i > 0) {  // dQ += dS K of the previous block must have retired before dS is overwritten
-                    mbar_wait(pv_done, (i - 1) & 1);
+                if (cc == 0 && i >= DSB) {  // the dQ += dS K that read this dS buffer (block i - DSB) must have retired
+                    mbar_wait(&pv_done[i % DSB], ((i / DSB) - 1) & 1);
                     tc_fence_after();
                 }
 #pragma unroll
@@ -266,7 +272,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         e[k] = col < valid ? ds : 0.f;
                     }
                     const uint32_t chunk = static_cast<uint32_t>(cc * 4 + g) ^ rx;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row + chunk * 16),
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row0 + (i % DSB) * 2 * kBAtom + chunk * 16),
                                  "r"(bwd_pack<PACK>(e[0], e[1])), "r"(bwd_pack<PACK>(e[2], e[3])),
                                  "r"(bwd_pack<PACK>(e[4], e[5])), "r"(bwd_pack<PACK>(e[6], e[7]))
                                  : "memory");
@@ -274,7 +280,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(p_full);
+            mbar_arrive(&p_full[i % DSB]);
         }
         // ---- epilogue: dQ = sm_scale * acc
         mbar_wait(o_full, 0);
@@ -639,13 +645,13 @@ static int make_tmap_rows(CUtensorMap* tm, const void* base, int64_t ld, int hd,
     return make_tmap_bf16(tm, base, 4, dims, strides, box);
 }
 
-template <int HD_MMA, int NATOM, int KV_STAGES, int PACK = 0>
+template <int HD_MMA, int NATOM, int KV_STAGES, int PACK = 0, int DSB = 1>
 static int launch_dq(const CUtensorMap* tms, const AttnBwdParams& p, cudaStream_t stream) {
-    using C = DqCfg<HD_MMA, NATOM, KV_STAGES>;
-    IMAGD_SET_MAX_SMEM((attn_bwd_dq_kernel<HD_MMA, NATOM, KV_STAGES, PACK>), C::kTotal);
+    using C = DqCfg<HD_MMA, NATOM, KV_STAGES, DSB>;
+    IMAGD_SET_MAX_SMEM((attn_bwd_dq_kernel<HD_MMA, NATOM, KV_STAGES, PACK, DSB>), C::kTotal);
     dim3 grid((p.Lq + 127) / 128, p.heads, p.B);
-    attn_bwd_dq_kernel<HD_MMA, NATOM, KV_STAGES, PACK><<<grid, 320, C::kTotal, stream>>>(tms[0], tms[1], tms[2], tms[3], tms[4],
-                                                                                         tms[5], p);
+    attn_bwd_dq_kernel<HD_MMA, NATOM, KV_STAGES, PACK, DSB><<<grid, 320, C::kTotal, stream>>>(tms[0], tms[1], tms[2], tms[3],
+                                                                                              tms[4], tms[5], p);
     IMAGD_LAUNCH_CHECK("attn_bwd_dq_kernel");
     return IMAGD_OK;
 }
@@ -741,12 +747,16 @@ extern "C" int imagd_attention_bwd_bf16(const void* q, int64_t q_ld, const void*
         // ahead of the tensor core and the ~1 us L2 -> shared latency of every block is exposed (measured ~4000 clk per
         // block against 1024 clk of exponentials); IMAGD_BWD_DQ_STAGES=2 restores the shallow ring for A/B.
         static const int dq_stages = [] { const char* e = getenv("IMAGD_BWD_DQ_STAGES"); return e ? atoi(e) : 4; }();
+        static const int dq_dsb = [] { const char* e = getenv("IMAGD_BWD_DQ_DSB"); return e ? atoi(e) : 2; }();
         switch (head_dim) {
-            case 40:
-                if (dq_stages >= 4) rc = launch_dq<48, 1, 4>(tms, p, st);
+            case 40:  // IMAGD_BWD_DQ_DSB=1 keeps the single dS buffer (A/B)
+                if (dq_stages >= 4) rc = dq_dsb >= 2 ? launch_dq<48, 1, 4, 0, 2>(tms, p, st) : launch_dq<48, 1, 4>(tms, p, st);
                 else rc = bwd_pack_mode == 2 ? launch_dq<48, 1, 2, 2>(tms, p, st) : launch_dq<48, 1, 2>(tms, p, st);
                 break;
-            case 64: rc = dq_stages >= 4 ? launch_dq<64, 1, 4>(tms, p, st) : launch_dq<64, 1, 2>(tms, p, st); break;
+            case 64:
+                if (dq_stages >= 4) rc = dq_dsb >= 2 ? launch_dq<64, 1, 4, 0, 2>(tms, p, st) : launch_dq<64, 1, 4>(tms, p, st);
+                else rc = launch_dq<64, 1, 2>(tms, p, st);
+                break;
             case 80: rc = launch_dq<80, 2, 2>(tms, p, st); break;
             default: rc = launch_dq<160, 3, 1>(tms, p, st); break;
         }
