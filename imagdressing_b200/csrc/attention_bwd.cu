@@ -44,7 +44,13 @@ struct AttnBwdParams {
     void* dv;
     int64_t dkv_ld;
     int kv_sample_rows;  // rows between samples in dk / dv
+    int spin;            // 1: the dS / P warps spin on their mbarriers instead of suspending (IMAGD_BWD_SPIN, A/B)
 };
+
+__device__ __forceinline__ void bwd_wait(uint64_t* bar, uint32_t parity, int spin) {
+    if (spin) mbar_wait_spin(bar, parity);
+    else mbar_wait(bar, parity);
+}
 
 constexpr int kBAtom = 128 * 128;  // one [128 rows x 64 bf16] swizzled tile
 
@@ -245,7 +251,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 w = s ? p.w1 : p.w0;
             }
             const int valid = (s ? p.len1 : p.len0) - j * 128 - half * 64;  // valid key columns in my half (may be <= 0)
-            mbar_wait(s_full, i & 1);
+            bwd_wait(s_full, i & 1, p.spin);
             tc_fence_after();
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
@@ -258,7 +264,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     mbar_arrive(s_free);
                 }
                 if (cc == 0 && i >= DSB) {  // the dQ += dS K that read this dS buffer (block i - DSB) must have retired
-                    mbar_wait(&pv_done[i % DSB], ((i / DSB) - 1) & 1);
+                    bwd_wait(&pv_done[i % DSB], ((i / DSB) - 1) & 1, p.spin);
                     tc_fence_after();
                 }
 #pragma unroll
@@ -315,7 +321,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------ dK / dV kernel
-template <int HD_MMA, int NATOM, int QB, int STAGES, int CTAS = 1>
+template <int HD_MMA, int NATOM, int QB, int STAGES, int CTAS = 1, int DSB = 1>
 struct DkvCfg {
     static constexpr int kQAtom = QB * 128;  // one [QB rows x 64 bf16] swizzled tile of Q / dO
     static constexpr int kPAtoms = QB / 64;  // P^T / dS^T: [128 keys x QB] = QB / 64 atoms of [128 x 64]
@@ -324,10 +330,10 @@ struct DkvCfg {
     static constexpr int kQOff = 2 * NATOM * kBAtom;
     static constexpr int kDoOff = kQOff + STAGES * NATOM * kQAtom;
     static constexpr int kPOff = kDoOff + STAGES * NATOM * kQAtom;
-    static constexpr int kDsOff = kPOff + kPAtoms * kBAtom;
-    static constexpr int kVecOff = kDsOff + kPAtoms * kBAtom;  // per stage: lse2[QB] | D[QB] fp32
+    static constexpr int kDsOff = kPOff + DSB * kPAtoms * kBAtom;  // DSB buffers each of P^T and dS^T
+    static constexpr int kVecOff = kDsOff + DSB * kPAtoms * kBAtom;  // per stage: lse2[QB] | D[QB] fp32
     static constexpr int kBarOff = kVecOff + STAGES * 2 * QB * 4;
-    static constexpr int kNumBars = 1 + 2 * STAGES + 5;
+    static constexpr int kNumBars = 1 + 2 * STAGES + 3 + 2 * DSB;
     static constexpr int kTotal = kBarOff + kNumBars * 8 + 16;
     static constexpr int kAccStride = (HD_MMA + 63) / 64 * 64;
     static constexpr int kTmemDv = 2 * QB;
@@ -339,13 +345,15 @@ struct DkvCfg {
 
 // CTAS = 2 (with QB = 64: 256 TMEM columns, ~100 KB of shared memory): two CTAs per SM, so one CTA's exponential phase runs
 // under the other's tensor-core / synchronisation phases — the forward kernel's two-CTAs-per-SM arrangement.
-template <int HD_MMA, int NATOM, int QB, int STAGES, int CTAS = 1, int PACK = 0>
+// DSB = 2: P^T / dS^T double-buffered with their own barrier pairs, as in the dQ kernel.
+template <int HD_MMA, int NATOM, int QB, int STAGES, int CTAS = 1, int PACK = 0, int DSB = 1>
 __global__ void __launch_bounds__(320, CTAS)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                     const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                     const AttnBwdParams p) {
-    using C = DkvCfg<HD_MMA, NATOM, QB, STAGES, CTAS>;
+    using C = DkvCfg<HD_MMA, NATOM, QB, STAGES, CTAS, DSB>;
     constexpr int kQA = C::kQAtom;
+    constexpr int kBufBytes = C::kPAtoms * kBAtom;  // one P^T (or dS^T) buffer
     extern __shared__ __align__(1024) uint8_t smem[];
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* sK = smem + C::kKOff;
@@ -359,11 +367,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* q_full = kv_full + 1;
     uint64_t* q_empty = q_full + STAGES;
     uint64_t* s_full = q_empty + STAGES;
-    uint64_t* p_full = s_full + 1;
-    uint64_t* o_full = p_full + 1;
+    uint64_t* o_full = s_full + 1;
     uint64_t* s_free = o_full + 1;
-    uint64_t* pv_done = s_free + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+    uint64_t* p_full = s_free + 1;       // [DSB]
+    uint64_t* pv_done = p_full + DSB;    // [DSB]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + DSB);
 
     const int warp = threadIdx.x >> 5;
     const int k0 = blockIdx.x * 128;
@@ -384,10 +392,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             mbar_init(&q_empty[i], 1);
         }
         mbar_init(s_full, 1);
-        mbar_init(p_full, 256);
         mbar_init(o_full, 1);
         mbar_init(s_free, 256);
-        mbar_init(pv_done, 1);
+        for (int i = 0; i < DSB; ++i) {
+            mbar_init(&p_full[i], 256);
+            mbar_init(&pv_done[i], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 9) {
@@ -465,9 +475,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     tc_fence_after();
                     issue_s(i + 1);
                 }
-                mbar_wait(p_full, i & 1);
+                mbar_wait(&p_full[i % DSB], (i / DSB) & 1);
                 tc_fence_after();
-                const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+                const uint32_t p_addr = smem_u32(sP) + (i % DSB) * kBufBytes, ds_addr = smem_u32(sDS) + (i % DSB) * kBufBytes;
                 const uint32_t q_addr = smem_u32(sQ + st * NATOM * kQA), do_addr = smem_u32(sDO + st * NATOM * kQA);
 #pragma unroll
                 for (int ks = 0; ks < QB / 16; ++ks) {
@@ -482,7 +492,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                               umma_smem_desc_sw128(q_addr + ks * 2048, kQA, 1024), idesc_o, (i > 0 || ks > 0) ? 1u : 0u);
                 }
                 umma_commit(&q_empty[st]);
-                umma_commit(pv_done);
+                umma_commit(&pv_done[i % DSB]);
                 if (!kEarly && i + 1 < T) {
                     mbar_wait(s_free, i & 1);
                     tc_fence_after();
@@ -514,8 +524,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             // the lse2 / D vectors arrive by bulk copy on q_full[st]: observe that barrier directly (the MMA thread's wait
             // does not order the async-proxy writes for this thread). The phase cannot advance twice under us: the slot is
             // re-armed only after q_empty[st], which follows the p_full arrival of every thread here.
-            mbar_wait(&q_full[st], (i / STAGES) & 1);
-            mbar_wait(s_full, i & 1);
+            bwd_wait(&q_full[st], (i / STAGES) & 1, p.spin);
+            bwd_wait(s_full, i & 1, p.spin);
             tc_fence_after();
 #pragma unroll
             for (int cc = 0; cc < kCC; ++cc) {
@@ -527,8 +537,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     tc_fence_before();
                     mbar_arrive(s_free);
                 }
-                if (cc == 0 && i > 0) {
-                    mbar_wait(pv_done, (i - 1) & 1);
+                if (cc == 0 && i >= DSB) {
+                    bwd_wait(&pv_done[i % DSB], ((i / DSB) - 1) & 1, p.spin);
                     tc_fence_after();
                 }
 #pragma unroll
@@ -548,11 +558,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         de[k] = pr * fmaf(w, __uint_as_float(vb[g * 8 + k]), -dd[k]);
                     }
                     const uint32_t chunk = (chunk0 + static_cast<uint32_t>(cc * 4 + g)) ^ rx;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + chunk * 16),
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + (i % DSB) * kBufBytes + chunk * 16),
                                  "r"(bwd_pack<PACK>(pe[0], pe[1])), "r"(bwd_pack<PACK>(pe[2], pe[3])),
                                  "r"(bwd_pack<PACK>(pe[4], pe[5])), "r"(bwd_pack<PACK>(pe[6], pe[7]))
                                  : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row + chunk * 16),
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ds_row + (i % DSB) * kBufBytes + chunk * 16),
                                  "r"(bwd_pack<PACK>(de[0], de[1])), "r"(bwd_pack<PACK>(de[2], de[3])),
                                  "r"(bwd_pack<PACK>(de[4], de[5])), "r"(bwd_pack<PACK>(de[6], de[7]))
                                  : "memory");
@@ -560,7 +570,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(p_full);
+            mbar_arrive(&p_full[i % DSB]);
         }
         // ---- epilogue: dV = w * acc_dV, dK = sm_scale * acc_dK
         mbar_wait(o_full, 0);
@@ -656,13 +666,13 @@ static int launch_dq(const CUtensorMap* tms, const AttnBwdParams& p, cudaStream_
     return IMAGD_OK;
 }
 
-template <int HD_MMA, int NATOM, int QB, int STAGES, int CTAS = 1, int PACK = 0>
+template <int HD_MMA, int NATOM, int QB, int STAGES, int CTAS = 1, int PACK = 0, int DSB = 1>
 static int launch_dkv(const CUtensorMap& tq, const CUtensorMap& tdo, const CUtensorMap& tk, const CUtensorMap& tv,
                       const AttnBwdParams& p, int len, cudaStream_t stream) {
-    using C = DkvCfg<HD_MMA, NATOM, QB, STAGES, CTAS>;
-    IMAGD_SET_MAX_SMEM((attn_bwd_dkv_kernel<HD_MMA, NATOM, QB, STAGES, CTAS, PACK>), C::kTotal);
+    using C = DkvCfg<HD_MMA, NATOM, QB, STAGES, CTAS, DSB>;
+    IMAGD_SET_MAX_SMEM((attn_bwd_dkv_kernel<HD_MMA, NATOM, QB, STAGES, CTAS, PACK, DSB>), C::kTotal);
     dim3 grid((len + 127) / 128, p.heads, p.B);
-    attn_bwd_dkv_kernel<HD_MMA, NATOM, QB, STAGES, CTAS, PACK><<<grid, 320, C::kTotal, stream>>>(tq, tdo, tk, tv, p);
+    attn_bwd_dkv_kernel<HD_MMA, NATOM, QB, STAGES, CTAS, PACK, DSB><<<grid, 320, C::kTotal, stream>>>(tq, tdo, tk, tv, p);
     IMAGD_LAUNCH_CHECK("attn_bwd_dkv_kernel");
     return IMAGD_OK;
 }
@@ -721,6 +731,8 @@ extern "C" int imagd_attention_bwd_bf16(const void* q, int64_t q_ld, const void*
     p.dsum = dsum;
     p.dq = dq;
     p.dq_ld = dq_ld;
+    static const int spin = [] { const char* e = getenv("IMAGD_BWD_SPIN"); return e ? atoi(e) : 0; }();
+    p.spin = spin;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     if (dq != nullptr) {
@@ -789,7 +801,9 @@ extern "C" int imagd_attention_bwd_bf16(const void* q, int64_t q_ld, const void*
         p.kv_sample_rows = ks->sample_rows > 0 ? ks->sample_rows : ks->len;
         switch (head_dim) {
             case 40:
-                if (dkv2 > 0)
+                if (dkv2 == 3)  // one CTA per SM, 64-query blocks, six-stage Q / dO ring, double-buffered P^T / dS^T
+                    rc = launch_dkv<48, 1, 64, 6, 1, 0, 2>(tq, tdo, tk, tv, p, ks->len, st);
+                else if (dkv2 > 0)
                     rc = pack_mode == 2 ? launch_dkv<48, 1, 64, 2, 2, 2>(tq, tdo, tk, tv, p, ks->len, st)
                                         : launch_dkv<48, 1, 64, 2, 2, 0>(tq, tdo, tk, tv, p, ks->len, st);
                 else if (dkv2 == 0)

@@ -62,6 +62,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Spinning wait (mbarrier.test_wait in a loop, no hardware suspend): the warp keeps its issue slot and resumes the cycle the
+// phase completes. For warps that have nothing else to do and sit on the critical path (the softmax warps of the attention
+// backward kernels: ncu showed ~7 suspends per key block per warp and an SMSP idle 68 % of the time). Bounded like mbar_wait.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0, tries = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P;\n\t}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!ok && ++tries > (1u << 28)) {
+            printf("imagd: mbarrier spin timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+            __trap();
+        }
+    } while (!ok);
+}
+
 // 1-D bulk copy shared -> global (async proxy), tracked by the issuing thread's bulk group. 16-byte aligned, size % 16 == 0.
 __device__ __forceinline__ void bulk_store_s2g(void* gptr, uint32_t smem_addr, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gptr), "r"(smem_addr), "r"(bytes)
