@@ -53,6 +53,7 @@ struct AttnParams {
     int causal;            // stream 0 only: query q sees keys 0..q
     int pdl_late;          // 1: release the dependent kernel when the last MMA is issued instead of at kernel entry
     int pp_sync;           // ping-pong kernels: 1 = the two softmax groups alternate on the MUFU pipe through named barriers
+    int spin;              // ping-pong kernel: 1 = the softmax warps spin on s_full instead of suspending (IMAGD_ATTN_SPIN, A/B)
     void* out;
     int64_t out_ld;
     // training-mode extras (imagd_attention_train_fwd_bf16; all null / 0 on the inference path): per-row log-sum-exp of
@@ -545,6 +546,8 @@ static int launch_attn_pp(const CUtensorMap* tms, AttnParams p, cudaStream_t str
     static const int variant = env_int("IMAGD_ATTN_PP_VARIANT", 1);
     static const int sync = env_int("IMAGD_ATTN_PP_SYNC", 1);
     p.pp_sync = sync;
+    static const int spin = env_int("IMAGD_ATTN_SPIN", 0);
+    p.spin = spin;
     dim3 grid((p.Lq + 255) / 256, p.heads, p.B);
     if (variant == 1) {
         using C = AttnPP1Cfg<kStages>;
@@ -651,6 +654,7 @@ static int attention_impl(const void* q, int64_t q_ld, void* out, int64_t out_ld
     p.oscale1 = has1 ? s1->out_scale : 0.f;
     p.causal = causal;
     p.pp_sync = 1;
+    p.spin = 0;
     p.pdl_late = pdl_mode() == 2 ? 1 : 0;
     p.out = out;
     p.out_ld = out_ld;
