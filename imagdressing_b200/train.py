@@ -291,7 +291,8 @@ class FlatAdamW:
 
     def __init__(self, params: Iterable[nn.Parameter], lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
                  bucket_bytes: int = 256 << 20, step_fn=None, shard_states: bool = False):
-        self.params = [p for p in params if p.requires_grad]
+        seen = set()
+        self.params = [p for p in params if p.requires_grad and not (id(p) in seen or seen.add(id(p)))]  # de-duplicated
         assert self.params, "no trainable parameters"
         dev = self.params[0].device
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
