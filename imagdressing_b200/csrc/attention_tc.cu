@@ -507,16 +507,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 #include "attention_pp.inc"
 #include "attention_pp1.inc"
+#include "attention_pp3.inc"
 
 // ------------------------------------------------------------------------------------------------ host side
 
 static int make_head_tmap(CUtensorMap* tm, const void* base, int64_t ld, int hd, int heads, int len, int nsamples,
-                          int sample_rows = 0) {
+                          int sample_rows = 0, int box_rows = 128) {
     uint64_t dims[4] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(heads), static_cast<uint64_t>(len),
                         static_cast<uint64_t>(nsamples)};
     uint64_t strides[3] = {static_cast<uint64_t>(hd) * 2, static_cast<uint64_t>(ld) * 2,
                            static_cast<uint64_t>(ld) * 2 * (sample_rows > 0 ? sample_rows : len)};
-    uint32_t box[4] = {64, 1, 128, 1};
+    uint32_t box[4] = {64, 1, static_cast<uint32_t>(box_rows), 1};
     return make_tmap_bf16(tm, base, 4, dims, strides, box);
 }
 
@@ -535,6 +536,26 @@ static int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
+// IMAGD_ATTN_PP_VARIANT: 1 = P aliases S (first build), 2 = separate P buffer, 3 = one thread per row, 64-key blocks,
+// double-buffered S (its K / V tensor maps fetch 64-row boxes)
+static int attn_pp_variant() {
+    static const int v = env_int("IMAGD_ATTN_PP_VARIANT", 1);
+    return v;
+}
+
+template <int HD_MMA>
+static int launch_attn_pp3(const CUtensorMap* tms, AttnParams p, cudaStream_t stream) {
+    constexpr int kStages = 6;
+    using C = AttnPP3Cfg<kStages>;
+    static const int sync = env_int("IMAGD_ATTN_PP_SYNC", 1);
+    p.pp_sync = sync;
+    dim3 grid((p.Lq + 255) / 256, p.heads, p.B);
+    IMAGD_SET_MAX_SMEM((attention_pp3_kernel<HD_MMA, kStages>), C::kTotal);
+    IMAGD_CUDA(launch_pdl(attention_pp3_kernel<HD_MMA, kStages>, grid, dim3(320), C::kTotal, stream, tms[0], tms[1], tms[2],
+                          tms[3], tms[4], p));
+    return IMAGD_OK;
+}
+
 template <int HD_MMA>
 static int launch_attn_pp(const CUtensorMap* tms, AttnParams p, cudaStream_t stream) {
     constexpr int kStages = 3;
@@ -543,7 +564,7 @@ static int launch_attn_pp(const CUtensorMap* tms, AttnParams p, cudaStream_t str
     // Measured on B200, level-0 hybrid attention, batch 1 / 8 (profiles/r02_call5_attention_matrix_clip.txt):
     //   variant 1 sync 1: 197.9 / 1202.8 us   variant 1 sync 0: 216.0 / 1260.0 us
     //   variant 2 sync 1: 221.7 / 1347.5 us   variant 2 sync 0: 212.0 / 1321.5 us   two-CTAs-per-SM kernel: 214 / 1298 us
-    static const int variant = env_int("IMAGD_ATTN_PP_VARIANT", 1);
+    static const int variant = attn_pp_variant();
     static const int sync = env_int("IMAGD_ATTN_PP_SYNC", 1);
     p.pp_sync = sync;
     static const int spin = env_int("IMAGD_ATTN_SPIN", 0);
@@ -689,8 +710,26 @@ static int attention_impl(const void* q, int64_t q_ld, void* out, int64_t out_ld
         tms[4] = tms[2];
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (attn_pp() && !aux && !causal && Lq > 128 && (head_dim == 40 || head_dim == 64))
+    if (attn_pp() && !aux && !causal && Lq > 128 && (head_dim == 40 || head_dim == 64)) {
+        if (attn_pp_variant() == 3) {  // K / V through 64-row boxes
+            rc = make_head_tmap(&tms[1], s0->k, s0->ld, head_dim, heads, s0->len, s0->broadcast ? 1 : B, s0->sample_rows, 64);
+            if (rc != IMAGD_OK) return rc;
+            rc = make_head_tmap(&tms[2], s0->v, s0->ld, head_dim, heads, s0->len, s0->broadcast ? 1 : B, s0->sample_rows, 64);
+            if (rc != IMAGD_OK) return rc;
+            if (has1) {
+                const int ns = s1->broadcast ? 1 : p.nq1;
+                rc = make_head_tmap(&tms[3], s1->k, s1->ld, head_dim, heads, s1->len, ns, s1->sample_rows, 64);
+                if (rc != IMAGD_OK) return rc;
+                rc = make_head_tmap(&tms[4], s1->v, s1->ld, head_dim, heads, s1->len, ns, s1->sample_rows, 64);
+                if (rc != IMAGD_OK) return rc;
+            } else {
+                tms[3] = tms[1];
+                tms[4] = tms[2];
+            }
+            return head_dim == 40 ? launch_attn_pp3<48>(tms, p, st) : launch_attn_pp3<64>(tms, p, st);
+        }
         return head_dim == 40 ? launch_attn_pp<48>(tms, p, st) : launch_attn_pp<64>(tms, p, st);
+    }
     switch (head_dim) {
         case 40: return attn_ptmem() ? launch_attn<48, 1, 2, true>(tms, p, st) : launch_attn<48, 1, 2, false>(tms, p, st);
         case 64: return attn_ptmem() ? launch_attn<64, 1, 2, true>(tms, p, st) : launch_attn<64, 1, 2, false>(tms, p, st);
