@@ -710,7 +710,11 @@ static int attention_impl(const void* q, int64_t q_ld, void* out, int64_t out_ld
         tms[4] = tms[2];
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (attn_pp() && !aux && !causal && Lq > 128 && (head_dim == 40 || head_dim == 64)) {
+    // the training-mode outputs (lse / per-stream O) exist in the first ping-pong build and in the two-CTAs-per-SM kernel;
+    // IMAGD_ATTN_TRAIN_PP=0 keeps training forwards on the latter (A/B)
+    static const int train_pp = env_int("IMAGD_ATTN_TRAIN_PP", 1);
+    const bool pp_ok = !aux || (train_pp && attn_pp_variant() == 1);
+    if (attn_pp() && pp_ok && !causal && Lq > 128 && (head_dim == 40 || head_dim == 64)) {
         if (attn_pp_variant() == 3) {  // K / V through 64-row boxes
             rc = make_head_tmap(&tms[1], s0->k, s0->ld, head_dim, heads, s0->len, s0->broadcast ? 1 : B, s0->sample_rows, 64);
             if (rc != IMAGD_OK) return rc;

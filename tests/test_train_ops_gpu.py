@@ -272,10 +272,16 @@ def test_mse_and_adamw(cuda_device):
     opt = torch.optim.AdamW([p_ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
     master, m, v = w0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
     param = w0.to(BF)
+    # the device-scalar variant (CUDA-graph replayable: step / lr read from memory; 4 elements per thread + scalar tail)
+    master2, m2, v2, param2 = w0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev), w0.to(BF)
+    hyper = torch.tensor([1e-3, 1e-2, 0.0, 1.0], device=dev)
     for step in range(1, 4):
         grad = (torch.randn(n, generator=g) * 0.1).to(BF).to(dev)
         p_ref.grad = grad.float()
         opt.step()
         ops.adamw_step(master, param, grad, m, v, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2, step=step)
+        hyper[2:3].add_(1.0)
+        ops.adamw_step_dev(master2, param2, grad, m2, v2, hyper, beta1=0.9, beta2=0.999, eps=1e-8)
     assert rel_l2(master, p_ref.detach()) < 1e-5
     assert torch.equal(param, master.to(BF))
+    assert rel_l2(master2, p_ref.detach()) < 1e-5 and torch.equal(param2, master2.to(BF))
