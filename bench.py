@@ -498,6 +498,40 @@ class CpuOracle:
                           f"scaled to {2 * STEPS_DDIM + 1} forwards/image", "s_per_forward": round(per_fwd, 3)}
 
 
+def cpu_train_baseline(h=640, w=512, threads=None):
+    """The reference's training step on the host cores: the fp32 oracle (oracle/train_step.py: SDModel forward through both
+    UNets + Resampler, MSE, torch-autograd backward; reference train.py:255-281,573-605) for ONE micro-batch-1 sample at
+    h x w — a bounded sample of configs[4]'s micro-batch-4 step (samples/s is per sample either way)."""
+    from oracle import processors as op
+    from oracle import train_step as ts
+    from oracle import unet as ou
+    from oracle.ddim import DDIMOracle
+
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = threads or min(32, avail)
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    with _no_default_init():
+        unet, ref = ou.UNet2DConditionModel(), ou.UNet2DConditionModel()
+    proj = op.Resampler(dim=768, depth=4, dim_head=64, heads=12, num_queries=16, embedding_dim=1280, output_dim=768, ff_mult=4)
+    with torch.no_grad():
+        for m in (unet, ref, proj):
+            for p in m.parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    adapters = ts.install_training_processors(unet, ref)
+    ts.set_trainable(unet, ref, proj, adapters)
+    lh, lw = h // 8, w // 8
+    r = lambda *sh: torch.randn(*sh, generator=g)
+    b = dict(latents=r(1, 4, lh, lw), ref_latents=r(1, 4, lh, lw), clip_image_embeddings=r(1, 257, 1280),
+             encoder_hidden_states=r(1, 77, 768), noise=r(1, 4, lh, lw), timesteps=torch.tensor([500]))
+    t0 = time.perf_counter()
+    loss = float(ts.train_step(unet, ref, proj, DDIMOracle(), **b))
+    dt = time.perf_counter() - t0
+    return {"value": round(1.0 / dt, 6), "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": f"one fp32 micro-batch-1 training step (forward + backward, {h}x{w}) of the oracle port = {dt:.1f} s; "
+                      f"loss {loss:.4f}"}
+
+
 CPU_SAMPLE_FORWARDS = 10  # per step, in both CPU legs (~15-30 s of CPU work on the GPU box's host)
 
 
@@ -512,6 +546,27 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    if a.impl == "reference" and a.workload == "train":
+        if rank != 0:
+            return
+        h, w = (640, 512) if (a.height, a.width) == (512, 512) else (a.height, a.width)
+        vals = []
+        cb = None
+        for i in range(min(a.warmup, 1) + max(1, min(a.steps, 3))):  # ~30-60 s each: bounded
+            cb = cpu_train_baseline(h, w)
+            if i >= min(a.warmup, 1):
+                vals.append(cb["value"])
+        v = sum(vals) / len(vals)
+        cb["value"] = round(v, 6)
+        print(json.dumps({"impl": "reference", "metric": f"training samples/sec, {h}x{w} forward+backward", "value": round(v, 6),
+                          "unit": "samples/s", "n_gpus": 0, "steps": len(vals), "warmup": min(a.warmup, 1),
+                          "ms_per_step": round(1000.0 / v, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "train.py step (BASELINE.json configs[4]) on the host cores: fp32 oracle port, "
+                                                 "micro-batch 1 per step", "global_batch": 1},
+                          "cpu_baseline": cb,
+                          "e2e": {"value": round(v, 6), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
     if a.impl == "reference":
         if rank != 0:
             return
@@ -553,7 +608,15 @@ def main():
         Bt = a.batch if a.batch != 1 else 4
         h, w = (640, 512) if (a.height, a.width) == (512, 512) else (a.height, a.width)
         rec = train_record(a, dev, rank, local, world, Bt, h, w, a.steps, max(a.warmup, 5))
+        cb = None
+        if rank == 0 and world == 1 and not a.no_cpu_baseline:
+            try:
+                cb = cpu_train_baseline(h, w)
+            except Exception as e:  # noqa: BLE001
+                cb = {"error": f"{type(e).__name__}: {e}"[:200]}
         if rank == 0:
+            if cb is not None:
+                rec["cpu_baseline"] = cb
             print(json.dumps({
                 "metric": f"training samples/sec, {h}x{w} bf16 forward+backward+AdamW, micro-batch {Bt}/GPU", "value": rec["samples_per_s"],
                 "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": rec["ms_per_step"],

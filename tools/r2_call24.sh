@@ -25,3 +25,6 @@ PY
 echo "== reference arm" >> $out
 timeout 900 python bench.py --impl reference --steps 1 --warmup 1 2>&1 | tail -1 | cut -c1-400 >> $out
 cat $out | cut -c1-330
+echo "== reference arm, training step on the host cores" >> gpurun_out/call24.txt
+timeout 900 python bench.py --impl reference --workload train --steps 1 --warmup 0 2>&1 | tail -1 | cut -c1-600 >> gpurun_out/call24.txt
+tail -2 gpurun_out/call24.txt | cut -c1-600
