@@ -213,26 +213,35 @@ class BaseSAttnProcessor2_0(_ModuleProc):
 
 
 class SAttnProcessor2_0(_ModuleProc):
-    """reference :103-200 — the concat-KV single-softmax variant (`cat([k, k_ref])`, :155-161). No script installs
-    it; constructing it works for import compatibility, calling it is not on the hot path."""
+    """reference :103-200 — the concat-KV single-softmax variant: for self-attention with garment features the keys / values
+    are to_k / to_v of cat([hidden_states, sa_hidden_states[name]], dim=1) (:155-161), ONE softmax over both. No reference
+    script installs it; on the kernels it is the one-stream attention over the concatenated context."""
 
     def __init__(self, name=None, hidden_size=None, cross_attention_dim=None, scale=1.0):
         super().__init__()
         self.name, self.hidden_size, self.cross_attention_dim, self.scale = name, hidden_size, cross_attention_dim, scale
 
-    def __call__(self, *a, **k):
-        raise NotImplementedError("SAttnProcessor2_0 (concat-KV variant) is not used by any reference script")
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
+                 cond_hidden_states=None, sa_hidden_states=None, **kwargs):
+        if encoder_hidden_states is None and sa_hidden_states is not None:
+            ref = sa_hidden_states[self.name]
+            encoder_hidden_states = torch.cat([hidden_states.to(ref.dtype), ref], dim=1)
+        return attention_forward(self, attn, hidden_states, encoder_hidden_states,
+                                 prepare_only=kwargs.get("_prepare_only", False))
 
 
 class RefCAttnProcessor2_0(_ModuleProc):
-    """reference :630-744 — cross-attention with a reference branch (unused by the scripts; import compat)."""
+    """reference :630-744 — (cross-)attention plus the reference branch scale * SDPA(q, to_k_ref(g), to_v_ref(g)) on the
+    same query: the two-stream kernel with the context as stream 0 (unused by the scripts)."""
 
     def __init__(self, name=None, hidden_size=None, cross_attention_dim=None, scale=1.0):
         super().__init__()
         self.name, self.hidden_size, self.cross_attention_dim, self.scale = name, hidden_size, cross_attention_dim, scale
-        kv = cross_attention_dim or hidden_size
-        self.to_k_ref = nn.Linear(kv, hidden_size, bias=False)
-        self.to_v_ref = nn.Linear(kv, hidden_size, bias=False)
+        self.to_k_ref = nn.Linear(hidden_size, hidden_size, bias=False)  # :643-644: hidden_size inputs
+        self.to_v_ref = nn.Linear(hidden_size, hidden_size, bias=False)
 
-    def __call__(self, *a, **k):
-        raise NotImplementedError("RefCAttnProcessor2_0 is not used by any reference script")
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
+                 cond_hidden_states=None, sa_hidden_states=None, ref_samples=None, **kwargs):
+        return attention_forward(self, attn, hidden_states, encoder_hidden_states,
+                                 second=ref_stream(self, hidden_states, sa_hidden_states, ref_samples),
+                                 prepare_only=kwargs.get("_prepare_only", False))

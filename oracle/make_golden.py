@@ -21,8 +21,20 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle", "_shim"))
 sys.path.insert(0, "/root/reference")
 
-from adapter import attention_processor as ref_ap  # noqa: E402  (the reference's file)
-from adapter import resampler as ref_rs  # noqa: E402
+import importlib.util  # noqa: E402
+
+
+def _load_reference(name, path):
+    """The reference's `adapter/` has no __init__.py (a namespace package), so this repo's `adapter` package of the same name
+    would shadow it on any sys.path order: load the reference FILES by path."""
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+ref_ap = _load_reference("reference_attention_processor", "/root/reference/adapter/attention_processor.py")  # the reference's file
+ref_rs = _load_reference("reference_resampler", "/root/reference/adapter/resampler.py")
 
 from oracle.unet import Attention  # noqa: E402
 
@@ -119,6 +131,19 @@ fill_(pp)
 idemb = rnd(B, 64)
 put("projplus", pp, id=idemb.bfloat16(), clip=clip.bfloat16(), out=pp(idemb, clip, shortcut=False),
     out_shortcut=pp(idemb, clip, shortcut=True, scale=0.5))
+
+# ---- (appended in round 2, AFTER everything above so the seeded values of the earlier goldens do not move)
+# SAttnProcessor2_0: concat-KV single softmax (:155-161); RefCAttnProcessor2_0: cross-attention + reference branch (:630-744)
+sproc = ref_ap.SAttnProcessor2_0(NAME, C)
+put("sattn", out=sproc(attn, x, sa_hidden_states={NAME: rnd(B, LREF, C)}), out_nosa=sproc(attn, x))
+g2 = rnd(B, LREF, C)
+put("sattn", g=g2.bfloat16(), out_g=sproc(attn, x, sa_hidden_states={NAME: g2}))
+rcproc = ref_ap.RefCAttnProcessor2_0(NAME.replace("attn1", "attn2"), C, 256, scale=0.7)
+fill_(rcproc)
+NAME2 = NAME.replace("attn1", "attn2")
+put("refc.proc", rcproc)
+put("refc", out=rcproc(attn2, x, encoder_hidden_states=t, sa_hidden_states={NAME2: g2}),
+    out_nosa=rcproc(attn2, x, encoder_hidden_states=t))
 
 dst = os.path.join(ROOT, "tests", "golden", "processors.safetensors")
 save_file(out, dst, metadata={"generator": "oracle/make_golden.py", "reference": "/root/reference @ 2e8a2bd",

@@ -74,6 +74,49 @@ class CAttnProcessor(nn.Module):
         return attn.to_out[1](attn.to_out[0](o))
 
 
+class SAttnProcessor(nn.Module):
+    """SAttnProcessor2_0 (attention_processor.py:103-200): ONE softmax over the concatenated keys — for self-attention with
+    garment features the context is cat([hidden_states, sa_hidden_states[name]], dim=1) (:155-161), projected by the layer's
+    own to_k / to_v."""
+
+    def __init__(self, name, hidden_size=None, cross_attention_dim=None):
+        super().__init__()
+        self.name = name
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
+                 cond_hidden_states=None, sa_hidden_states=None):
+        B = hidden_states.shape[0]
+        if encoder_hidden_states is None:
+            ctx = hidden_states if sa_hidden_states is None else torch.cat([hidden_states, sa_hidden_states[self.name]], 1)
+        else:
+            ctx = encoder_hidden_states
+        o = _sdpa(attn.to_q(hidden_states), attn.to_k(ctx), attn.to_v(ctx), B, attn.heads)  # :163-182
+        return attn.to_out[1](attn.to_out[0](o))
+
+
+class RefCAttnProcessor(nn.Module):
+    """RefCAttnProcessor2_0 (attention_processor.py:630-744): (cross-)attention + scale * SDPA(q, to_k_ref(g), to_v_ref(g));
+    to_k_ref / to_v_ref take hidden_size inputs (:643-644)."""
+
+    def __init__(self, name, hidden_size, cross_attention_dim=None, scale=1.0):
+        super().__init__()
+        self.name = name
+        self.to_k_ref = nn.Linear(hidden_size, hidden_size, bias=False)
+        self.to_v_ref = nn.Linear(hidden_size, hidden_size, bias=False)
+        self.scale = scale
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0,
+                 cond_hidden_states=None, sa_hidden_states=None):
+        B = hidden_states.shape[0]
+        ctx = hidden_states if encoder_hidden_states is None else encoder_hidden_states
+        q = attn.to_q(hidden_states)
+        o = _sdpa(q, attn.to_k(ctx), attn.to_v(ctx), B, attn.heads)  # :691-706
+        if sa_hidden_states is not None:  # :709-727
+            g = sa_hidden_states[self.name]
+            o = o + _sdpa(q, self.to_k_ref(g), self.to_v_ref(g), B, attn.heads) * self.scale
+        return attn.to_out[1](attn.to_out[0](o))
+
+
 class LoRALinear(nn.Module):
     """diffusers-0.24 LoRALinearLayer with network_alpha=None: up(down(x))."""
 

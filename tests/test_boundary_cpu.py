@@ -196,3 +196,40 @@ def test_scale_change_and_processor_reload_between_calls(emu):
     c = pipe(guidance_scale=7.5, image_scale=0.3, **common(x)).images
     ref_c = sample_one(o, ro, x["latents"], x["prompt"], x["negative"], x["gtok"], x["garment"], 7.5, STEPS)
     assert rel(c, ref_c) < 4e-2 and rel(b, ref_c) > rel(c, ref_c)
+
+
+@torch.no_grad()
+def test_sattn_and_refc_drop_ins_match_reference_goldens(monkeypatch):
+    """SAttnProcessor2_0 (concat-KV single softmax, reference :103-200) and RefCAttnProcessor2_0 (cross-attention + reference
+    branch, :630-744) — installed by no reference script, implemented all the same — through the drop-in classes with the
+    kernel wrappers emulated, against goldens produced by the reference's own classes (oracle/make_golden.py)."""
+    import os
+
+    from safetensors import safe_open
+
+    import emulated_ops
+
+    emulated_ops.install(monkeypatch)
+    import adapter.attention_processor as ap
+    from imagdressing_b200.modeling import Attention
+
+    with safe_open(os.path.join(os.path.dirname(__file__), "golden", "processors.safetensors"), "pt") as f:
+        gold = {k: f.get_tensor(k) for k in f.keys()}
+
+    def load(module, prefix):
+        module.load_state_dict({k[len(prefix) + 3:]: v.float() for k, v in gold.items() if k.startswith(prefix + ".w.")})
+        return module
+
+    rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm())
+    name = "down_blocks.0.attentions.0.transformer_blocks.0.attn1.processor"
+    name2 = name.replace("attn1", "attn2")
+    C, H = 160, 4
+    attn, attn2 = load(Attention(C, None, H), "refs"), load(Attention(C, 256, H), "cattn")
+    x, g2, t = gold["refs.x"], gold["sattn.g"], gold["cattn.t"]
+    sp = ap.SAttnProcessor2_0(name, C)
+    assert rel(sp(attn, x, sa_hidden_states={name: g2}), gold["sattn.out_g"]) < 1e-2
+    assert rel(sp(attn, x), gold["sattn.out_nosa"]) < 1e-2
+    rc = load(ap.RefCAttnProcessor2_0(name2, C, 256, scale=0.7), "refc.proc")
+    assert rel(rc(attn2, x, encoder_hidden_states=t, sa_hidden_states={name2: g2}), gold["refc.out"]) < 1e-2
+    assert rel(rc(attn2, x, encoder_hidden_states=t), gold["refc.out_nosa"]) < 1e-2
+    assert set(rc.state_dict()) == {"to_k_ref.weight", "to_v_ref.weight"}

@@ -53,6 +53,15 @@ def test_processors_vs_reference_goldens(cuda_device, gold):
     ip = load(ap.LoRAIPAttnProcessor2_0(C, 256, rank=16, lora_scale=0.2, scale=0.9, num_tokens=4), gold, "loraip.proc", dev)
     assert rel_l2(ip(attn2, x, encoder_hidden_states=gold["loraip.t"]), gold["loraip.out"]) < TOL
     assert rel_l2(ip(attn2, x, encoder_hidden_states=gold["cattn.t"]), gold["loraip.out_noface"]) < TOL  # quirk B11
+    # the two classes no reference script installs: concat-KV single softmax, cross-attention + reference branch
+    sp = ap.SAttnProcessor2_0(NAME, C).to(dev)
+    assert rel_l2(sp(attn, x, sa_hidden_states={NAME: gold["sattn.g"]}), gold["sattn.out_g"]) < TOL
+    assert rel_l2(sp(attn, x), gold["sattn.out_nosa"]) < TOL
+    name2 = NAME.replace("attn1", "attn2")
+    rc = load(ap.RefCAttnProcessor2_0(name2, C, 256, scale=0.7), gold, "refc.proc", dev)
+    assert rel_l2(rc(attn2, x, encoder_hidden_states=gold["cattn.t"], sa_hidden_states={name2: gold["sattn.g"]}),
+                  gold["refc.out"]) < TOL
+    assert rel_l2(rc(attn2, x, encoder_hidden_states=gold["cattn.t"]), gold["refc.out_nosa"]) < TOL
     # mutable scales take effect (set_scale / set_ipa_scale path): scale 0 == no second stream
     p.scale = 0.0
     assert rel_l2(p(attn, x, sa_hidden_states={NAME: g}), gold["refs.out_nosa"]) < TOL
