@@ -515,15 +515,32 @@ def load_checkpoint(load_dir: str, sd_model: "SDModel", optimizer: Optional[Flat
     return int(st["epoch"]), int(st["last_global_step"])
 
 
+def compute_snr(scheduler, timesteps: torch.Tensor) -> torch.Tensor:
+    """SNR(t) = abar_t / (1 - abar_t)   (train.py:214-241)."""
+    a = scheduler.alphas_cumprod.to(timesteps.device)[timesteps].float()
+    return a / (1.0 - a)
+
+
+def training_loss(pred: torch.Tensor, target: torch.Tensor, scheduler=None, timesteps=None, snr_gamma: float = 0.0):
+    """train.py:573-596 for the epsilon objective: plain MSE (snr_gamma == 0, the script's default) or min-SNR-gamma weighting,
+    mean_b( mean((pred_b - target_b)^2) * min(snr_b, gamma) / snr_b ) — the per-sample weight enters as sqrt(w_b) on both
+    operands of the MSE kernel (mean over all elements of w_b d^2 is the same number)."""
+    if snr_gamma == 0:
+        return ag.mse_loss(pred.float(), target.float())
+    snr = compute_snr(scheduler, timesteps)
+    w = (torch.minimum(snr, torch.full_like(snr, float(snr_gamma))) / snr).sqrt().view(-1, *([1] * (pred.dim() - 1)))
+    return ag.mse_loss(pred.float() * w, target.float() * w)
+
+
 def train_step(sd_model: SDModel, scheduler, latents, ref_latents, clip_image_embeddings, encoder_hidden_states, noise,
-               timesteps, optimizer: Optional[FlatAdamW] = None) -> torch.Tensor:
-    """One micro-batch of train.py:527-609 after the frozen VAE / CLIP encoders: add noise, predict, MSE against the noise,
-    backward, (optimizer step). Returns the detached loss."""
+               timesteps, optimizer: Optional[FlatAdamW] = None, snr_gamma: float = 0.0) -> torch.Tensor:
+    """One micro-batch of train.py:527-609 after the frozen VAE / CLIP encoders: add noise, predict, MSE against the noise
+    (optionally min-SNR-gamma weighted), backward, (optimizer step). Returns the detached loss."""
     if optimizer is not None:
         optimizer.zero_grad()
     noisy = scheduler.add_noise(latents, noise, timesteps)                                                        # :545
     pred = sd_model(encoder_hidden_states, noisy, ref_latents, clip_image_embeddings, timesteps)                  # :565-571
-    loss = ag.mse_loss(pred.float(), noise.float())                                                                # :577
+    loss = training_loss(pred, noise, scheduler, timesteps, snr_gamma)                                             # :575-596
     loss.backward()                                                                                                # :603
     if optimizer is not None:
         optimizer.step()                                                                                           # :604

@@ -250,6 +250,24 @@ def test_sdmodel_step_matches_oracle(emu):
     assert (num / den) ** 0.5 < 3e-2, ((num / den) ** 0.5, worst)
 
 
+def test_min_snr_gamma_loss_matches_oracle(emu):
+    """train.py:579-596: loss = mean_b(mse_b * min(snr_b, gamma) / snr_b), forward value and gradient."""
+    from imagdressing_b200 import train
+    from imagdressing_b200.scheduler import DDIMScheduler
+
+    sched = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False)
+    t = torch.tensor([5, 400, 990])
+    pred, tgt = rb(3, 4, 6, 6, seed=1), rb(3, 4, 6, 6, seed=2)
+    (pl,) = leaves(pred)
+    lo = ts.training_loss(pl, tgt, DDIMOracle().alphas_cumprod, t, snr_gamma=5.0)
+    lo.backward()
+    (pp,) = leaves(pred)
+    lp = train.training_loss(pp, tgt, sched, t, snr_gamma=5.0)
+    lp.backward()
+    assert abs(float(lp) - float(lo)) < 1e-6 * abs(float(lo)) + 1e-9 and rel(pp.grad, pl.grad) < 1e-5
+    assert torch.allclose(train.compute_snr(sched, t), ts.compute_snr(DDIMOracle().alphas_cumprod, t), rtol=1e-5)
+
+
 def test_flat_adamw_updates_views(emu):
     from imagdressing_b200 import train
 
