@@ -178,3 +178,33 @@ def test_graphed_step_equals_eager_step(cuda_device):
     for a, g in zip(eager, graphed):
         assert abs(a - g) <= 1e-5 * abs(a)
     assert rel(after_graphed, opt.param) < 1e-4
+
+
+def test_adamw_steps_track_the_oracle_trajectory(cuda_device):
+    """Three optimizer steps on one batch: the kernels' step (bf16 working weights, fp32 master weights in FlatAdamW) against
+    the fp32 oracle trained with torch.optim.AdamW at the same hyper-parameters — the loss trajectories must coincide (the
+    reference trains this way under DeepSpeed bf16, train.py:386-398,573-609)."""
+    from imagdressing_b200 import train
+    from imagdressing_b200.scheduler import DDIMScheduler
+    from oracle import train_step as ts
+    from oracle.ddim import DDIMOracle
+
+    dev = cuda_device
+    (o_unet, o_ref, o_proj, o_ad), (p_unet, p_ref, p_proj, p_ad) = build(dev)
+    b = batch(dev, 2, 16, 16)
+    hp = dict(lr=2e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    o_params = ts.set_trainable(o_unet, o_ref, o_proj, o_ad)
+    o_opt = torch.optim.AdamW(o_params, **hp)
+    sd = train.SDModel(p_unet, p_ref, p_proj, p_ad)
+    p_opt = train.FlatAdamW(train.set_trainable(p_unet, p_ref, p_proj, p_ad), **hp)
+    sched = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False)
+    lo, lp = [], []
+    for _ in range(3):
+        o_opt.zero_grad(set_to_none=True)
+        lo.append(float(ts.train_step(o_unet, o_ref, o_proj, DDIMOracle(), **b)))
+        o_opt.step()
+        lp.append(float(train.train_step(sd, sched, optimizer=p_opt, **b)))
+    print("loss trajectory: oracle fp32 + torch AdamW", [round(v, 5) for v in lo], "| kernels + FlatAdamW", [round(v, 5) for v in lp])
+    for a, g in zip(lo, lp):
+        assert abs(a - g) < 2e-2 * abs(a)
+    assert lo[2] < lo[0] and lp[2] < lp[0]
