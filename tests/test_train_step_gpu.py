@@ -182,8 +182,10 @@ def test_graphed_step_equals_eager_step(cuda_device):
 
 def test_adamw_steps_track_the_oracle_trajectory(cuda_device):
     """Three optimizer steps on one batch: the kernels' step (bf16 working weights, fp32 master weights in FlatAdamW) against
-    the fp32 oracle trained with torch.optim.AdamW at the same hyper-parameters — the loss trajectories must coincide (the
-    reference trains this way under DeepSpeed bf16, train.py:386-398,573-609)."""
+    the oracle trained in the SAME regime with torch.optim.AdamW — fp32 master parameters, every forward / backward on their
+    bf16-rounded values (the reference trains this way under DeepSpeed bf16, train.py:386-398,573-609). A plain fp32 oracle is
+    NOT comparable here: at lr 2e-5 the first Adam update (+-lr per weight) is below half a bf16 ulp of most weights, so the
+    bf16 working copy barely moves while fp32 weights all do (measured: loss 1.34 -> 2.00 in fp32, 1.34 -> 1.38 in bf16)."""
     from imagdressing_b200 import train
     from imagdressing_b200.scheduler import DDIMScheduler
     from oracle import train_step as ts
@@ -201,10 +203,19 @@ def test_adamw_steps_track_the_oracle_trajectory(cuda_device):
     lo, lp = [], []
     for _ in range(3):
         o_opt.zero_grad(set_to_none=True)
+        master = [p.detach().clone() for p in o_params]
+        with torch.no_grad():
+            for p in o_params:
+                p.copy_(p.to(BF).float())  # the working copy the model computes with
         lo.append(float(ts.train_step(o_unet, o_ref, o_proj, DDIMOracle(), **b)))
+        with torch.no_grad():
+            for p, m in zip(o_params, master):
+                p.copy_(m)  # the update applies to the fp32 master weights
         o_opt.step()
         lp.append(float(train.train_step(sd, sched, optimizer=p_opt, **b)))
-    print("loss trajectory: oracle fp32 + torch AdamW", [round(v, 5) for v in lo], "| kernels + FlatAdamW", [round(v, 5) for v in lp])
+    print("loss trajectory: oracle (fp32 master, bf16 working copy) + torch AdamW", [round(v, 5) for v in lo],
+          "| kernels + FlatAdamW", [round(v, 5) for v in lp])
     for a, g in zip(lo, lp):
         assert abs(a - g) < 2e-2 * abs(a)
-    assert lo[2] < lo[0] and lp[2] < lp[0]
+    # the parameters themselves: the garment UNet's first conv after three steps
+    assert rel(p_ref.conv_in.weight, o_ref.conv_in.weight.to(BF)) < 2e-3
