@@ -17,6 +17,7 @@ backward; all arithmetic is in libimagd_b200.so.
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, Iterable, List, Optional
 
 import torch
@@ -287,16 +288,23 @@ class FlatAdamW:
     fp32 master weights and moments live beside them. With torch.distributed initialised, the gradient buffer is reduced in
     buckets: each parameter's post-accumulate hook counts its bucket down and the completed bucket's all-reduce is launched
     at once (NCCL over NVLink on its own stream), overlapping the remaining backward pass; step() waits for the handles and
-    applies the update with the 1/world scale folded into the kernel."""
+    applies the update with the 1/world scale folded into the kernel.
+
+    accumulation_steps = k (train.py:106-111, :606 `--gradient_accumulation_steps`): k micro-steps share one update. The first
+    micro-step's gradients are copied into the flat buffer, the following ones added to it (bf16 sums), the bucket all-reduces
+    are launched by the LAST micro-step only, step() returns False without touching the weights until then, and 1/k joins
+    1/world in the kernel's gradient scale."""
 
     def __init__(self, params: Iterable[nn.Parameter], lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
-                 bucket_bytes: int = 256 << 20, step_fn=None, shard_states: bool = False):
+                 bucket_bytes: int = 256 << 20, step_fn=None, shard_states: bool = False, accumulation_steps: int = 1):
         seen = set()
         self.params = [p for p in params if p.requires_grad and not (id(p) in seen or seen.add(id(p)))]  # de-duplicated
         assert self.params, "no trainable parameters"
         dev = self.params[0].device
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.t = 0
+        self.accum = max(1, int(accumulation_steps))
+        self._micro = 0  # index of the running micro-step inside its accumulation window
         self._step_fn = step_fn  # test hook with the host-scalar signature of ops.adamw_step; None = the device-scalar kernel
         # backward produces gradients roughly in reverse registration order: lay the buffer out reversed so that buckets
         # complete front to back
@@ -321,7 +329,7 @@ class FlatAdamW:
         self.v = torch.zeros(n_own, device=dev, dtype=torch.float32)
         # {lr, weight_decay, step, grad_scale} in device memory: what the update kernel reads, so a captured CUDA graph of the
         # step replays with a moving step count / learning-rate schedule (set_lr rewrites it between replays)
-        self.hyper = torch.tensor([lr, weight_decay, 0.0, 1.0 / world], device=dev, dtype=torch.float32)
+        self.hyper = torch.tensor([lr, weight_decay, 0.0, 1.0 / (world * self.accum)], device=dev, dtype=torch.float32)
         off = 0
         self._spans = []
         self._gviews = []  # per parameter: its slot of the flat gradient buffer
@@ -359,9 +367,12 @@ class FlatAdamW:
         idx = self._ready[bucket]
         if idx:
             with torch.no_grad():
-                torch._foreach_copy_([self._gviews[i] for i in idx], [self._order[i].grad for i in idx])
+                if self._micro == 0:
+                    torch._foreach_copy_([self._gviews[i] for i in idx], [self._order[i].grad for i in idx])
+                else:
+                    torch._foreach_add_([self._gviews[i] for i in idx], [self._order[i].grad for i in idx])
             self._ready[bucket] = []
-        if self._dist:
+        if self._dist and self._micro == self.accum - 1:
             lo, hi, _ = self._buckets[bucket]
             self._handles.append(torch.distributed.all_reduce(self.grad[lo:hi], async_op=True))
 
@@ -374,7 +385,9 @@ class FlatAdamW:
         return hook
 
     def zero_grad(self):
-        self.grad.zero_()
+        """Start of a micro-step. Inside an accumulation window (after its first micro-step) the flat buffer keeps its sums."""
+        if self._micro == 0:
+            self.grad.zero_()
         for p in self.params:
             p.grad = None
         self._pending = [b[2] for b in self._buckets]
@@ -391,10 +404,15 @@ class FlatAdamW:
             h.wait()
         self._handles = []
 
-    def step(self):
+    def step(self) -> bool:
+        """End of a micro-step; True when the weights were updated (the accumulation window closed)."""
         self.reduce_remaining()
+        if self._micro < self.accum - 1:
+            self._micro += 1
+            return False
+        self._micro = 0
         self.t += 1
-        world = torch.distributed.get_world_size() if self._dist else 1
+        world = (torch.distributed.get_world_size() if self._dist else 1) * self.accum
         lo, hi = self._own
         self.hyper[2:3].add_(1.0)  # device-side step count (a kernel, so it is part of a captured graph)
         if self._step_fn is not None:
@@ -408,7 +426,7 @@ class FlatAdamW:
         # the kernel wrote through raw pointers: bump the version counters so that weight-derived caches keyed on
         # (data_ptr, _version) — processors._ver, autograd._cached — see the update
         torch.autograd.graph.increment_version([self.param, *self.params])
-
+        return True
 
     def set_lr(self, lr: float, weight_decay: Optional[float] = None) -> None:
         """Learning-rate schedule hook: rewrites the device-side scalars (outside any graph capture)."""
@@ -424,6 +442,7 @@ class FlatAdamW:
         self.v.zero_()
         self.hyper[2:3].zero_()
         self.t = 0
+        self._micro = 0
 
     def state_dict(self) -> Dict[str, object]:
         return {"t": self.t, "own": self._own, "master": self.master, "m": self.m, "v": self.v,
@@ -441,6 +460,86 @@ class FlatAdamW:
         if self.shard:
             torch.distributed.all_gather_into_tensor(self.param, self.param[self._own[0]:self._own[1]].clone())
         torch.autograd.graph.increment_version([self.param, *self.params])
+
+
+# ------------------------------------------------------------------------------------------------ learning-rate schedule
+LR_SCHEDULES = ("linear", "cosine", "cosine_with_restarts", "polynomial", "constant", "constant_with_warmup")  # train.py:129
+
+
+def lr_multiplier(name: str, step: int, num_warmup_steps: int = 0, num_training_steps: Optional[int] = None,
+                  num_cycles: Optional[float] = None, power: float = 1.0, lr_init: float = 1.0, lr_end: float = 1e-7) -> float:
+    """The factor on the base learning rate after `step` updates, for the six schedule names train.py:125-130 accepts and
+    hands to diffusers.optimization.get_scheduler (train.py:433-439; diffusers==0.24.0 per requirements.txt:12 — not in this
+    image; its schedules are the published transformers ones, and tests pin this restatement against
+    transformers.optimization.get_scheduler): linear warm-up from 0 over num_warmup_steps, then
+      constant / constant_with_warmup : 1
+      linear                          : (T - s) / (T - W), floored at 0
+      cosine                          : 0.5 (1 + cos(2 pi c p)), c = 0.5 cycles, p = (s - W) / (T - W)
+      cosine_with_restarts            : 0.5 (1 + cos(pi (c p mod 1))), c = 1 cycle, 0 once p >= 1
+      polynomial                      : ((lr_init - lr_end) (1 - p)^power + lr_end) / lr_init, lr_end / lr_init after T."""
+    if name not in LR_SCHEDULES:
+        raise ValueError(f"unknown lr scheduler {name!r}; one of {LR_SCHEDULES}")
+    s, W = int(step), int(num_warmup_steps)
+    if name == "constant":
+        return 1.0
+    if s < W:
+        return s / float(max(1, W))
+    if name == "constant_with_warmup":
+        return 1.0
+    if num_training_steps is None:
+        raise ValueError(f"lr scheduler {name!r} needs num_training_steps")
+    T = int(num_training_steps)
+    if name == "linear":
+        return max(0.0, (T - s) / float(max(1, T - W)))
+    progress = (s - W) / float(max(1, T - W))
+    if name == "cosine":
+        c = 0.5 if num_cycles is None else float(num_cycles)
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * c * 2.0 * progress)))
+    if name == "cosine_with_restarts":
+        c = 1.0 if num_cycles is None else float(num_cycles)
+        if progress >= 1.0:
+            return 0.0
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * ((c * progress) % 1.0))))
+    # polynomial
+    if s > T:
+        return lr_end / lr_init
+    remaining = 1.0 - (s - W) / float(T - W)
+    return ((lr_init - lr_end) * remaining ** power + lr_end) / lr_init
+
+
+class LRScheduler:
+    """What train.py:433-439 builds and :608 / :618 use: `.step()` after every optimizer update, `.get_lr()[0]` for the log
+    line. The new rate goes into FlatAdamW's device-side scalar (set_lr), so a captured step graph replays with it."""
+
+    def __init__(self, name: str, optimizer: FlatAdamW, num_warmup_steps: int = 0, num_training_steps: Optional[int] = None,
+                 num_cycles: Optional[float] = None, power: float = 1.0):
+        self.name, self.opt = name, optimizer
+        self.base_lr = float(optimizer.lr)
+        self.kw = dict(num_warmup_steps=num_warmup_steps, num_training_steps=num_training_steps, num_cycles=num_cycles,
+                       power=power, lr_init=self.base_lr)
+        self.last_epoch = 0
+        self._apply()
+
+    def _apply(self) -> None:
+        self._lr = self.base_lr * lr_multiplier(self.name, self.last_epoch, **self.kw)
+        self.opt.set_lr(self._lr)
+
+    def step(self) -> None:
+        self.last_epoch += 1
+        self._apply()
+
+    def get_last_lr(self) -> List[float]:
+        return [self._lr]
+
+    get_lr = get_last_lr
+
+    def state_dict(self) -> Dict[str, object]:
+        return {"last_epoch": self.last_epoch, "base_lr": self.base_lr}
+
+    def load_state_dict(self, sd: Dict[str, object]) -> None:
+        self.last_epoch, self.base_lr = int(sd["last_epoch"]), float(sd["base_lr"])
+        self.kw["lr_init"] = self.base_lr
+        self._apply()
 
 
 # ------------------------------------------------------------------------------------------------ the callers' side of the step
@@ -560,6 +659,8 @@ class GraphedTrainStep:
 
     def __init__(self, sd_model: SDModel, scheduler, optimizer: FlatAdamW, example: Dict[str, torch.Tensor], warmup: int = 3):
         self.sd, self.sched, self.opt = sd_model, scheduler, optimizer
+        if optimizer.accum != 1:
+            raise ValueError("GraphedTrainStep captures one whole update; gradient accumulation runs through train_step")
         self.static = {k: v.detach().clone() for k, v in example.items()}
         self.static["noisy"] = scheduler.add_noise(example["latents"], example["noise"], example["timesteps"]).detach().clone()
         lr = optimizer.lr

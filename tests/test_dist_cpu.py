@@ -65,7 +65,7 @@ def test_shard_range_covers_everything():
 
 
 # ------------------------------------------------------------------------------------------------ training: gradient all-reduce
-def _train_worker(rank, world, port, out_q):
+def _train_worker(rank, world, port, out_q, accum=1):
     """Data-parallel step of FlatAdamW (imagdressing_b200/train.py; reference train.py:601-609 DeepSpeed gradient reduction):
     each rank back-propagates its own shard, the per-bucket hooks all-reduce the flat gradient buffer, the update uses the
     mean gradient — both ranks must end with the parameters of a single-process step on the whole batch."""
@@ -80,20 +80,29 @@ def _train_worker(rank, world, port, out_q):
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 4), torch.nn.Linear(4, 3)).to(torch.bfloat16)
     net[3].requires_grad_(False)  # a frozen tail layer: no hook fires for it, nothing is reduced for it
-    opt = train.FlatAdamW(net.parameters(), lr=1e-2, weight_decay=0.0, bucket_bytes=32, step_fn=emulated_ops.adamw_step)
+    opt = train.FlatAdamW(net.parameters(), lr=1e-2, weight_decay=0.0, bucket_bytes=32, step_fn=emulated_ops.adamw_step,
+                          accumulation_steps=accum)
     assert opt._dist and len(opt._buckets) >= 2
     x = torch.randn(8, 6, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16)
     lo, hi = shard_range(8, rank, world)
+    per = (hi - lo) // accum
+    reduces = []
+    real = dist.all_reduce
+    dist.all_reduce = lambda *a, **k: (reduces.append(opt._micro), real(*a, **k))[1]
     for _ in range(2):
-        opt.zero_grad()
-        net(x[lo:hi]).float().square().mean().backward()
-        opt.step()
+        for k in range(accum):  # train.py:606: the shard in `accum` micro-batches, one update
+            opt.zero_grad()
+            net(x[lo + k * per:lo + (k + 1) * per]).float().square().mean().backward()
+            assert opt.step() is (k == accum - 1)
+    dist.all_reduce = real
+    assert reduces and all(m == accum - 1 for m in reduces)  # gradients cross ranks in the window's last micro-step only
     out_q.put((rank, opt.param.float().numpy().copy(), opt.grad.float().numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_flat_adamw_gradient_allreduce_world2():
+@pytest.mark.parametrize("accum", [1, 2])
+def test_flat_adamw_gradient_allreduce_world2(accum):
     import sys
 
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -103,7 +112,7 @@ def test_flat_adamw_gradient_allreduce_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q, accum)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])

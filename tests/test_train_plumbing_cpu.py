@@ -150,3 +150,67 @@ def test_checkpoint_round_trip_in_deepspeed_layout(tmp_path, monkeypatch):
 
     fresh = modeling.UNet2DConditionModel(**CFG)
     fresh.load_state_dict({k[len("ref_unet."):]: v.float() for k, v in st["module"].items() if k.startswith("ref_unet.")})
+
+
+@pytest.mark.parametrize("name", ["linear", "cosine", "cosine_with_restarts", "polynomial", "constant", "constant_with_warmup"])
+def test_lr_schedules_match_the_published_ones(name):
+    """train.py:433-439 get_scheduler(args.lr_scheduler, optimizer, num_warmup_steps, num_training_steps) — diffusers 0.24.0
+    is not in this image; its schedules are transformers' (same formulas, same defaults), which IS here and is the oracle."""
+    from transformers.optimization import get_scheduler
+
+    from imagdressing_b200 import train
+
+    base, W, T = 1e-4, 3, 11
+    lin = torch.nn.Linear(4, 4).to(BF)
+    opt = train.FlatAdamW(lin.parameters(), lr=base, step_fn=emulated_ops.adamw_step)
+    mine = train.LRScheduler(name, opt, num_warmup_steps=W, num_training_steps=T)
+    ref_opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=base)
+    ref = get_scheduler(name, ref_opt, num_warmup_steps=W, num_training_steps=T)
+    for step in range(T + 4):
+        want = ref.get_last_lr()[0]
+        assert mine.get_lr()[0] == pytest.approx(want, rel=1e-12, abs=1e-18), (name, step)
+        assert opt.lr == mine.get_lr()[0] and float(opt.hyper[0]) == pytest.approx(want, rel=1e-6, abs=1e-12)  # device scalar
+        ref_opt.step()
+        ref.step()
+        mine.step()
+    resumed = train.LRScheduler(name, opt, num_warmup_steps=W, num_training_steps=T)
+    resumed.load_state_dict(mine.state_dict())
+    assert resumed.get_lr() == mine.get_lr() and resumed.last_epoch == T + 4
+    with pytest.raises(ValueError):
+        train.lr_multiplier("exponential", 0)
+
+
+def test_gradient_accumulation_equals_the_whole_batch_step(monkeypatch):
+    """train.py:606 `(step + 1) % gradient_accumulation_steps == 0`: k micro-batches, one update with the mean gradient."""
+    emulated_ops.install(monkeypatch)
+    from imagdressing_b200 import train
+
+    def make(accum):
+        torch.manual_seed(3)
+        net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 4)).to(BF)
+        return net, train.FlatAdamW(net.parameters(), lr=1e-2, weight_decay=0.01, bucket_bytes=32,
+                                    step_fn=emulated_ops.adamw_step, accumulation_steps=accum)
+
+    x = torch.randn(8, 6, generator=torch.Generator().manual_seed(1)).to(BF)
+    whole_net, whole = make(1)
+    acc_net, acc = make(4)
+    assert float(acc.hyper[3]) == 0.25
+    for _ in range(2):
+        whole.zero_grad()
+        whole_net(x).float().square().mean().backward()
+        assert whole.step() is True
+        before = acc.param.clone()
+        for k in range(4):
+            acc.zero_grad()
+            acc_net(x[2 * k:2 * k + 2]).float().square().mean().backward()
+            updated = acc.step()
+            assert updated is (k == 3)
+            if k < 3:
+                assert torch.equal(acc.param, before)  # nothing moves inside the window
+        assert not torch.equal(acc.param, before)
+        g_acc, g_whole = acc.grad.float() / 4, whole.grad.float()  # the window's summed gradient, scaled as the kernel does
+        assert float((g_acc - g_whole).norm() / g_whole.norm()) < 2e-2
+    assert acc.t == 2 and whole.t == 2
+    assert float((acc.param.float() - whole.param.float()).abs().max()) < 2e-2  # bf16 gradient sums vs one bf16 gradient
+    with pytest.raises(ValueError):
+        train.GraphedTrainStep(None, None, acc, {})
