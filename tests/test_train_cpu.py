@@ -288,3 +288,50 @@ def test_flat_adamw_updates_views(emu):
     for p, q in zip(lin.parameters(), ref.parameters()):
         assert p.dtype == BF and rel(p, q) < 2e-2
         assert p.data_ptr() >= opt.param.data_ptr() and p.data_ptr() < opt.param.data_ptr() + opt.param.numel() * 2
+
+
+def test_accumulation_window_and_schedule_through_the_whole_step(emu):
+    """CPU twin of tests/test_train_step_gpu.py::test_gradient_accumulation_and_lr_schedule_on_the_kernels (train.py:606-608):
+    two one-sample micro-steps with accumulation_steps=2 against one step on the batch of two; LRScheduler's rate reaches the
+    update through the device-side scalar."""
+    from imagdressing_b200 import train
+    from imagdressing_b200.scheduler import DDIMScheduler
+
+    _, (p_unet, p_ref, p_proj, p_ad) = build_pair()
+    sd = train.SDModel(p_unet, p_ref, p_proj, p_ad)
+    for m in (p_unet, p_ref, p_proj):
+        m.to(BF)
+    params = train.set_trainable(p_unet, p_ref, p_proj, p_ad)
+    sched = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False)
+    b = batch()
+    opt = train.FlatAdamW(params, lr=1e-3, weight_decay=1e-2, accumulation_steps=2)
+    start = (opt.param.clone(), opt.master.clone())
+    lrs = train.LRScheduler("constant_with_warmup", opt, num_warmup_steps=1)
+    assert lrs.get_lr()[0] == 0.0 and float(opt.hyper[0]) == 0.0 and float(opt.hyper[3]) == 0.5
+
+    def window():
+        out = []
+        for k in range(2):
+            out.append(float(train.train_step(sd, sched, **{key: v[k:k + 1] for key, v in b.items()}, optimizer=opt)))
+            assert opt._micro == (1 if k == 0 else 0)
+        return out
+
+    window()
+    assert opt.t == 1 and torch.equal(opt.param, start[0])  # rate 0: nothing moves
+    lrs.step()
+    opt.reset_state()
+    l_acc = window()
+    g_acc, p_acc = opt.grad.float().clone() * 0.5, opt.param.float().clone()
+    assert not torch.equal(opt.param, start[0])
+    with torch.no_grad():
+        opt.param.copy_(start[0])
+        opt.master.copy_(start[1])
+    opt.reset_state()
+    opt.accum = 1
+    opt.hyper[3:4].fill_(1.0)
+    torch.autograd.graph.increment_version([opt.param, *opt.params])
+    l_whole = float(train.train_step(sd, sched, **b, optimizer=opt))
+    assert abs(0.5 * (l_acc[0] + l_acc[1]) - l_whole) < 2e-3 * abs(l_whole)
+    assert rel(g_acc, opt.grad.float()) < 2e-2
+    moved = (opt.param.float() - start[0].float()).abs().mean()
+    assert float((p_acc - opt.param.float()).abs().mean()) < 0.1 * float(moved)

@@ -219,3 +219,59 @@ def test_adamw_steps_track_the_oracle_trajectory(cuda_device):
         assert abs(a - g) < 2e-2 * abs(a)
     # the parameters themselves: the garment UNet's first conv after three steps
     assert rel(p_ref.conv_in.weight, o_ref.conv_in.weight.to(BF)) < 2e-3
+
+
+def test_gradient_accumulation_and_lr_schedule_on_the_kernels(cuda_device):
+    """train.py:606-608: two micro-batches of one sample with accumulation_steps=2 against ONE step on the batch of two, from
+    the same weights, through the real kernels (gradient hand-over copy-then-add, 1/k in adamw_dev_kernel's scale); and the
+    LRScheduler's rate reaching the update kernel through the device scalar (a warm-up step at rate 0 moves nothing)."""
+    from imagdressing_b200 import train
+    from imagdressing_b200.scheduler import DDIMScheduler
+
+    dev = cuda_device
+    _, (p_unet, p_ref, p_proj, p_ad) = build(dev)
+    sd = train.SDModel(p_unet, p_ref, p_proj, p_ad)
+    params = train.set_trainable(p_unet, p_ref, p_proj, p_ad)
+    sched = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False)
+    b = batch(dev, 2, 16, 16)
+    opt = train.FlatAdamW(params, lr=1e-3, weight_decay=1e-2, accumulation_steps=2)
+    start = (opt.param.clone(), opt.master.clone())
+    lrs = train.LRScheduler("constant_with_warmup", opt, num_warmup_steps=1)
+    assert lrs.get_lr()[0] == 0.0 and float(opt.hyper[0]) == 0.0 and float(opt.hyper[3]) == 0.5
+
+    def window():
+        losses = []
+        for k in range(2):
+            mb = {key: v[k:k + 1] for key, v in b.items()}
+            losses.append(float(train.train_step(sd, sched, **mb, optimizer=opt)))
+            if k == 0:
+                assert opt._micro == 1
+        return losses
+
+    window()  # schedule step 0: rate 0 -> the weights stay put (moments do move)
+    assert opt.t == 1 and torch.equal(opt.param, start[0])
+    lrs.step()
+    assert lrs.get_lr()[0] == 1e-3
+    opt.reset_state()
+    l_acc = window()
+    g_acc = opt.grad.float().clone() * 0.5
+    p_acc = opt.param.float().clone()
+    assert not torch.equal(opt.param, start[0])
+
+    with torch.no_grad():  # back to the start, one whole-batch step with a plain optimizer state
+        opt.param.copy_(start[0])
+        opt.master.copy_(start[1])
+    opt.reset_state()
+    opt.accum = 1
+    opt.hyper[3:4].fill_(1.0)
+    torch.autograd.graph.increment_version([opt.param, *opt.params])
+    l_whole = float(train.train_step(sd, sched, **b, optimizer=opt))
+    g_whole = opt.grad.float()
+    print("accumulated", l_acc, "whole", l_whole, "grad rel", rel(g_acc, g_whole))
+    assert abs(0.5 * (l_acc[0] + l_acc[1]) - l_whole) < 2e-3 * abs(l_whole)  # mean of per-sample MSEs = batch MSE
+    # per-sample gradients summed in bf16 vs the batch gradient: GroupNorm / attention are per sample, so only rounding differs
+    assert rel(g_acc, g_whole) < 2e-2
+    # Adam's first update is lr * sign(g) almost everywhere: the two end states differ only where a near-zero gradient rounds
+    # to the other sign
+    moved = (opt.param.float() - start[0].float()).abs().mean()
+    assert float((p_acc - opt.param.float()).abs().mean()) < 0.1 * float(moved)
