@@ -1,5 +1,7 @@
 // GroupNorm (+SiLU) and LayerNorm over token-major bf16 activations. HBM/L2-bound: every element is read with
 // 128-bit loads, statistics are fp32 with fixed-order (bit-reproducible) reductions.
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -272,6 +274,186 @@ __global__ void __launch_bounds__(kGnThreads, 2) groupnorm_fused_kernel(
     }
 }
 
+// Cluster GroupNorm for the latency-bound regime (batch 1: a handful of CTAs per sample, where the L2 rendezvous of the
+// kernel above costs more than the data movement). A cluster of kGnCS CTAs owns one (sample, slice of whole groups):
+// CTA r keeps rows [r * rpc, (r + 1) * rpc) x the slice's channels IN SHARED MEMORY, so every element is read from
+// global memory exactly once; the per-CTA {mean, M2} partials are exchanged through distributed shared memory between
+// two cluster barriers (no L2 atomics, no co-residency assumption, clusters are independent), merged by every CTA in
+// rank order (bit-reproducible, same shifted / Chan arithmetic as above), and the tile is normalised out of shared memory.
+constexpr int kGnCS = 8;  // portable cluster size
+__global__ void __launch_bounds__(kGnThreads, 2) groupnorm_cluster_kernel(
+    const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y, int64_t ldy, int HW, int C,
+    int groups, int gps, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int fuse_silu,
+    float* __restrict__ stats_out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float s_a[kGnThreads * 8];  // phase 1: per (row slot, channel) sums      | phase 2: per-channel scale
+    __shared__ float s_b[kGnThreads * 8];  // phase 1: per (row slot, channel) sum of sq | phase 2: per-channel shift
+    __shared__ float s_part[64 * 2];       // my {mean, M2} per group of the slice: what the other CTAs of the cluster read
+    __shared__ float s_mean[64];
+    __shared__ float s_rstd[64];
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    const int cpg = C / groups;
+    const int SC = gps * cpg;  // channels of my slice (multiple of 8)
+    const int SV = SC / 8;
+    float* s_gamma = reinterpret_cast<float*>(s_dyn);
+    float* s_beta = s_gamma + SC;
+    float* s_piv = s_beta + SC;
+    uint4* tile = reinterpret_cast<uint4*>(s_dyn + ((3 * SC * sizeof(float) + 15) / 16) * 16);
+    const int rank = static_cast<int>(cluster.block_rank());
+    const int slice = blockIdx.x / kGnCS, n = blockIdx.y;
+    const int c_base = slice * SC;
+    const int rpc = (HW + kGnCS - 1) / kGnCS;
+    const int p_begin = min(HW, rank * rpc);
+    const int p_end = min(HW, p_begin + rpc);
+    for (int c = threadIdx.x; c < SC; c += kGnThreads) {
+        s_gamma[c] = gamma ? __ldg(gamma + c_base + c) : 1.f;
+        s_beta[c] = beta ? __ldg(beta + c_base + c) : 0.f;
+    }
+    // ---------------- phase 1: my rows -> shared memory, shifted per-channel sums on the way
+    const int cv = threadIdx.x % SV;
+    const int prow = threadIdx.x / SV;
+    const int rows = kGnThreads / SV;  // row slots (>= 1: SC <= kGnMaxC)
+    if (prow < rows) {
+        float sum[8], sq[8], piv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum[k] = sq[k] = piv[k] = 0.f;
+        const __nv_bfloat16* base = x + (static_cast<int64_t>(n) * HW) * ldx + c_base + cv * 8;
+        if (p_begin < p_end) {
+            const uint4 pv = __ldg(reinterpret_cast<const uint4*>(base + static_cast<int64_t>(p_begin) * ldx));
+            const uint32_t u[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                piv[2 * k] = bf16lo(u[k]);
+                piv[2 * k + 1] = bf16hi(u[k]);
+            }
+        }
+        if (prow == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s_piv[cv * 8 + k] = piv[k];
+        }
+        for (int pix = p_begin + prow; pix < p_end; pix += rows * 4) {
+            uint4 v[4];
+            float live[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                v[t] = make_uint4(0u, 0u, 0u, 0u);
+                live[t] = 0.f;
+                if (pix + t * rows < p_end) {
+                    v[t] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<int64_t>(pix + t * rows) * ldx));
+                    live[t] = 1.f;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                if (pix + t * rows < p_end) tile[(pix + t * rows - p_begin) * SV + cv] = v[t];
+                const uint32_t u[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float a = (bf16lo(u[k]) - piv[2 * k]) * live[t], b = (bf16hi(u[k]) - piv[2 * k + 1]) * live[t];
+                    sum[2 * k] += a;
+                    sq[2 * k] += a * a;
+                    sum[2 * k + 1] += b;
+                    sq[2 * k + 1] += b * b;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            s_a[prow * SC + cv * 8 + k] = sum[k];
+            s_b[prow * SC + cv * 8 + k] = sq[k];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < SC; c += kGnThreads) {  // fold the row slots (fixed order)
+        float a = s_a[c], b = s_b[c];
+        for (int r = 1; r < rows; ++r) {
+            a += s_a[r * SC + c];
+            b += s_b[r * SC + c];
+        }
+        s_a[c] = a;
+        s_b[c] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x < gps) {  // channels -> group, Chan's formula (as in groupnorm_fused_kernel)
+        const int g = threadIdx.x;
+        const float npix = static_cast<float>(p_end - p_begin);
+        const float inv = npix > 0.f ? 1.f / npix : 0.f;
+        float mean_g = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) mean_g += s_piv[c] + s_a[c] * inv;
+        mean_g /= static_cast<float>(cpg);
+        float m2 = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            const float d = s_piv[c] + s_a[c] * inv - mean_g;
+            m2 += (s_b[c] - s_a[c] * s_a[c] * inv) + npix * d * d;
+        }
+        s_part[2 * g] = npix > 0.f ? mean_g : 0.f;
+        s_part[2 * g + 1] = npix > 0.f ? m2 : 0.f;
+    }
+    cluster.sync();  // every CTA's partials are visible cluster-wide
+    if (threadIdx.x < gps) {  // CTAs -> sample, in rank order, relative to rank 0's mean
+        const int g = threadIdx.x;
+        float a = 0.f, b = 0.f;
+        const float pivot = cluster.map_shared_rank(s_part, 0)[2 * g];
+        for (int r = 0; r < kGnCS; ++r) {
+            const float* rp = cluster.map_shared_rank(s_part, r);
+            const float cnt_r = static_cast<float>(cpg) * static_cast<float>(max(min(HW, (r + 1) * rpc) - min(HW, r * rpc), 0));
+            const float d = rp[2 * g] - pivot;
+            a += cnt_r * d;
+            b += rp[2 * g + 1] + cnt_r * d * d;
+        }
+        const float cnt = static_cast<float>(cpg) * static_cast<float>(HW);
+        const float dm = a / cnt;
+        const float var = fmaxf((b - a * dm) / cnt, 0.f);
+        s_mean[g] = pivot + dm;
+        s_rstd[g] = rsqrtf(var + eps);
+        if (stats_out != nullptr && rank == 0) {
+            stats_out[(static_cast<int64_t>(n) * groups + slice * gps + g) * 2] = pivot + dm;
+            stats_out[(static_cast<int64_t>(n) * groups + slice * gps + g) * 2 + 1] = s_rstd[g];
+        }
+    }
+    cluster.barrier_arrive();  // my remote reads are done (the matching wait is at the end: nobody exits while being read)
+    __syncthreads();
+    for (int c = threadIdx.x; c < SC; c += kGnThreads) {
+        const int g = c / cpg;
+        const float sc = s_gamma[c] * s_rstd[g];
+        s_a[c] = sc;
+        s_b[c] = s_beta[c] - s_mean[g] * sc;
+    }
+    __syncthreads();
+    // ---------------- phase 2: normalise my tile out of shared memory
+    const int total = (p_end - p_begin) * SV;
+    const int step_row = kGnThreads / SV, step_col = kGnThreads % SV;
+    int walk_row = prow, walk_col = cv;
+    for (int idx = threadIdx.x; idx < total; idx += kGnThreads) {
+        const uint4 v = tile[idx];
+        const int c0 = walk_col * 8;
+        const int64_t row = static_cast<int64_t>(n) * HW + p_begin + walk_row;
+        walk_row += step_row;
+        walk_col += step_col;
+        if (walk_col >= SV) {
+            walk_col -= SV;
+            ++walk_row;
+        }
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            f[2 * k] = bf16lo(u[k]) * s_a[c0 + 2 * k] + s_b[c0 + 2 * k];
+            f[2 * k + 1] = bf16hi(u[k]) * s_a[c0 + 2 * k + 1] + s_b[c0 + 2 * k + 1];
+        }
+        if (fuse_silu) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = silu(f[k]);
+        }
+        *reinterpret_cast<uint4*>(y + row * ldy + c_base + c0) = make_uint4(
+            pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+    cluster.barrier_wait();
+}
+
 // LayerNorm: one warp normalises R rows at a time (R x VPL independent 128-bit loads in flight per lane — the rows are
 // only 640 B..2.5 KB, so memory-level parallelism, not arithmetic, sets the speed). C <= 2048, C % 8 == 0.
 template <int VPL, int R>
@@ -360,6 +542,53 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
     }
 }
 
+// Which GroupNorm kernel: IMAGD_GN_CLUSTER = 0 the chunked rendezvous kernel always; 1 the cluster kernel when the whole
+// launch is one wave of clusters (the latency-bound regime it exists for); 2 whenever a slice fits shared memory.
+static int gn_cluster_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("IMAGD_GN_CLUSTER");
+        v = e ? atoi(e) : 0;
+        if (v < 0 || v > 2) v = 0;
+    }
+    return v;
+}
+struct GnClusterPlan {
+    int gps;      // groups per slice
+    size_t smem;  // dynamic shared memory per CTA
+};
+constexpr size_t kGnClusterMaxDyn = 190 * 1024;  // + 33.5 KB static stays under the 227 KB per-CTA limit
+static bool gn_cluster_plan(int NB, int HW, int C, int groups, GnClusterPlan* plan) {
+    const int mode = gn_cluster_mode();
+    if (mode == 0) return false;
+    const int cpg = C / groups;
+    const int rpc = (HW + kGnCS - 1) / kGnCS;
+    double best = 0.0;
+    bool found = false;
+    for (int gps = 1; gps <= groups; ++gps) {
+        if (groups % gps != 0) continue;
+        const int SC = gps * cpg;
+        if (SC % 8 != 0 || SC / 8 > kGnThreads) continue;
+        const size_t tile = static_cast<size_t>(rpc) * SC * 2;
+        const size_t dyn = (3 * static_cast<size_t>(SC) * sizeof(float) + 15) / 16 * 16 + tile;
+        if (dyn > kGnClusterMaxDyn) continue;
+        const int per_sm = (dyn + 35 * 1024) * 2 <= 228 * 1024 ? 2 : 1;
+        const int64_t ctas = static_cast<int64_t>(NB) * (groups / gps) * kGnCS;
+        const int64_t slots = 144LL * per_sm;  // 18 clusters of 8 per CTA slot
+        const int64_t waves = (ctas + slots - 1) / slots;
+        if (mode == 1 && waves > 1) continue;
+        // a wave costs a fixed latency chain (~ the time 64 KB take) + its tile; rows under 128 B waste sectors
+        const double cost = static_cast<double>(waves) * (64.0 * 1024 + static_cast<double>(tile) * (SC * 2 < 128 ? 1.3 : 1.0));
+        if (!found || cost < best) {
+            best = cost;
+            plan->gps = gps;
+            plan->smem = dyn;
+            found = true;
+        }
+    }
+    return found;
+}
+
 template <int VPL, int R>
 static int launch_ln(const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int C, const float* gamma,
                      const float* beta, float eps, cudaStream_t st) {
@@ -394,6 +623,28 @@ int imagd_groupnorm_stats_bf16(const void* x, int64_t ldx, void* y, int64_t ldy,
     IMAGD_CHECK_ARG(groups > 0 && groups <= 64 && C % groups == 0, "groupnorm: groups=%d", groups);
     IMAGD_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y), "groupnorm: alignment");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GnClusterPlan plan;
+    if (gn_cluster_plan(NB, HW, C, groups, &plan)) {
+        IMAGD_SET_MAX_SMEM(groupnorm_cluster_kernel, static_cast<int>(kGnClusterMaxDyn));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(kGnCS * (groups / plan.gps), NB);
+        cfg.blockDim = dim3(kGnThreads);
+        cfg.dynamicSmemBytes = plan.smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kGnCS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        IMAGD_CUDA(cudaLaunchKernelEx(&cfg, groupnorm_cluster_kernel, reinterpret_cast<const __nv_bfloat16*>(x), ldx,
+                                      reinterpret_cast<__nv_bfloat16*>(y), ldy, HW, C, groups, plan.gps, gamma, beta, eps,
+                                      fuse_silu, stats_out));
+        return IMAGD_OK;
+    }
     const int chunks = gn_chunks(HW, NB);
     // 33 KB static + up to 20 KB dynamic (gamma | beta) exceeds the 48 KB default
     IMAGD_SET_MAX_SMEM(groupnorm_fused_kernel, 64 * 1024);

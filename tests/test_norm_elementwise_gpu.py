@@ -21,7 +21,7 @@ def _rand(shape, dev, seed, scale=1.0):
     "NB,H,W,C,silu,eps",
     [(1, 64, 64, 320, True, 1e-5), (2, 32, 32, 640, True, 1e-5), (2, 16, 16, 1920, True, 1e-5),
      (3, 8, 8, 2560, True, 1e-5), (1, 8, 8, 1280, False, 1e-6), (1, 64, 64, 960, True, 1e-5),
-     (1, 12, 9, 1280, True, 1e-5)],
+     (1, 12, 9, 1280, True, 1e-5), (2, 1, 5, 640, True, 1e-5), (2, 96, 72, 320, True, 1e-5), (4, 32, 32, 320, False, 1e-5)],
 )
 def test_groupnorm(cuda_device, NB, H, W, C, silu, eps):
     from imagdressing_b200 import ops
@@ -32,6 +32,13 @@ def test_groupnorm(cuda_device, NB, H, W, C, silu, eps):
     out = ops.groupnorm(x, gamma, beta, 32, eps, silu=silu)
     ref = ops_ref.groupnorm_ref(x, gamma, beta, 32, eps, silu)
     assert rel_l2(out, ref) < 5e-3
+    # fixed-order statistics: a second launch (and the training-mode launch that also emits {mean, rstd}) is bit-identical
+    stats = torch.empty(NB, 32, 2, device=cuda_device, dtype=torch.float32)
+    assert torch.equal(out, ops.groupnorm(x, gamma, beta, 32, eps, silu=silu))
+    assert torch.equal(out, ops.groupnorm(x, gamma, beta, 32, eps, silu=silu, stats_out=stats))
+    xg = x.float().reshape(NB, H * W, 32, C // 32)
+    assert torch.allclose(stats[..., 0], xg.mean(dim=(1, 3)), atol=2e-4, rtol=1e-4)
+    assert torch.allclose(stats[..., 1], torch.rsqrt(xg.var(dim=(1, 3), unbiased=False) + eps), rtol=1e-3)
 
 
 @pytest.mark.parametrize("NB,H,W,C,mean,std,tol", [(1, 64, 64, 320, 300.0, 4.0, 5e-3), (2, 32, 32, 640, -800.0, 16.0, 5e-3),
