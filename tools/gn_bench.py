@@ -1,6 +1,6 @@
 """GroupNorm(+SiLU) launch time over the UNet's GroupNorm shapes, per kernel choice (IMAGD_GN_CLUSTER = 0 / 1 / 2; the library
-reads the knob once, so each mode runs in its own process). CUDA events around 200 back-to-back launches per shape after a
-warm-up; prints one table and the launch-weighted total for one denoising step.
+reads the knob once, so each mode runs in its own process). CUDA events around 10 replays of a 20-launch CUDA graph per shape
+after a warm-up; prints one table and the launch-weighted total for one denoising step.
 
     python tools/gn_bench.py [--batch 1]
 """
@@ -27,13 +27,20 @@ def child(batch: int) -> None:
     for H, W, C, n in SHAPES:
         x = torch.randn(NB, H, W, C, device=dev).bfloat16()
         gamma, beta = torch.ones(C, device=dev), torch.zeros(C, device=dev)
-        for _ in range(20):
-            ops.groupnorm(x, gamma, beta, 32, 1e-5, silu=True)
+        out = torch.empty_like(x)
+        for _ in range(5):
+            ops.groupnorm(x, gamma, beta, 32, 1e-5, silu=True, out=out)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()  # 20 launches per replay: the python call (~11 us) would hide the kernel otherwise
+        with torch.cuda.graph(graph):
+            for _ in range(20):
+                ops.groupnorm(x, gamma, beta, 32, 1e-5, silu=True, out=out)
+        graph.replay()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(200):
-            ops.groupnorm(x, gamma, beta, 32, 1e-5, silu=True)
+        for _ in range(10):
+            graph.replay()
         b.record()
         torch.cuda.synchronize()
         us = a.elapsed_time(b) * 1000.0 / 200
@@ -50,9 +57,9 @@ if __name__ == "__main__":
     if os.environ.get("GN_BENCH_CHILD"):
         child(batch)
     else:
-        for mode in ("0", "1", "2"):
-            print(f"IMAGD_GN_CLUSTER={mode} (batch {batch})", flush=True)
-            env = dict(os.environ, IMAGD_GN_CLUSTER=mode, GN_BENCH_CHILD="1")
+        for mode, blk in (("0", "1"), ("1", "0"), ("1", "1"), ("2", "1")):
+            print(f"IMAGD_GN_CLUSTER={mode} IMAGD_GN_BULK={blk} (batch {batch})", flush=True)
+            env = dict(os.environ, IMAGD_GN_CLUSTER=mode, IMAGD_GN_BULK=blk, GN_BENCH_CHILD="1")
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--batch", str(batch)], env=env, capture_output=True,
                                text=True, timeout=300)
             print(r.stdout + (r.stderr[-600:] if r.returncode else ""), flush=True)
