@@ -284,7 +284,7 @@ constexpr int kGnCS = 8;  // portable cluster size
 __global__ void __launch_bounds__(kGnThreads, 2) groupnorm_cluster_kernel(
     const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y, int64_t ldy, int HW, int C,
     int groups, int gps, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int fuse_silu,
-    float* __restrict__ stats_out, int bulk) {
+    float* __restrict__ stats_out) {
     pdl_launch_dependents();
     pdl_wait();
     namespace cg = cooperative_groups;
@@ -292,7 +292,6 @@ __global__ void __launch_bounds__(kGnThreads, 2) groupnorm_cluster_kernel(
     __shared__ float s_a[kGnThreads * 8];  // phase 1: per (row slot, channel) sums      | phase 2: per-channel scale
     __shared__ float s_b[kGnThreads * 8];  // phase 1: per (row slot, channel) sum of sq | phase 2: per-channel shift
     __shared__ float s_part[64 * 2];       // my {mean, M2} per group of the slice: what the other CTAs of the cluster read
-    __shared__ __align__(8) uint64_t s_bar;
     __shared__ float s_mean[64];
     __shared__ float s_rstd[64];
     extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -317,29 +316,13 @@ __global__ void __launch_bounds__(kGnThreads, 2) groupnorm_cluster_kernel(
     const int cv = threadIdx.x % SV;
     const int prow = threadIdx.x / SV;
     const int rows = kGnThreads / SV;  // row slots (>= 1: SC <= kGnMaxC)
-    const int nrows = p_end - p_begin;
-    if (bulk) {
-        // one bulk copy per row piece (SC * 2 bytes, 16-byte aligned), all in flight at once on one mbarrier: the load phase
-        // runs at the memory system's pace instead of 4 x 16 bytes per thread and round trip
-        if (threadIdx.x == 0) {
-            mbar_init(&s_bar, 1);
-            fence_barrier_init();
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) mbar_arrive_expect_tx(&s_bar, static_cast<uint32_t>(nrows) * SC * 2);
-        __syncthreads();
-        const __nv_bfloat16* src = x + (static_cast<int64_t>(n) * HW + p_begin) * ldx + c_base;
-        for (int r = threadIdx.x; r < nrows; r += kGnThreads)
-            bulk_load_g2s(smem_u32(tile + r * SV), src + static_cast<int64_t>(r) * ldx, SC * 2, &s_bar);
-        mbar_wait(&s_bar, 0);
-    }
     if (prow < rows) {
         float sum[8], sq[8], piv[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) sum[k] = sq[k] = piv[k] = 0.f;
         const __nv_bfloat16* base = x + (static_cast<int64_t>(n) * HW) * ldx + c_base + cv * 8;
         if (p_begin < p_end) {
-            const uint4 pv = bulk ? tile[cv] : __ldg(reinterpret_cast<const uint4*>(base + static_cast<int64_t>(p_begin) * ldx));
+            const uint4 pv = __ldg(reinterpret_cast<const uint4*>(base + static_cast<int64_t>(p_begin) * ldx));
             const uint32_t u[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -359,14 +342,13 @@ __global__ void __launch_bounds__(kGnThreads, 2) groupnorm_cluster_kernel(
                 v[t] = make_uint4(0u, 0u, 0u, 0u);
                 live[t] = 0.f;
                 if (pix + t * rows < p_end) {
-                    v[t] = bulk ? tile[(pix + t * rows - p_begin) * SV + cv]
-                                : __ldg(reinterpret_cast<const uint4*>(base + static_cast<int64_t>(pix + t * rows) * ldx));
+                    v[t] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<int64_t>(pix + t * rows) * ldx));
                     live[t] = 1.f;
                 }
             }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                if (!bulk && pix + t * rows < p_end) tile[(pix + t * rows - p_begin) * SV + cv] = v[t];
+                if (pix + t * rows < p_end) tile[(pix + t * rows - p_begin) * SV + cv] = v[t];
                 const uint32_t u[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -560,22 +542,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
     }
 }
 
-// Which GroupNorm kernel: IMAGD_GN_CLUSTER = 0 the chunked rendezvous kernel always; 1 the cluster kernel when the whole
-// launch is one wave of clusters (the latency-bound regime it exists for); 2 whenever a slice fits shared memory.
+// Which GroupNorm kernel: IMAGD_GN_CLUSTER = 0 the chunked rendezvous kernel always; 1 (default) the cluster kernel in the
+// latency-bound regime it exists for — the whole launch is one wave of clusters and a CTA's tile is at most 32 KB; 2 whenever
+// a slice fits shared memory. Measured on the UNet's shapes at batch 1 (profiles/r02_call29_gn_cluster_bulk.txt, graph-replayed
+// launches): tiles <= 30 KB 8-12 us against 9-21 us for the rendezvous kernel (C = 2560: 8.8 vs 21.3 us); 41 KB tiles mixed
+// (64x64x320 13.5 vs 11.5 us); the 123 KB tile of 64x64x960 29 vs 19 us — hence the cap. Replayed B=1 step 5.54 -> 5.34 ms.
 static int gn_cluster_mode() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("IMAGD_GN_CLUSTER");
-        v = e ? atoi(e) : 0;
-        if (v < 0 || v > 2) v = 0;
-    }
-    return v;
-}
-static int gn_cluster_bulk() {  // IMAGD_GN_BULK: row pieces arrive by cp.async.bulk (1) or by per-thread 128-bit loads (0)
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("IMAGD_GN_BULK");
-        v = e ? (atoi(e) != 0) : 1;
+        v = e ? atoi(e) : 1;
+        if (v < 0 || v > 2) v = 1;
     }
     return v;
 }
@@ -602,7 +579,7 @@ static bool gn_cluster_plan(int NB, int HW, int C, int groups, GnClusterPlan* pl
         const int64_t ctas = static_cast<int64_t>(NB) * (groups / gps) * kGnCS;
         const int64_t slots = 144LL * per_sm;  // 18 clusters of 8 per CTA slot
         const int64_t waves = (ctas + slots - 1) / slots;
-        if (mode == 1 && waves > 1) continue;
+        if (mode == 1 && (waves > 1 || tile > 32 * 1024)) continue;
         // a wave costs a fixed latency chain (~ the time 64 KB take) + its tile; rows under 128 B waste sectors
         const double cost = static_cast<double>(waves) * (64.0 * 1024 + static_cast<double>(tile) * (SC * 2 < 128 ? 1.3 : 1.0));
         if (!found || cost < best) {
@@ -668,7 +645,7 @@ int imagd_groupnorm_stats_bf16(const void* x, int64_t ldx, void* y, int64_t ldy,
         cfg.numAttrs = pdl_enabled() ? 2 : 1;
         IMAGD_CUDA(cudaLaunchKernelEx(&cfg, groupnorm_cluster_kernel, reinterpret_cast<const __nv_bfloat16*>(x), ldx,
                                       reinterpret_cast<__nv_bfloat16*>(y), ldy, HW, C, groups, plan.gps, gamma, beta, eps,
-                                      fuse_silu, stats_out, gn_cluster_bulk()));
+                                      fuse_silu, stats_out));
         return IMAGD_OK;
     }
     const int chunks = gn_chunks(HW, NB);

@@ -57,9 +57,9 @@ if __name__ == "__main__":
     if os.environ.get("GN_BENCH_CHILD"):
         child(batch)
     else:
-        for mode, blk in (("0", "1"), ("1", "0"), ("1", "1"), ("2", "1")):
-            print(f"IMAGD_GN_CLUSTER={mode} IMAGD_GN_BULK={blk} (batch {batch})", flush=True)
-            env = dict(os.environ, IMAGD_GN_CLUSTER=mode, IMAGD_GN_BULK=blk, GN_BENCH_CHILD="1")
+        for mode in ("0", "1", "2"):
+            print(f"IMAGD_GN_CLUSTER={mode} (batch {batch})", flush=True)
+            env = dict(os.environ, IMAGD_GN_CLUSTER=mode, GN_BENCH_CHILD="1")
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--batch", str(batch)], env=env, capture_output=True,
                                text=True, timeout=300)
             print(r.stdout + (r.stderr[-600:] if r.returncode else ""), flush=True)
