@@ -565,6 +565,9 @@ static bool gn_cluster_plan(int NB, int HW, int C, int groups, GnClusterPlan* pl
     const int mode = gn_cluster_mode();
     if (mode == 0) return false;
     const int cpg = C / groups;
+    // mode 1 keeps to the group widths of the UNet / ControlNet family (10..80 channels), where the kernel was measured and
+    // swept on the GPU; narrower groups (VAE: 4..16 channels, 8..32-byte row pieces per slice) stay on the rendezvous kernel
+    if (mode == 1 && cpg < 10) return false;
     const int rpc = (HW + kGnCS - 1) / kGnCS;
     double best = 0.0;
     bool found = false;
